@@ -1,0 +1,186 @@
+/* vcgpu.h — C-ABI of the B200 calibration-solve library (libvcgpu.so).
+ *
+ * Drop-in boundary for the path that sits behind `ceres::Solve` in the reference:
+ * it replaces ceres::Problem construction + ceres::Solve + Problem::Evaluate as used by
+ * ViCalibrator (include/vicalib/vicalibrator.h:152, 548-679, 859-916, 956-971).  Plain
+ * pointers and sizes only; every entry point returns 0 on success and a negative code on
+ * error (message via vcgpu_last_error); nothing throws or aborts across this boundary.
+ *
+ * All arithmetic is FP64.  Quaternions are (x, y, z, w); SE3 is [q(4) | t(3)], the storage
+ * the reference's parameter blocks use (local-param-se3.h:34, vicalibrator.h:460-461).
+ */
+#ifndef VCGPU_H_
+#define VCGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vcgpu_handle vcgpu_handle;
+
+/* camera model ids; intrinsics are fu, fv, u0, v0, <distortion...> (vicalib-engine.cc:205-250) */
+enum {
+  VCGPU_CAM_LINEAR = 0, /* K=4  calibu_fu_fv_u0_v0         vicalibrator.h:448 */
+  VCGPU_CAM_FOV = 1,    /* K=5  calibu_fu_fv_u0_v0_w       vicalibrator.h:412 */
+  VCGPU_CAM_POLY2 = 2,  /* K=6  calibu_fu_fv_u0_v0_k1_k2   vicalibrator.h:419 */
+  VCGPU_CAM_POLY3 = 3,  /* K=7  ..._k1_k2_k3               vicalibrator.h:427 */
+  VCGPU_CAM_KB4 = 4     /* K=8  calibu_fu_fv_u0_v0_kb4     vicalibrator.h:441 */
+};
+#define VCGPU_MAX_INTR 10 /* stride of the intrinsics array per camera */
+
+enum {
+  VCGPU_OK = 0,
+  VCGPU_ERR_INVALID = -1,  /* bad argument / call order (reference: glog CHECK, vicalibrator.h:254,356,396) */
+  VCGPU_ERR_CUDA = -2,     /* CUDA runtime failure (no CPU fallback exists) */
+  VCGPU_ERR_NUMERIC = -3,  /* normal equations not positive definite even after damping */
+  VCGPU_ERR_COMM = -4      /* NCCL failure */
+};
+
+typedef struct {
+  int device; /* CUDA device ordinal, -1 = current device */
+} vcgpu_config;
+
+/* Which parameter blocks are variable — ViCalibrator::SetupProblem's constant masks
+ * (vicalibrator.h:572-592, 651-676) and SetOptimizationFlags (vicalibrator.h:252-260). */
+typedef struct {
+  int inertial;         /* is_inertial_active_ && FLAGS_calibrate_imu: IMU residuals on, cam0 q_ck variable */
+  int rotation_only;    /* optimize_rotation_only_: IMU residual rows 0-2,6-8 zeroed, gravity & cam0 p_ck constant */
+  int bias_active;      /* is_bias_active_ */
+  int scale_active;     /* is_scale_factor_active_ */
+  int optimize_ts;      /* optimize_time_offset_ */
+  int fix_intrinsics;   /* fix_intrinsics_ (vicalibrator.h:346,591) */
+  int visual;           /* is_visual_active_ */
+  double visual_mult;   /* residual-block multiplicity of the staged flow (vicalibrator.h:641-656 re-adds blocks) */
+  double imu_mult;
+} vcgpu_flags;
+
+/* ceres::Solver::Options as ViCalibrator sets them (vicalibrator.h:141-152) */
+typedef struct {
+  int max_iters;           /* FLAGS_max_iters, default 200 (vicalib-engine.cc:94) */
+  double function_tol;     /* 1e-6 (vicalibrator.h:149) */
+  double gradient_tol;     /* Ceres default 1e-10 */
+  double param_tol;        /* Ceres default 1e-8 */
+  double init_radius;      /* Ceres default 1e4 */
+  int strategy;            /* 0 = LEVENBERG_MARQUARDT, 1 = DOGLEG (vicalibrator.h:151) */
+  int jacobi_scaling;      /* Ceres default on */
+  int update_imu_weights;  /* run UpdateImuWeights before the solve and after every iteration (vicalibrator.h:691,955) */
+  int update_state_every_iteration; /* copy the state to the host mirrors before each callback (vicalibrator.h:148) */
+} vcgpu_options;
+
+/* ceres::IterationSummary fields the reference's callback reads (vicalibrator.h:696-714) */
+typedef struct {
+  int iteration;
+  int step_is_successful;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double gradient_norm;
+  double step_norm;
+  double relative_decrease;
+  double trust_region_radius;
+} vcgpu_iteration;
+
+/* return nonzero to stop (ceres::SOLVER_TERMINATE_SUCCESSFULLY, vicalibrator.h:717) */
+typedef int (*vcgpu_iter_cb)(const vcgpu_iteration* it, void* user);
+
+enum {
+  VCGPU_TERM_NO_CONVERGENCE = 0, /* max iterations */
+  VCGPU_TERM_FUNCTION_TOL = 1,
+  VCGPU_TERM_GRADIENT_TOL = 2,
+  VCGPU_TERM_PARAM_TOL = 3,
+  VCGPU_TERM_CALLBACK = 4,       /* callback asked to stop, or gradient norm < 1e-9 rule (vicalibrator.h:713-717) */
+  VCGPU_TERM_RADIUS = 5
+};
+
+/* ceres::Solver::Summary subset (vicalibrator.h:975-976) */
+typedef struct {
+  int iterations;
+  int successful_steps;
+  int termination;
+  int num_residuals;
+  double initial_cost;
+  double final_cost;
+  double device_seconds; /* CUDA-event time of the iteration loop */
+  int kernel_launches;   /* kernels this library launched during the solve */
+} vcgpu_summary;
+
+int vcgpu_create(const vcgpu_config* cfg, vcgpu_handle** out);
+int vcgpu_destroy(vcgpu_handle* h);
+const char* vcgpu_last_error(const vcgpu_handle* h);
+
+/* ---- problem upload (host buffers are copied; caller keeps ownership) --------------------
+ * replaces AddParameterBlock / AddResidualBlock (vicalibrator.h:559-604, 628-632, 645-654) */
+int vcgpu_set_cameras(vcgpu_handle* h, int n_cams, const int32_t* model, const double* intr /*n*10*/,
+                      const double* q_ck /*n*4*/, const double* p_ck /*n*3*/);
+int vcgpu_set_frames(vcgpu_handle* h, int n_frames, const double* T_wp /*n*7*/, const double* v_w /*n*3*/,
+                     const double* time /*n*/);
+/* any order; the library groups by (camera, frame) internally and keeps the caller's order for outputs */
+int vcgpu_set_observations(vcgpu_handle* h, int64_t n_obs, const int32_t* frame_id, const int32_t* cam_id,
+                           const double* p_w /*n*3*/, const double* p_c /*n*2*/);
+/* strictly increasing timestamps (vicalibrator.h:373-378) */
+int vcgpu_set_imu(vcgpu_handle* h, int n, const double* t, const double* w /*n*3*/, const double* a /*n*3*/,
+                  double sigma_g, double sigma_a);
+int vcgpu_set_imu_params(vcgpu_handle* h, const double g[2], const double b[6], const double sf[6], double ts);
+int vcgpu_set_flags(vcgpu_handle* h, const vcgpu_flags* flags);
+int vcgpu_set_options(vcgpu_handle* h, const vcgpu_options* opts);
+void vcgpu_default_flags(vcgpu_flags* flags);
+void vcgpu_default_options(vcgpu_options* opts);
+
+/* host mirrors updated before every callback when update_state_every_iteration is set, and at
+ * the end of vcgpu_solve; any pointer may be NULL (vicalibrator.h:148: the GUI thread polls them) */
+int vcgpu_register_mirrors(vcgpu_handle* h, double* intr, double* q_ck, double* p_ck, double* T_wp,
+                           double* v_w, double* g, double* b, double* sf, double* ts);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* ceres::Solve(solver_options_, problem_, &summary)  (vicalibrator.h:956) */
+int vcgpu_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out);
+/* run exactly n trust-region iterations with no convergence test and no host round trip per
+ * iteration (benchmark entry: LM iterations / second) */
+int vcgpu_iterate(vcgpu_handle* h, int n_iterations, vcgpu_summary* out);
+
+/* Problem::Evaluate with residual_blocks = camera `cam` (or all visual blocks if cam < 0),
+ * apply_loss_function = false: cost = 1/2 sum |r|^2, residuals in caller observation order
+ * (2 per active observation of that camera)  (vicalibrator.h:873-887, 958-966) */
+int vcgpu_evaluate(vcgpu_handle* h, int cam, double* cost, double* residuals_or_null, int64_t* n_blocks);
+/* total robustified cost 1/2 sum rho(|r|^2) over all active residual blocks at the current state */
+int vcgpu_cost(vcgpu_handle* h, double* cost);
+/* RemoveOutliers (vicalibrator.h:859-916): drops observations with |r| > threshold * rmse[cam] */
+int vcgpu_remove_outliers(vcgpu_handle* h, const double* rmse, double threshold, int64_t* n_removed);
+int vcgpu_get_obs_active(vcgpu_handle* h, uint8_t* active /*n_obs, caller order*/);
+/* UpdateImuWeights (vicalibrator.h:723-799) */
+int vcgpu_update_imu_weights(vcgpu_handle* h);
+int vcgpu_get_imu_weights(vcgpu_handle* h, double* w_sqrt /*(n_frames-1)*81*/);
+int vcgpu_set_imu_weights(vcgpu_handle* h, const double* w_sqrt);
+
+int vcgpu_get_state(vcgpu_handle* h, double* intr, double* q_ck, double* p_ck, double* T_wp, double* v_w,
+                    double* g, double* b, double* sf, double* ts);
+int vcgpu_num_residuals(vcgpu_handle* h, int* out);
+int vcgpu_frame_dim(vcgpu_handle* h, int* out);   /* 6, or 9 with inertial terms */
+int vcgpu_num_globals(vcgpu_handle* h, int* out); /* sum_c (6 + K_c) (+15 with inertial terms) */
+
+/* ---- inspection hooks used by the parity tests (what AutoDiffCostFunction::Evaluate and the
+ * normal-equation build produce inside Ceres) ------------------------------------------------ */
+/* loss-free residuals and tangent-space Jacobians per observation, caller order.
+ * J: n_obs * 2 * 22, row-major 2 x (6 pose | 3 w_ck | 3 p_ck | K), zero padded to 22 columns. */
+int vcgpu_eval_reproj(vcgpu_handle* h, double* r /*n*2*/, double* J_or_null);
+/* per IMU interval: r 9, J 9 x 33 = (pose2 6 | pose1 6 | v2 3 | v1 3 | g 2 | b 6 | sf 6 | ts 1) */
+int vcgpu_eval_imu(vcgpu_handle* h, double* r /*(n_frames-1)*9*/, double* J_or_null);
+/* block normal equations at the current state: B nf*fd*fd, U nf*fd*fd (U[f] = H[f-1,f]),
+ * E nf*fd*G, gf nf*fd, C G*G, gc G; any may be NULL */
+int vcgpu_normal_equations(vcgpu_handle* h, double* B, double* U, double* E, double* gf, double* C,
+                           double* gc, double* cost);
+/* one damped solve (H*scale^2 + diag(D2)) x = -g*scale with the device arrow solver */
+int vcgpu_solve_arrow(vcgpu_handle* h, const double* scale, const double* D2, double* x);
+
+/* ---- multi-GPU: one process per GPU, frames sharded contiguously, one NCCL all-reduce of the
+ * reduced normal equations per iteration ---------------------------------------------------- */
+#define VCGPU_UNIQUE_ID_BYTES 128
+int vcgpu_comm_unique_id(uint8_t id[VCGPU_UNIQUE_ID_BYTES]);
+int vcgpu_comm_init(vcgpu_handle* h, const uint8_t id[VCGPU_UNIQUE_ID_BYTES], int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCGPU_H_ */

@@ -1,0 +1,106 @@
+// Internal declarations shared by the .cu translation units of libvcgpu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vcgpu.h"
+
+namespace vc {
+
+constexpr int kMaxCams = 8;
+constexpr int kCamStateStride = 17;  // q_ck(4) p_ck(3) intr(10)
+constexpr int kImuStateSize = 15;    // g2 b6 sf6 ts1
+constexpr int kMaxW = 21;            // 6 pose + (6 + K<=8) globals + residual column
+constexpr int kCgStride = 120;       // per-group packed global block: sym (6+K)^2 (<=105) + gradient (<=14)
+constexpr int kReduceBlocks = 64;    // level-1 partials of the global-block reduction
+
+struct CamInfo {
+  int model, K;
+  int goff;         // offset of [w_ck p_ck intr] in the global tangent vector
+  int obs_start;    // first sorted observation of this camera
+  int n_obs;
+  int group_start;  // first (cam, frame) group
+  int n_groups;
+  int64_t joff;     // offset (doubles) of this camera's Jacobian columns in d_J
+};
+
+// device-resident description handed to kernels by value
+struct DevProblem {
+  int n_cams, n_frames, fd, G, imu_goff;
+  int inertial, rotation_only;
+  double visual_mult, imu_mult;
+  CamInfo cams[kMaxCams];
+  // state layout (doubles): T_wp 7*nf | v_w 3*nf | cams 17*nc | imu 15
+  int64_t off_v, off_cam, off_imu, state_size;
+};
+
+struct Blocks {  // block normal equations (device pointers)
+  double *B, *U, *E, *gf, *C, *gc, *cost;
+};
+
+}  // namespace vc
+
+struct vcgpu_handle {
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long launches = 0;
+
+  // ---- host copies of the problem
+  int n_cams = 0, n_frames = 0;
+  int64_t n_obs_all = 0;  // as given by the caller
+  std::vector<int32_t> h_model;
+  std::vector<double> h_intr, h_qck, h_pck, h_T, h_v, h_time;
+  std::vector<int32_t> h_obs_frame, h_obs_cam;
+  std::vector<double> h_pw, h_pc;
+  std::vector<uint8_t> h_active;
+  std::vector<double> h_imu_t, h_imu_w, h_imu_a;
+  double sigma_g = 5.3088444e-5, sigma_a = 0.001883649;
+  double h_g[2] = {0, 0}, h_b[6] = {0, 0, 0, 0, 0, 0}, h_sf[6] = {1, 1, 1, 1, 1, 1}, h_ts = 0;
+  vcgpu_flags flags;
+  vcgpu_options opts;
+  double* mirror[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+  // ---- derived (rebuilt by prepare())
+  bool dirty = true;        // structure changed: re-sort / re-allocate
+  bool state_dirty = true;  // host state changed: re-upload
+  vc::DevProblem dp;
+  int64_t n_obs = 0;               // active observations (sorted order)
+  std::vector<int64_t> perm;       // sorted index -> caller index
+  int n_groups = 0;
+  int cur = 0;                     // which of the double buffers holds the accepted point
+  bool blocks_valid = false;
+
+  // ---- device memory
+  double* d_state[2] = {nullptr, nullptr};
+  double* d_obs = nullptr;        // SoA [5][n_obs]: pw.x pw.y pw.z pc.u pc.v
+  int32_t* d_obs_frame = nullptr;
+  int32_t *d_grp_start = nullptr, *d_grp_count = nullptr, *d_group_of = nullptr;
+  double* d_mask = nullptr;       // [G] 0/1 per global tangent column
+  double* d_r = nullptr;          // [2][n_obs] loss-corrected residuals
+  double* d_J = nullptr;          // per camera: [2*(12+K)][n_obs_cam] column SoA, loss-corrected
+  double* d_cost_part = nullptr;  // per eval block partial costs
+  int n_cost_part = 0;
+  double* d_Cg = nullptr;         // [n_groups][kCgStride]
+  double* d_Cpart = nullptr;      // [kReduceBlocks][G*G+G]
+  vc::Blocks blk[2];
+  double* d_blk_mem[2] = {nullptr, nullptr};
+  double* d_scale = nullptr;      // Jacobi scaling [nf*fd+G]
+  double* d_X = nullptr;          // [nf][fd][G+1]
+  double* d_Spart = nullptr;      // [solve blocks][G*G+G]
+  int n_solve_blocks = 0;
+  double* d_delta = nullptr;      // [nf*fd+G] scaled step
+  double* d_red = nullptr;        // small reduction scratch
+  double* d_scalars = nullptr;    // device scalars (see vcgpu.cu)
+  double* h_scalars = nullptr;    // pinned mirror
+  // IMU
+  double* d_imu = nullptr;        // [7][n_imu]: t w3 a3
+  int n_imu = 0;
+  double* d_wsqrt = nullptr;      // [(nf-1)][81]
+  double* d_imu_r = nullptr;      // [(nf-1)][9]
+  double* d_imu_J = nullptr;      // [(nf-1)][9*33]
+};

@@ -1,0 +1,647 @@
+// CUDA kernels of the calibration solve (sm_100a, FP64).
+//
+// Per LM iteration (vision terms):
+//   eval_reproj_kernel   one thread per grid corner: SE3 pose chain + camera model + analytic
+//                        Jacobian + SoftLOne corrector; residuals/Jacobian columns stored SoA so
+//                        every store instruction of a warp is one contiguous 256 B segment
+//   build_frames_kernel  one CTA per frame: stages the frame's Jacobian tile in shared memory and
+//                        forms the block normal equations [Jf Jg r]^T [Jf Jg r]
+//   reduce_globals_*     deterministic two-level tree for the per-camera global blocks + cost
+//   frame_solve_kernel   per-frame 6x6 Cholesky + Schur contribution E^T B^-1 E
+//   global_solve_kernel  dense Cholesky of the reduced (globals) system
+//   backsub_update_kernel back-substitution + x (+) delta into the trial state
+// The reference does all of this inside ceres::Solve (vicalibrator.h:956).
+#pragma once
+#include "vc_internal.h"
+#include "vc_math.cuh"
+
+namespace vc {
+
+// ---------------------------------------------------------------- reprojection evaluate
+struct EvalArgs {
+  const double* state;     // frame poses at state[7*f]
+  const double* cam;       // this camera's 17 state doubles
+  const int32_t* frame;    // per observation (camera-local arrays from here on)
+  const double *pwx, *pwy, *pwz, *pcu, *pcv;
+  const double* mask;      // 6+K column mask (w_ck, p_ck, intr)
+  double *r0, *r1;
+  double* J;               // column c at J + c*n
+  double* cost_part;       // one per block
+  int n;
+  int apply_loss;          // 1: SoftLOne corrector + robust cost; 0: raw residuals, cost 1/2|r|^2
+  double mult;
+};
+
+template <int MODEL, bool JAC>
+__global__ void __launch_bounds__(256) eval_reproj_kernel(EvalArgs a) {
+  constexpr int K = Cam<MODEL>::K, NT = 12 + K;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double cost = 0.0;
+  if (i < a.n) {
+    const double* T = a.state + 7 * static_cast<int64_t>(a.frame[i]);
+    const Q4 q{T[0], T[1], T[2], T[3]};
+    const V3 t{T[4], T[5], T[6]};
+    const V3 pw{a.pwx[i], a.pwy[i], a.pwz[i]};
+    const V3 pk = qrot(qconj(q), pw - t);  // T_wk^-1 * p_w
+    const Q4 qc{a.cam[0], a.cam[1], a.cam[2], a.cam[3]};
+    double R[9];
+    qmat(qc, R);
+    const V3 pc = mat_mul(R, pk) + V3{a.cam[4], a.cam[5], a.cam[6]};
+    double z[2], dzp[6], dzi[2 * K];
+    Cam<MODEL>::project(pc, a.cam + 7, z, JAC ? dzp : nullptr, JAC ? dzi : nullptr);
+    double r0 = z[0] - a.pcu[i], r1 = z[1] - a.pcv[i];
+    const double s = r0 * r0 + r1 * r1;
+    double sc = 1.0;
+    if (a.apply_loss) {
+      double rho0, rho1;
+      soft_l_one(s, &rho0, &rho1);
+      cost = 0.5 * rho0 * a.mult;
+      sc = sqrt(rho1);  // Ceres corrector for rho'' <= 0: scale residual and Jacobian by sqrt(rho')
+    } else {
+      cost = 0.5 * s;
+    }
+    a.r0[i] = r0 * sc;
+    a.r1[i] = r1 * sc;
+    if (JAC) {
+      const int64_t n = a.n;
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        const double* d = dzp + 3 * row;
+        // M = dz/dpc * R_ck
+        const double m0 = d[0] * R[0] + d[1] * R[3] + d[2] * R[6];
+        const double m1 = d[0] * R[1] + d[1] * R[4] + d[2] * R[7];
+        const double m2 = d[0] * R[2] + d[1] * R[5] + d[2] * R[8];
+        // M [pk]x
+        const double w0 = m1 * pk.z - m2 * pk.y;
+        const double w1 = m2 * pk.x - m0 * pk.z;
+        const double w2 = m0 * pk.y - m1 * pk.x;
+        double* Jc = a.J + static_cast<int64_t>(row * NT) * n + i;
+        Jc[0 * n] = -m0 * sc;
+        Jc[1 * n] = -m1 * sc;
+        Jc[2 * n] = -m2 * sc;
+        Jc[3 * n] = w0 * sc;
+        Jc[4 * n] = w1 * sc;
+        Jc[5 * n] = w2 * sc;
+        Jc[6 * n] = -w0 * sc * a.mask[0];
+        Jc[7 * n] = -w1 * sc * a.mask[1];
+        Jc[8 * n] = -w2 * sc * a.mask[2];
+        Jc[9 * n] = d[0] * sc * a.mask[3];
+        Jc[10 * n] = d[1] * sc * a.mask[4];
+        Jc[11 * n] = d[2] * sc * a.mask[5];
+#pragma unroll
+        for (int k = 0; k < K; ++k) Jc[(12 + k) * n] = dzi[row * K + k] * sc * a.mask[6 + k];
+      }
+    }
+  }
+  // deterministic block reduction of the cost
+  __shared__ double wsum[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cost += __shfl_down_sync(0xffffffffu, cost, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cost;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += wsum[w];
+    a.cost_part[blockIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------- per-frame block build
+struct BuildArgs {
+  DevProblem dp;
+  const int32_t *grp_start, *grp_count, *group_of;
+  const double* r;   // [2][n_obs]
+  const double* J;
+  int64_t n_obs;
+  Blocks out;
+  double* Cg;
+};
+
+constexpr int kBuildThreads = 128;
+constexpr int kBuildChunk = 128;  // observations staged per pass
+
+template <int FD>
+__global__ void __launch_bounds__(kBuildThreads) build_frames_kernel(BuildArgs a) {
+  extern __shared__ double smem[];
+  double* tile = smem;                              // [2*kBuildChunk][W]
+  double* smB = smem + 2 * kBuildChunk * kMaxW;     // [FD*FD]
+  double* smg = smB + FD * FD;                      // [FD]
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const int G = a.dp.G, nf = a.dp.n_frames;
+  for (int k = tid; k < FD * FD + FD; k += kBuildThreads) smB[k] = 0.0;
+  double* Ef = a.out.E + static_cast<int64_t>(f) * FD * G;
+  for (int k = tid; k < FD * G; k += kBuildThreads) Ef[k] = 0.0;
+  // entry decode (independent of W): e -> (i >= j)
+  int ei[2], ej[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int e = tid + s * kBuildThreads;
+    int i = static_cast<int>((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+    while (i * (i + 1) / 2 > e) --i;
+    ei[s] = i;
+    ej[s] = e - i * (i + 1) / 2;
+  }
+  __syncthreads();
+  for (int c = 0; c < a.dp.n_cams; ++c) {
+    const int g = a.group_of[c * nf + f];
+    if (g < 0) continue;
+    const CamInfo& ci = a.dp.cams[c];
+    const int NT = 12 + ci.K, W = NT + 1, ntri = W * (W + 1) / 2;
+    const int start = a.grp_start[g], cnt = a.grp_count[g];  // start is a sorted (global) index
+    const int64_t nc = ci.n_obs;
+    const double* Jc = a.J + ci.joff + (start - ci.obs_start);
+    double acc[2] = {0.0, 0.0};
+    for (int ch = 0; ch < cnt; ch += kBuildChunk) {
+      const int m = min(kBuildChunk, cnt - ch);
+      for (int col = 0; col < 2 * NT; ++col) {
+        const int row = col / NT, k = col - row * NT;
+        const double* src = Jc + col * nc + ch;
+        for (int li = tid; li < m; li += kBuildThreads) tile[(2 * li + row) * W + k] = src[li];
+      }
+      for (int li = tid; li < m; li += kBuildThreads) {
+        tile[(2 * li) * W + NT] = a.r[start + ch + li];
+        tile[(2 * li + 1) * W + NT] = a.r[a.n_obs + start + ch + li];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (tid + s * kBuildThreads < ntri) {
+          const int i = ei[s], j = ej[s];
+          double sum = 0.0;
+          for (int row = 0; row < 2 * m; ++row) sum += tile[row * W + i] * tile[row * W + j];
+          acc[s] += sum;
+        }
+      }
+      __syncthreads();
+    }
+    double* Cgg = a.Cg + static_cast<int64_t>(g) * kCgStride;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (tid + s * kBuildThreads >= ntri) continue;
+      const int i = ei[s], j = ej[s];
+      const double v = acc[s] * a.dp.visual_mult;
+      if (i < 6) {
+        smB[i * FD + j] += v;
+        if (i != j) smB[j * FD + i] += v;
+      } else if (i < W - 1) {
+        if (j < 6) Ef[j * G + ci.goff + (i - 6)] = v;
+        else Cgg[(i - 6) * (i - 5) / 2 + (j - 6)] = v;
+      } else {
+        if (j < 6) smg[j] += v;
+        else if (j < W - 1) Cgg[105 + (j - 6)] = v;
+      }
+    }
+  }
+  __syncthreads();
+  double* Bf = a.out.B + static_cast<int64_t>(f) * FD * FD;
+  for (int k = tid; k < FD * FD; k += kBuildThreads) Bf[k] = smB[k];
+  for (int k = tid; k < FD; k += kBuildThreads) a.out.gf[static_cast<int64_t>(f) * FD + k] = smg[k];
+}
+
+// ---------------------------------------------------------------- global blocks: level 1
+struct ReduceArgs {
+  DevProblem dp;
+  const double* Cg;
+  double* Cpart;  // [kReduceBlocks][G*G+G]
+};
+__global__ void __launch_bounds__(256) reduce_globals_kernel(ReduceArgs a) {
+  extern __shared__ double acc[];
+  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G;
+  for (int k = tid; k < NS; k += blockDim.x) acc[k] = 0.0;
+  __syncthreads();
+  for (int c = 0; c < a.dp.n_cams; ++c) {
+    const CamInfo& ci = a.dp.cams[c];
+    const int NG = 6 + ci.K, nsym = NG * (NG + 1) / 2;
+    const int lo = static_cast<int>(static_cast<int64_t>(ci.n_groups) * blockIdx.x / gridDim.x);
+    const int hi = static_cast<int>(static_cast<int64_t>(ci.n_groups) * (blockIdx.x + 1) / gridDim.x);
+    for (int e = tid; e < nsym + NG; e += blockDim.x) {
+      int src, dst, dst2 = -1;
+      if (e < nsym) {
+        int i = static_cast<int>((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        while (i * (i + 1) / 2 > e) --i;
+        const int j = e - i * (i + 1) / 2;
+        src = e;
+        dst = (ci.goff + i) * G + ci.goff + j;
+        if (i != j) dst2 = (ci.goff + j) * G + ci.goff + i;
+      } else {
+        src = 105 + (e - nsym);
+        dst = G * G + ci.goff + (e - nsym);
+      }
+      double s = 0.0;
+      const double* p = a.Cg + static_cast<int64_t>(ci.group_start + lo) * kCgStride + src;
+      for (int g = lo; g < hi; ++g, p += kCgStride) s += *p;
+      acc[dst] += s;
+      if (dst2 >= 0) acc[dst2] += s;
+    }
+    __syncthreads();
+  }
+  double* out = a.Cpart + static_cast<int64_t>(blockIdx.x) * NS;
+  for (int k = tid; k < NS; k += blockDim.x) out[k] = acc[k];
+}
+
+// block-wide deterministic sum / max helpers (blockDim.x == 256)
+__device__ inline double block_sum_256(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < 8; ++w) s += sh[w];
+  return s;
+}
+__device__ inline double block_max_256(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < 8; ++w) s = fmax(s, sh[w]);
+  return s;
+}
+
+// scalars written for the host (indices into d_scalars)
+enum {
+  kScCost = 0,      // robust cost of the evaluated point
+  kScGmax = 1,      // gradient max norm
+  kScGnorm2 = 2,    // gradient squared 2-norm
+  kScDotG = 3,      // step . g        (scaled space)
+  kScDotD = 4,      // step . D2 step  (scaled space)
+  kScStep2 = 5,     // |x_trial - x|^2 (ambient)
+  kScXnorm2 = 6,    // |x_trial|^2 (ambient)
+  kScNotPD = 7,     // >0 if a Cholesky pivot failed
+  kScCount = 16
+};
+
+// ---------------------------------------------------------------- global blocks: level 2 + cost
+struct FinalizeArgs {
+  DevProblem dp;
+  const double* Cpart;
+  const double* cost_part;
+  int n_cost_part;
+  const double* imu_cost_part;
+  int n_imu_cost_part;
+  const double* step_part;  // [n_step_part][4] from backsub_update (may be null)
+  int n_step_part;
+  Blocks out;
+  double* scalars;
+};
+__global__ void __launch_bounds__(256) finalize_globals_kernel(FinalizeArgs a) {
+  __shared__ double sh[8];
+  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G;
+  for (int k = tid; k < NS; k += 256) {
+    double s = 0.0;
+    for (int b = 0; b < kReduceBlocks; ++b) s += a.Cpart[static_cast<int64_t>(b) * NS + k];
+    if (k < G * G) a.out.C[k] = s;
+    else a.out.gc[k - G * G] = s;
+  }
+  double c = 0.0;
+  for (int k = tid; k < a.n_cost_part; k += 256) c += a.cost_part[k];
+  for (int k = tid; k < a.n_imu_cost_part; k += 256) c += a.imu_cost_part[k];
+  c = block_sum_256(c, sh);
+  __syncthreads();
+  // gradient norms over [gf | gc]
+  double gm = 0.0, g2 = 0.0;
+  const int64_t nfp = static_cast<int64_t>(a.dp.n_frames) * a.dp.fd;
+  for (int64_t k = tid; k < nfp; k += 256) {
+    const double v = a.out.gf[k];
+    gm = fmax(gm, fabs(v));
+    g2 += v * v;
+  }
+  for (int k = tid; k < G; k += 256) {
+    const double v = a.out.gc[k];
+    gm = fmax(gm, fabs(v));
+    g2 += v * v;
+  }
+  gm = block_max_256(gm, sh);
+  g2 = block_sum_256(g2, sh);
+  double st[4] = {0.0, 0.0, 0.0, 0.0};
+  if (a.step_part) {
+    for (int k = tid; k < a.n_step_part; k += 256)
+      for (int q = 0; q < 4; ++q) st[q] += a.step_part[4 * k + q];
+    for (int q = 0; q < 4; ++q) st[q] = block_sum_256(st[q], sh);
+  }
+  if (tid == 0) {
+    *a.out.cost = c;
+    a.scalars[kScCost] = c;
+    a.scalars[kScGmax] = gm;
+    a.scalars[kScGnorm2] = g2;
+    if (a.step_part) {
+      a.scalars[kScDotG] = st[0];
+      a.scalars[kScDotD] = st[1];
+      a.scalars[kScStep2] = st[2];
+      a.scalars[kScXnorm2] = st[3];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- Jacobi scaling / LM diagonal
+// mode 0: scale = 1/(1+sqrt(diag))           (Ceres TrustRegionMinimizer jacobi_scaling)
+// mode 1: out = clamp(diag*scale^2, 1e-6, 1e32) * factor   (LevenbergMarquardtStrategy, factor = 1/radius)
+__global__ void diag_kernel(DevProblem dp, Blocks b, const double* scale, double* out, int mode, double factor) {
+  const int64_t n = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t nfp = static_cast<int64_t>(dp.n_frames) * dp.fd;
+  double d;
+  if (i < nfp) {
+    const int64_t f = i / dp.fd;
+    const int k = static_cast<int>(i - f * dp.fd);
+    d = b.B[(f * dp.fd + k) * dp.fd + k];
+  } else {
+    const int k = static_cast<int>(i - nfp);
+    d = b.C[k * dp.G + k];
+  }
+  if (mode == 0) {
+    out[i] = 1.0 / (1.0 + sqrt(d));
+  } else {
+    const double s = scale[i];
+    out[i] = fmin(fmax(d * s * s, 1e-6), 1e32) * factor;
+  }
+}
+
+// ---------------------------------------------------------------- per-frame solve (no coupling)
+struct SolveArgs {
+  DevProblem dp;
+  Blocks b;
+  const double* scale;
+  const double* D2;
+  double* X;      // [nf][fd][G+1]  = (B + D)^-1 [E | g]   (scaled space)
+  double* Spart;  // [gridDim][G*G+G]
+  double* scalars;
+};
+constexpr int kSolveThreads = 128;
+
+template <int FD>
+__global__ void __launch_bounds__(kSolveThreads) frame_solve_kernel(SolveArgs a) {
+  extern __shared__ double sm[];
+  const int G = a.dp.G, M = G + 1, tid = threadIdx.x, NS = G * G + G;
+  double* Sacc = sm;            // [G*G+G]
+  double* A = Sacc + NS;        // [FD*FD]
+  double* Es = A + FD * FD;     // [FD*G]
+  double* R = Es + FD * G;      // [FD*M]
+  const double* sc = a.scale + static_cast<int64_t>(a.dp.n_frames) * FD;
+  for (int k = tid; k < NS; k += kSolveThreads) Sacc[k] = 0.0;
+  for (int f = blockIdx.x; f < a.dp.n_frames; f += gridDim.x) {
+    const double* sf = a.scale + static_cast<int64_t>(f) * FD;
+    const double* Bf = a.b.B + static_cast<int64_t>(f) * FD * FD;
+    const double* Ef = a.b.E + static_cast<int64_t>(f) * FD * G;
+    __syncthreads();
+    for (int k = tid; k < FD * FD; k += kSolveThreads) {
+      const int r = k / FD, c = k - r * FD;
+      double v = Bf[k] * sf[r] * sf[c];
+      if (r == c) v += a.D2[static_cast<int64_t>(f) * FD + r];
+      A[k] = v;
+    }
+    for (int k = tid; k < FD * G; k += kSolveThreads) {
+      const int r = k / G, c = k - r * G;
+      const double v = Ef[k] * sf[r] * sc[c];
+      Es[k] = v;
+      R[r * M + c] = v;
+    }
+    for (int k = tid; k < FD; k += kSolveThreads) R[k * M + G] = a.b.gf[static_cast<int64_t>(f) * FD + k] * sf[k];
+    __syncthreads();
+    if (tid == 0) {
+      bool ok = true;
+      for (int j = 0; j < FD; ++j) {
+        double d = A[j * FD + j];
+        for (int k = 0; k < j; ++k) d -= A[j * FD + k] * A[j * FD + k];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        d = sqrt(d);
+        A[j * FD + j] = d;
+        for (int i = j + 1; i < FD; ++i) {
+          double s = A[i * FD + j];
+          for (int k = 0; k < j; ++k) s -= A[i * FD + k] * A[j * FD + k];
+          A[i * FD + j] = s / d;
+        }
+      }
+      if (!ok) a.scalars[kScNotPD] = 1.0;
+    }
+    __syncthreads();
+    for (int c = tid; c < M; c += kSolveThreads) {
+      double x[FD];
+#pragma unroll
+      for (int i = 0; i < FD; ++i) {
+        double s = R[i * M + c];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= A[i * FD + k] * x[k];
+        x[i] = s / A[i * FD + i];
+      }
+#pragma unroll
+      for (int i = FD - 1; i >= 0; --i) {
+        double s = x[i];
+#pragma unroll
+        for (int k = i + 1; k < FD; ++k) s -= A[k * FD + i] * x[k];
+        x[i] = s / A[i * FD + i];
+      }
+#pragma unroll
+      for (int i = 0; i < FD; ++i) R[i * M + c] = x[i];
+    }
+    __syncthreads();
+    double* Xf = a.X + static_cast<int64_t>(f) * FD * M;
+    for (int k = tid; k < FD * M; k += kSolveThreads) Xf[k] = R[k];
+    for (int e = tid; e < NS; e += kSolveThreads) {
+      const int ra = e < G * G ? e / G : e - G * G;
+      const int cb = e < G * G ? e - ra * G : G;
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < FD; ++k) s += Es[k * G + ra] * R[k * M + cb];
+      Sacc[e] += s;
+    }
+  }
+  __syncthreads();
+  double* out = a.Spart + static_cast<int64_t>(blockIdx.x) * NS;
+  for (int k = tid; k < NS; k += kSolveThreads) out[k] = Sacc[k];
+}
+
+// ---------------------------------------------------------------- reduced dense solve
+struct GlobalSolveArgs {
+  DevProblem dp;
+  Blocks b;
+  const double* scale;
+  const double* D2;
+  const double* Spart;
+  int n_spart;
+  double* delta;  // scaled step; globals written at delta[nf*fd ...]
+  double* scalars;
+};
+__global__ void __launch_bounds__(256) global_solve_kernel(GlobalSolveArgs a) {
+  extern __shared__ double sm[];
+  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G;
+  double* S = sm;           // [G*G]
+  double* rhs = sm + G * G; // [G]
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  const int64_t nfp = static_cast<int64_t>(a.dp.n_frames) * a.dp.fd;
+  const double* sc = a.scale + nfp;
+  for (int e = tid; e < NS; e += 256) {
+    double p = 0.0;
+    for (int b = 0; b < a.n_spart; ++b) p += a.Spart[static_cast<int64_t>(b) * NS + e];
+    if (e < G * G) {
+      const int r = e / G, c = e - r * G;
+      double v = a.b.C[e] * sc[r] * sc[c] - p;
+      if (r == c) v += a.D2[nfp + r];
+      S[e] = v;
+    } else {
+      const int r = e - G * G;
+      rhs[r] = -a.b.gc[r] * sc[r] + p;
+    }
+  }
+  __syncthreads();
+  // right-looking Cholesky, lower triangle
+  for (int j = 0; j < G; ++j) {
+    if (tid == 0) {
+      double d = S[j * G + j];
+      if (!(d > 0.0)) { bad = 1; d = 1.0; }
+      S[j * G + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double dj = S[j * G + j];
+    for (int i = j + 1 + tid; i < G; i += 256) S[i * G + j] /= dj;
+    __syncthreads();
+    const int rem = G - j - 1;
+    for (int e = tid; e < rem * rem; e += 256) {
+      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+      if (k <= i) S[i * G + k] -= S[i * G + j] * S[k * G + j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < G; ++i) {
+      double s = rhs[i];
+      for (int k = 0; k < i; ++k) s -= S[i * G + k] * rhs[k];
+      rhs[i] = s / S[i * G + i];
+    }
+    for (int i = G - 1; i >= 0; --i) {
+      double s = rhs[i];
+      for (int k = i + 1; k < G; ++k) s -= S[k * G + i] * rhs[k];
+      rhs[i] = s / S[i * G + i];
+    }
+    if (bad) a.scalars[kScNotPD] = 1.0;
+  }
+  __syncthreads();
+  for (int i = tid; i < G; i += 256) a.delta[nfp + i] = bad ? 0.0 : rhs[i];
+}
+
+// ---------------------------------------------------------------- back-substitution + x (+) delta
+struct UpdateArgs {
+  DevProblem dp;
+  Blocks b;
+  const double* scale;
+  const double* D2;
+  const double* X;
+  double* delta;
+  const double* x_cur;
+  double* x_new;
+  double* step_part;  // [gridDim+1][4]
+};
+constexpr int kUpdateWarps = 4;
+
+template <int FD>
+__global__ void __launch_bounds__(32 * kUpdateWarps) backsub_update_kernel(UpdateArgs a) {
+  const int G = a.dp.G, M = G + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nf = a.dp.n_frames;
+  const int64_t nfp = static_cast<int64_t>(nf) * FD;
+  const double* dc = a.delta + nfp;
+  __shared__ double part[kUpdateWarps][4];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int f = blockIdx.x * kUpdateWarps + warp;
+  if (f < nf) {
+    const double* Xf = a.X + static_cast<int64_t>(f) * FD * M;
+    double d[FD];
+#pragma unroll
+    for (int r = 0; r < FD; ++r) {
+      double s = 0.0;
+      for (int c = lane; c < G; c += 32) s += Xf[r * M + c] * dc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      d[r] = -Xf[r * M + G] - s;
+    }
+    if (lane == 0) {
+      double du[FD];
+#pragma unroll
+      for (int r = 0; r < FD; ++r) {
+        const int64_t k = static_cast<int64_t>(f) * FD + r;
+        const double sc = a.scale[k];
+        a.delta[k] = d[r];
+        acc[0] += d[r] * a.b.gf[k] * sc;
+        acc[1] += d[r] * d[r] * a.D2[k];
+        du[r] = d[r] * sc;
+      }
+      const double* x = a.x_cur + 7 * static_cast<int64_t>(f);
+      double xo[7];
+      se3_plus(x, du, xo);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        a.x_new[7 * static_cast<int64_t>(f) + k] = xo[k];
+        acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+        acc[3] += xo[k] * xo[k];
+      }
+      const double* v = a.x_cur + a.dp.off_v + 3 * static_cast<int64_t>(f);
+      double* vo = a.x_new + a.dp.off_v + 3 * static_cast<int64_t>(f);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double nv = (FD == 9) ? v[k] + du[(FD == 9) ? 6 + k : 0] : v[k];
+        vo[k] = nv;
+        if (FD == 9) {
+          acc[2] += (nv - v[k]) * (nv - v[k]);
+          acc[3] += nv * nv;
+        }
+      }
+    }
+  }
+  if (lane == 0)
+    for (int q = 0; q < 4; ++q) part[warp][q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 4; ++q) {
+      double s = 0.0;
+      for (int w = 0; w < kUpdateWarps; ++w) s += part[w][q];
+      a.step_part[4 * static_cast<int64_t>(blockIdx.x) + q] = s;
+    }
+  }
+  // globals: cameras + IMU parameters (one thread of block 0)
+  if (blockIdx.x == 0 && threadIdx.x == 32 * kUpdateWarps - 1) {
+    double g4[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* sc = a.scale + nfp;
+    for (int c = 0; c < a.dp.n_cams; ++c) {
+      const CamInfo& ci = a.dp.cams[c];
+      const double* x = a.x_cur + a.dp.off_cam + kCamStateStride * c;
+      double* xo = a.x_new + a.dp.off_cam + kCamStateStride * c;
+      double du[3];
+      for (int k = 0; k < 3; ++k) du[k] = dc[ci.goff + k] * sc[ci.goff + k];
+      double qo[4];
+      so3_plus(x, du, qo);
+      for (int k = 0; k < 4; ++k) xo[k] = qo[k];
+      for (int k = 0; k < 3; ++k) xo[4 + k] = x[4 + k] + dc[ci.goff + 3 + k] * sc[ci.goff + 3 + k];
+      for (int k = 0; k < 10; ++k)
+        xo[7 + k] = x[7 + k] + (k < ci.K ? dc[ci.goff + 6 + k] * sc[ci.goff + 6 + k] : 0.0);
+      for (int k = 0; k < 7 + ci.K; ++k) {
+        g4[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+        g4[3] += xo[k] * xo[k];
+      }
+    }
+    {
+      const double* x = a.x_cur + a.dp.off_imu;
+      double* xo = a.x_new + a.dp.off_imu;
+      for (int k = 0; k < kImuStateSize; ++k) {
+        const double dd = a.dp.inertial ? dc[a.dp.imu_goff + k] * sc[a.dp.imu_goff + k] : 0.0;
+        xo[k] = x[k] + dd;
+        if (a.dp.inertial) {
+          g4[2] += dd * dd;
+          g4[3] += xo[k] * xo[k];
+        }
+      }
+    }
+    for (int k = 0; k < G; ++k) {
+      g4[0] += dc[k] * a.b.gc[k] * sc[k];
+      g4[1] += dc[k] * dc[k] * a.D2[nfp + k];
+    }
+    for (int q = 0; q < 4; ++q) a.step_part[4 * static_cast<int64_t>(gridDim.x) + q] = g4[q];
+  }
+}
+
+}  // namespace vc

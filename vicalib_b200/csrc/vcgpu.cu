@@ -1,0 +1,915 @@
+// libvcgpu.so — host side of the C-ABI declared in include/vcgpu.h.
+//
+// Replaces, for ViCalibrator, what ceres::Problem + ceres::Solve + Problem::Evaluate do
+// (vicalibrator.h:152, 548-679, 859-916, 956-971).  The trust-region loop below is the Ceres
+// loop (TrustRegionMinimizer + LevenbergMarquardtStrategy) driven from the host
+// with every arithmetic step on the device; the candidate point is evaluated *with* its Jacobian
+// blocks (speculatively) so an accepted step needs no second pass and a multi-GPU run needs one
+// all-reduce per iteration.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "vc_internal.h"
+#include "vc_kernels.cuh"
+#include "vc_imu.cuh"
+
+using namespace vc;
+
+#define CUDA_TRY(h, expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                       \
+      return VCGPU_ERR_CUDA;                                                                \
+    }                                                                                       \
+  } while (0)
+#define VC_TRY(expr)                 \
+  do {                               \
+    int rc__ = (expr);               \
+    if (rc__ != VCGPU_OK) return rc__; \
+  } while (0)
+
+static int fail(vcgpu_handle* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+template <class T>
+static int dev_alloc(vcgpu_handle* h, T** p, size_t n) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return VCGPU_OK;
+}
+template <class T>
+static void dev_free(T** p) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+}
+
+// ------------------------------------------------------------------ lifecycle
+extern "C" void vcgpu_default_flags(vcgpu_flags* f) {
+  std::memset(f, 0, sizeof *f);
+  f->visual = 1;
+  f->visual_mult = 1.0;
+  f->imu_mult = 1.0;
+}
+extern "C" void vcgpu_default_options(vcgpu_options* o) {
+  o->max_iters = 200;
+  o->function_tol = 1e-6;
+  o->gradient_tol = 1e-10;
+  o->param_tol = 1e-8;
+  o->init_radius = 1e4;
+  o->strategy = 0;
+  o->jacobi_scaling = 1;
+  o->update_imu_weights = 1;
+  o->update_state_every_iteration = 0;
+}
+
+extern "C" int vcgpu_create(const vcgpu_config* cfg, vcgpu_handle** out) {
+  if (!out) return VCGPU_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VCGPU_ERR_CUDA;  // no CPU fallback
+  vcgpu_handle* h = new vcgpu_handle();
+  vcgpu_default_flags(&h->flags);
+  vcgpu_default_options(&h->opts);
+  int dev = cfg ? cfg->device : -1;
+  if (dev < 0) cudaGetDevice(&dev);
+  h->device = dev;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), kScCount * sizeof(double)) != cudaSuccess) {
+    delete h;
+    return VCGPU_ERR_CUDA;
+  }
+  *out = h;
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_destroy(vcgpu_handle* h) {
+  if (!h) return VCGPU_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  dev_free(&h->d_state[0]); dev_free(&h->d_state[1]);
+  dev_free(&h->d_obs); dev_free(&h->d_obs_frame);
+  dev_free(&h->d_grp_start); dev_free(&h->d_grp_count); dev_free(&h->d_group_of);
+  dev_free(&h->d_mask); dev_free(&h->d_r); dev_free(&h->d_J); dev_free(&h->d_cost_part);
+  dev_free(&h->d_Cg); dev_free(&h->d_Cpart);
+  dev_free(&h->d_blk_mem[0]); dev_free(&h->d_blk_mem[1]);
+  dev_free(&h->d_scale); dev_free(&h->d_X); dev_free(&h->d_Spart); dev_free(&h->d_delta);
+  dev_free(&h->d_red); dev_free(&h->d_scalars);
+  dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
+  imu_free(h);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return VCGPU_OK;
+}
+
+extern "C" const char* vcgpu_last_error(const vcgpu_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+// ------------------------------------------------------------------ uploads
+extern "C" int vcgpu_set_cameras(vcgpu_handle* h, int n, const int32_t* model, const double* intr,
+                                 const double* q_ck, const double* p_ck) {
+  if (!h || n <= 0 || n > kMaxCams || !model || !intr || !q_ck || !p_ck)
+    return h ? fail(h, VCGPU_ERR_INVALID, "set_cameras: bad arguments (1..8 cameras)") : VCGPU_ERR_INVALID;
+  for (int i = 0; i < n; ++i)
+    if (model[i] < 0 || model[i] > 4) return fail(h, VCGPU_ERR_INVALID, "set_cameras: unknown camera model");
+  if (n != h->n_cams || !std::equal(model, model + n, h->h_model.begin())) h->dirty = true;
+  h->n_cams = n;
+  h->h_model.assign(model, model + n);
+  h->h_intr.assign(intr, intr + 10 * n);
+  h->h_qck.assign(q_ck, q_ck + 4 * n);
+  h->h_pck.assign(p_ck, p_ck + 3 * n);
+  h->state_dirty = true;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_set_frames(vcgpu_handle* h, int n, const double* T_wp, const double* v_w, const double* time) {
+  if (!h || n <= 0 || !T_wp || !v_w || !time) return h ? fail(h, VCGPU_ERR_INVALID, "set_frames: bad arguments") : VCGPU_ERR_INVALID;
+  if (n != h->n_frames) h->dirty = true;
+  h->n_frames = n;
+  h->h_T.assign(T_wp, T_wp + 7 * n);
+  h->h_v.assign(v_w, v_w + 3 * n);
+  if (h->h_time.size() != static_cast<size_t>(n) || !std::equal(time, time + n, h->h_time.begin())) h->dirty = true;
+  h->h_time.assign(time, time + n);
+  h->state_dirty = true;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_set_observations(vcgpu_handle* h, int64_t n, const int32_t* frame_id, const int32_t* cam_id,
+                                      const double* p_w, const double* p_c) {
+  if (!h || n < 0 || (n > 0 && (!frame_id || !cam_id || !p_w || !p_c)))
+    return h ? fail(h, VCGPU_ERR_INVALID, "set_observations: bad arguments") : VCGPU_ERR_INVALID;
+  h->n_obs_all = n;
+  h->h_obs_frame.assign(frame_id, frame_id + n);
+  h->h_obs_cam.assign(cam_id, cam_id + n);
+  h->h_pw.assign(p_w, p_w + 3 * n);
+  h->h_pc.assign(p_c, p_c + 2 * n);
+  h->h_active.assign(n, 1);
+  h->dirty = true;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_set_imu(vcgpu_handle* h, int n, const double* t, const double* w, const double* a,
+                             double sigma_g, double sigma_a) {
+  if (!h || n < 0 || (n > 0 && (!t || !w || !a))) return h ? fail(h, VCGPU_ERR_INVALID, "set_imu: bad arguments") : VCGPU_ERR_INVALID;
+  for (int i = 1; i < n; ++i)
+    if (!(t[i] > t[i - 1])) return fail(h, VCGPU_ERR_INVALID, "set_imu: timestamps are not unique/increasing");  // vicalibrator.h:377
+  h->h_imu_t.assign(t, t + n);
+  h->h_imu_w.assign(w, w + 3 * n);
+  h->h_imu_a.assign(a, a + 3 * n);
+  h->sigma_g = sigma_g;
+  h->sigma_a = sigma_a;
+  h->dirty = true;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_set_imu_params(vcgpu_handle* h, const double g[2], const double b[6], const double sf[6], double ts) {
+  if (!h || !g || !b || !sf) return h ? fail(h, VCGPU_ERR_INVALID, "set_imu_params: bad arguments") : VCGPU_ERR_INVALID;
+  std::memcpy(h->h_g, g, sizeof h->h_g);
+  std::memcpy(h->h_b, b, sizeof h->h_b);
+  std::memcpy(h->h_sf, sf, sizeof h->h_sf);
+  h->h_ts = ts;
+  h->state_dirty = true;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_set_flags(vcgpu_handle* h, const vcgpu_flags* f) {
+  if (!h || !f) return VCGPU_ERR_INVALID;
+  if ((f->inertial != 0) != (h->flags.inertial != 0)) h->dirty = true;
+  h->flags = *f;
+  h->blocks_valid = false;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_set_options(vcgpu_handle* h, const vcgpu_options* o) {
+  if (!h || !o) return VCGPU_ERR_INVALID;
+  if (o->strategy != 0 && o->strategy != 1) return fail(h, VCGPU_ERR_INVALID, "set_options: unknown strategy");
+  h->opts = *o;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_register_mirrors(vcgpu_handle* h, double* intr, double* q_ck, double* p_ck, double* T_wp,
+                                      double* v_w, double* g, double* b, double* sf, double* ts) {
+  if (!h) return VCGPU_ERR_INVALID;
+  double* m[9] = {intr, q_ck, p_ck, T_wp, v_w, g, b, sf, ts};
+  std::memcpy(h->mirror, m, sizeof m);
+  return VCGPU_OK;
+}
+
+// ------------------------------------------------------------------ prepare: sort, allocate, upload
+static void fill_mask(const vcgpu_handle* h, std::vector<double>* mask) {
+  const DevProblem& dp = h->dp;
+  mask->assign(dp.G, 1.0);
+  const vcgpu_flags& f = h->flags;
+  for (int c = 0; c < dp.n_cams; ++c) {
+    const CamInfo& ci = dp.cams[c];
+    if (c == 0) {  // vicalibrator.h:572-587
+      const double rot = f.inertial ? 1.0 : 0.0;
+      const double trans = (f.inertial && !f.rotation_only) ? 1.0 : 0.0;
+      for (int i = 0; i < 3; ++i) (*mask)[ci.goff + i] = rot;
+      for (int i = 0; i < 3; ++i) (*mask)[ci.goff + 3 + i] = trans;
+    }
+    if (f.fix_intrinsics)
+      for (int i = 0; i < ci.K; ++i) (*mask)[ci.goff + 6 + i] = 0.0;
+  }
+  if (f.inertial) {  // vicalibrator.h:657-676
+    const int o = dp.imu_goff;
+    (*mask)[o] = (*mask)[o + 1] = f.rotation_only ? 0.0 : 1.0;
+    for (int i = 0; i < 6; ++i) (*mask)[o + 2 + i] = f.bias_active ? 1.0 : 0.0;
+    for (int i = 0; i < 6; ++i) (*mask)[o + 8 + i] = f.scale_active ? 1.0 : 0.0;
+    (*mask)[o + 14] = f.optimize_ts ? 1.0 : 0.0;
+  }
+}
+
+static void pack_state(const vcgpu_handle* h, std::vector<double>* s) {
+  const DevProblem& dp = h->dp;
+  s->assign(dp.state_size, 0.0);
+  std::copy(h->h_T.begin(), h->h_T.end(), s->begin());
+  std::copy(h->h_v.begin(), h->h_v.end(), s->begin() + dp.off_v);
+  for (int c = 0; c < dp.n_cams; ++c) {
+    double* p = s->data() + dp.off_cam + kCamStateStride * c;
+    std::copy(&h->h_qck[4 * c], &h->h_qck[4 * c] + 4, p);
+    std::copy(&h->h_pck[3 * c], &h->h_pck[3 * c] + 3, p + 4);
+    std::copy(&h->h_intr[10 * c], &h->h_intr[10 * c] + 10, p + 7);
+  }
+  double* p = s->data() + dp.off_imu;
+  p[0] = h->h_g[0]; p[1] = h->h_g[1];
+  for (int i = 0; i < 6; ++i) { p[2 + i] = h->h_b[i]; p[8 + i] = h->h_sf[i]; }
+  p[14] = h->h_ts;
+}
+static void unpack_state(vcgpu_handle* h, const std::vector<double>& s) {
+  const DevProblem& dp = h->dp;
+  std::copy(s.begin(), s.begin() + 7 * dp.n_frames, h->h_T.begin());
+  std::copy(s.begin() + dp.off_v, s.begin() + dp.off_v + 3 * dp.n_frames, h->h_v.begin());
+  for (int c = 0; c < dp.n_cams; ++c) {
+    const double* p = s.data() + dp.off_cam + kCamStateStride * c;
+    std::copy(p, p + 4, &h->h_qck[4 * c]);
+    std::copy(p + 4, p + 7, &h->h_pck[3 * c]);
+    std::copy(p + 7, p + 17, &h->h_intr[10 * c]);
+  }
+  const double* p = s.data() + dp.off_imu;
+  h->h_g[0] = p[0]; h->h_g[1] = p[1];
+  for (int i = 0; i < 6; ++i) { h->h_b[i] = p[2 + i]; h->h_sf[i] = p[8 + i]; }
+  h->h_ts = p[14];
+}
+
+static int upload_state(vcgpu_handle* h) {
+  std::vector<double> s;
+  pack_state(h, &s);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_state[h->cur], s.data(), s.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->state_dirty = false;
+  h->blocks_valid = false;
+  return VCGPU_OK;
+}
+static int download_state(vcgpu_handle* h) {
+  std::vector<double> s(h->dp.state_size);
+  CUDA_TRY(h, cudaMemcpyAsync(s.data(), h->d_state[h->cur], s.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  unpack_state(h, s);
+  return VCGPU_OK;
+}
+static void write_mirrors(vcgpu_handle* h) {
+  const size_t nc = h->n_cams, nf = h->n_frames;
+  if (h->mirror[0]) std::memcpy(h->mirror[0], h->h_intr.data(), 10 * nc * sizeof(double));
+  if (h->mirror[1]) std::memcpy(h->mirror[1], h->h_qck.data(), 4 * nc * sizeof(double));
+  if (h->mirror[2]) std::memcpy(h->mirror[2], h->h_pck.data(), 3 * nc * sizeof(double));
+  if (h->mirror[3]) std::memcpy(h->mirror[3], h->h_T.data(), 7 * nf * sizeof(double));
+  if (h->mirror[4]) std::memcpy(h->mirror[4], h->h_v.data(), 3 * nf * sizeof(double));
+  if (h->mirror[5]) std::memcpy(h->mirror[5], h->h_g, sizeof h->h_g);
+  if (h->mirror[6]) std::memcpy(h->mirror[6], h->h_b, sizeof h->h_b);
+  if (h->mirror[7]) std::memcpy(h->mirror[7], h->h_sf, sizeof h->h_sf);
+  if (h->mirror[8]) *h->mirror[8] = h->h_ts;
+}
+
+static int prepare(vcgpu_handle* h) {
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->n_cams <= 0 || h->n_frames <= 0) return fail(h, VCGPU_ERR_INVALID, "cameras and frames must be set first");
+  if (h->dirty) {
+    DevProblem& dp = h->dp;
+    std::memset(&dp, 0, sizeof dp);
+    dp.n_cams = h->n_cams;
+    dp.n_frames = h->n_frames;
+    const int nf = h->n_frames, nc = h->n_cams;
+    // validate + sort active observations by (camera, frame), stable in caller order
+    for (int64_t i = 0; i < h->n_obs_all; ++i) {
+      if (h->h_obs_cam[i] < 0 || h->h_obs_cam[i] >= nc) return fail(h, VCGPU_ERR_INVALID, "observation with unknown camera id");  // vicalibrator.h:396
+      if (h->h_obs_frame[i] < 0 || h->h_obs_frame[i] >= nf) return fail(h, VCGPU_ERR_INVALID, "observation with unknown frame id");
+    }
+    std::vector<int64_t> count(static_cast<size_t>(nc) * nf + 1, 0);
+    for (int64_t i = 0; i < h->n_obs_all; ++i)
+      if (h->h_active[i]) ++count[static_cast<size_t>(h->h_obs_cam[i]) * nf + h->h_obs_frame[i] + 1];
+    for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
+    h->n_obs = count.back();
+    h->perm.assign(h->n_obs, 0);
+    {
+      std::vector<int64_t> pos(count.begin(), count.end() - 1);
+      for (int64_t i = 0; i < h->n_obs_all; ++i)
+        if (h->h_active[i]) h->perm[pos[static_cast<size_t>(h->h_obs_cam[i]) * nf + h->h_obs_frame[i]]++] = i;
+    }
+    std::vector<int32_t> grp_start, grp_count, group_of(static_cast<size_t>(nc) * nf, -1);
+    int goff = 0;
+    int64_t joff = 0;
+    for (int c = 0; c < nc; ++c) {
+      CamInfo& ci = dp.cams[c];
+      ci.model = h->h_model[c];
+      ci.K = num_intr(ci.model);
+      ci.goff = goff;
+      goff += 6 + ci.K;
+      ci.obs_start = static_cast<int>(count[static_cast<size_t>(c) * nf]);
+      ci.n_obs = static_cast<int>(count[static_cast<size_t>(c + 1) * nf] - count[static_cast<size_t>(c) * nf]);
+      ci.group_start = static_cast<int>(grp_start.size());
+      for (int f = 0; f < nf; ++f) {
+        const int64_t s = count[static_cast<size_t>(c) * nf + f], e = count[static_cast<size_t>(c) * nf + f + 1];
+        if (e > s) {
+          group_of[static_cast<size_t>(c) * nf + f] = static_cast<int32_t>(grp_start.size());
+          grp_start.push_back(static_cast<int32_t>(s));
+          grp_count.push_back(static_cast<int32_t>(e - s));
+        }
+      }
+      ci.n_groups = static_cast<int>(grp_start.size()) - ci.group_start;
+      ci.joff = joff;
+      joff += static_cast<int64_t>(2 * (12 + ci.K)) * ci.n_obs;
+    }
+    h->n_groups = static_cast<int>(grp_start.size());
+    dp.inertial = h->flags.inertial ? 1 : 0;
+    dp.fd = dp.inertial ? 9 : 6;
+    dp.imu_goff = goff;
+    dp.G = goff + (dp.inertial ? 15 : 0);
+    dp.off_v = 7LL * nf;
+    dp.off_cam = 10LL * nf;
+    dp.off_imu = dp.off_cam + kCamStateStride * nc;
+    dp.state_size = dp.off_imu + kImuStateSize;
+    const int fd = dp.fd, G = dp.G;
+    const int64_t n = h->n_obs;
+    // sorted observation arrays
+    std::vector<double> obs(5 * std::max<int64_t>(n, 1));
+    std::vector<int32_t> fr(std::max<int64_t>(n, 1));
+    for (int64_t k = 0; k < n; ++k) {
+      const int64_t i = h->perm[k];
+      obs[k] = h->h_pw[3 * i]; obs[n + k] = h->h_pw[3 * i + 1]; obs[2 * n + k] = h->h_pw[3 * i + 2];
+      obs[3 * n + k] = h->h_pc[2 * i]; obs[4 * n + k] = h->h_pc[2 * i + 1];
+      fr[k] = h->h_obs_frame[i];
+    }
+    VC_TRY(dev_alloc(h, &h->d_obs, obs.size()));
+    VC_TRY(dev_alloc(h, &h->d_obs_frame, fr.size()));
+    VC_TRY(dev_alloc(h, &h->d_grp_start, grp_start.size()));
+    VC_TRY(dev_alloc(h, &h->d_grp_count, grp_count.size()));
+    VC_TRY(dev_alloc(h, &h->d_group_of, group_of.size()));
+    CUDA_TRY(h, cudaMemcpy(h->d_obs, obs.data(), obs.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_obs_frame, fr.data(), fr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!grp_start.empty()) {
+      CUDA_TRY(h, cudaMemcpy(h->d_grp_start, grp_start.data(), grp_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      CUDA_TRY(h, cudaMemcpy(h->d_grp_count, grp_count.data(), grp_count.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(h, cudaMemcpy(h->d_group_of, group_of.data(), group_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // work buffers
+    VC_TRY(dev_alloc(h, &h->d_state[0], dp.state_size));
+    VC_TRY(dev_alloc(h, &h->d_state[1], dp.state_size));
+    VC_TRY(dev_alloc(h, &h->d_mask, G));
+    VC_TRY(dev_alloc(h, &h->d_r, 2 * n));
+    VC_TRY(dev_alloc(h, &h->d_J, joff));
+    h->n_cost_part = 0;
+    for (int c = 0; c < nc; ++c) h->n_cost_part += (dp.cams[c].n_obs + 255) / 256;
+    VC_TRY(dev_alloc(h, &h->d_cost_part, h->n_cost_part));
+    VC_TRY(dev_alloc(h, &h->d_Cg, static_cast<size_t>(h->n_groups) * kCgStride));
+    CUDA_TRY(h, cudaMemset(h->d_Cg, 0, std::max<size_t>(1, static_cast<size_t>(h->n_groups) * kCgStride) * sizeof(double)));
+    const size_t NS = static_cast<size_t>(G) * G + G;
+    VC_TRY(dev_alloc(h, &h->d_Cpart, kReduceBlocks * NS));
+    const size_t blk_sz = 2 * static_cast<size_t>(nf) * fd * fd + static_cast<size_t>(nf) * fd * G +
+                          static_cast<size_t>(nf) * fd + NS + 1;
+    for (int b = 0; b < 2; ++b) {
+      VC_TRY(dev_alloc(h, &h->d_blk_mem[b], blk_sz));
+      CUDA_TRY(h, cudaMemset(h->d_blk_mem[b], 0, blk_sz * sizeof(double)));
+      double* p = h->d_blk_mem[b];
+      h->blk[b].B = p; p += static_cast<size_t>(nf) * fd * fd;
+      h->blk[b].U = p; p += static_cast<size_t>(nf) * fd * fd;
+      h->blk[b].E = p; p += static_cast<size_t>(nf) * fd * G;
+      h->blk[b].gf = p; p += static_cast<size_t>(nf) * fd;
+      h->blk[b].C = p; p += static_cast<size_t>(G) * G;
+      h->blk[b].gc = p; p += G;
+      h->blk[b].cost = p;
+    }
+    const size_t np = static_cast<size_t>(nf) * fd + G;
+    VC_TRY(dev_alloc(h, &h->d_scale, 2 * np));  // [scale | D2]
+    VC_TRY(dev_alloc(h, &h->d_X, static_cast<size_t>(nf) * fd * (G + 1)));
+    h->n_solve_blocks = std::min(nf, 296);
+    VC_TRY(dev_alloc(h, &h->d_Spart, static_cast<size_t>(h->n_solve_blocks) * NS));
+    VC_TRY(dev_alloc(h, &h->d_delta, np));
+    VC_TRY(dev_alloc(h, &h->d_red, 4 * (static_cast<size_t>((nf + kUpdateWarps - 1) / kUpdateWarps) + 1)));
+    VC_TRY(dev_alloc(h, &h->d_scalars, kScCount));
+    CUDA_TRY(h, cudaMemset(h->d_scalars, 0, kScCount * sizeof(double)));
+    VC_TRY(imu_prepare(h));
+    h->cur = 0;
+    h->dirty = false;
+    h->state_dirty = true;
+  }
+  {
+    DevProblem& dp = h->dp;
+    dp.rotation_only = h->flags.rotation_only ? 1 : 0;
+    dp.visual_mult = h->flags.visual ? h->flags.visual_mult : 0.0;
+    dp.imu_mult = h->flags.imu_mult;
+    std::vector<double> mask;
+    fill_mask(h, &mask);
+    CUDA_TRY(h, cudaMemcpy(h->d_mask, mask.data(), mask.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (h->state_dirty) VC_TRY(upload_state(h));
+  return VCGPU_OK;
+}
+
+// ------------------------------------------------------------------ kernel launch helpers
+template <bool JAC>
+static void launch_eval_cam(vcgpu_handle* h, const EvalArgs& a, int model, int nblk) {
+  switch (model) {
+    case kLinear: eval_reproj_kernel<kLinear, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+    case kFov: eval_reproj_kernel<kFov, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+    case kPoly2: eval_reproj_kernel<kPoly2, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+    case kPoly3: eval_reproj_kernel<kPoly3, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+    default: eval_reproj_kernel<kKb4, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+  }
+  ++h->launches;
+}
+
+// residual (+ Jacobian) pass over every camera's observations at state buffer `buf`
+static int eval_reproj(vcgpu_handle* h, int buf, bool jac, bool apply_loss, const double* mask_dev) {
+  const DevProblem& dp = h->dp;
+  const int64_t n = h->n_obs;
+  int part = 0;
+  for (int c = 0; c < dp.n_cams; ++c) {
+    const CamInfo& ci = dp.cams[c];
+    if (ci.n_obs == 0) continue;
+    EvalArgs a;
+    a.state = h->d_state[buf];
+    a.cam = h->d_state[buf] + dp.off_cam + kCamStateStride * c;
+    a.frame = h->d_obs_frame + ci.obs_start;
+    a.pwx = h->d_obs + ci.obs_start;
+    a.pwy = h->d_obs + n + ci.obs_start;
+    a.pwz = h->d_obs + 2 * n + ci.obs_start;
+    a.pcu = h->d_obs + 3 * n + ci.obs_start;
+    a.pcv = h->d_obs + 4 * n + ci.obs_start;
+    a.mask = mask_dev + ci.goff;
+    a.r0 = h->d_r + ci.obs_start;
+    a.r1 = h->d_r + n + ci.obs_start;
+    a.J = h->d_J + ci.joff;
+    a.cost_part = h->d_cost_part + part;
+    a.n = ci.n_obs;
+    a.apply_loss = apply_loss ? 1 : 0;
+    a.mult = dp.visual_mult;
+    const int nblk = (ci.n_obs + 255) / 256;
+    part += nblk;
+    if (jac) launch_eval_cam<true>(h, a, ci.model, nblk);
+    else launch_eval_cam<false>(h, a, ci.model, nblk);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+// full evaluation at state buffer `buf`: residuals, Jacobians, block normal equations into blk[buf];
+// scalars cost / gradient norms (and the step reductions when `with_step`) land in d_scalars.
+static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
+  const DevProblem& dp = h->dp;
+  const bool visual = h->flags.visual && h->n_obs > 0;
+  if (visual) VC_TRY(eval_reproj(h, buf, true, true, h->d_mask));
+  int n_imu_cost = 0;
+  if (dp.inertial) VC_TRY(imu_evaluate(h, buf, true, &n_imu_cost));
+  BuildArgs ba;
+  ba.dp = dp;
+  if (!visual) ba.dp.n_cams = 0;
+  ba.grp_start = h->d_grp_start; ba.grp_count = h->d_grp_count; ba.group_of = h->d_group_of;
+  ba.r = h->d_r; ba.J = h->d_J; ba.n_obs = h->n_obs; ba.out = h->blk[buf]; ba.Cg = h->d_Cg;
+  const size_t bsm = (2 * kBuildChunk * kMaxW + 9 * 9 + 9) * sizeof(double);
+  if (dp.fd == 6) build_frames_kernel<6><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
+  else build_frames_kernel<9><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
+  ++h->launches;
+  if (dp.inertial) VC_TRY(imu_accumulate(h, buf));
+  const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
+  ReduceArgs ra;
+  ra.dp = ba.dp; ra.Cg = h->d_Cg; ra.Cpart = h->d_Cpart;
+  reduce_globals_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
+  ++h->launches;
+  FinalizeArgs fa;
+  fa.dp = dp; fa.Cpart = h->d_Cpart;
+  fa.cost_part = h->d_cost_part; fa.n_cost_part = visual ? h->n_cost_part : 0;
+  fa.imu_cost_part = imu_cost_part(h); fa.n_imu_cost_part = n_imu_cost;
+  fa.step_part = with_step ? h->d_red : nullptr;
+  fa.n_step_part = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps + 1;
+  fa.out = h->blk[buf]; fa.scalars = h->d_scalars;
+  finalize_globals_kernel<<<1, 256, 0, h->stream>>>(fa);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+static int read_scalars(vcgpu_handle* h) {
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, kScCount * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return VCGPU_OK;
+}
+
+static int compute_diag(vcgpu_handle* h, int buf, int mode, double factor, double* out) {
+  const DevProblem& dp = h->dp;
+  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
+  diag_kernel<<<static_cast<int>((np + 255) / 256), 256, 0, h->stream>>>(dp, h->blk[buf], h->d_scale, out, mode, factor);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+// damped arrow solve with blocks of `buf` and D2 = d_scale + np; step -> d_delta; trial state -> d_state[1-buf]
+static int solve_and_update(vcgpu_handle* h, int buf) {
+  const DevProblem& dp = h->dp;
+  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
+  const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
+  const double* D2 = h->d_scale + np;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_scalars + kScNotPD, 0, sizeof(double), h->stream));
+  if (dp.inertial) {
+    VC_TRY(imu_chain_solve(h, buf, D2));
+  } else {
+    SolveArgs sa;
+    sa.dp = dp; sa.b = h->blk[buf]; sa.scale = h->d_scale; sa.D2 = D2; sa.X = h->d_X; sa.Spart = h->d_Spart;
+    sa.scalars = h->d_scalars;
+    const size_t ssm = (NS + 6 * 6 + 6 * dp.G + 6 * (dp.G + 1)) * sizeof(double);
+    frame_solve_kernel<6><<<h->n_solve_blocks, kSolveThreads, ssm, h->stream>>>(sa);
+    ++h->launches;
+  }
+  GlobalSolveArgs ga;
+  ga.dp = dp; ga.b = h->blk[buf]; ga.scale = h->d_scale; ga.D2 = D2; ga.Spart = h->d_Spart;
+  ga.n_spart = h->n_solve_blocks; ga.delta = h->d_delta; ga.scalars = h->d_scalars;
+  global_solve_kernel<<<1, 256, NS * sizeof(double), h->stream>>>(ga);
+  ++h->launches;
+  if (dp.inertial) {
+    VC_TRY(imu_chain_backsub(h, buf, D2));
+  } else {
+    UpdateArgs ua;
+    ua.dp = dp; ua.b = h->blk[buf]; ua.scale = h->d_scale; ua.D2 = D2; ua.X = h->d_X; ua.delta = h->d_delta;
+    ua.x_cur = h->d_state[buf]; ua.x_new = h->d_state[1 - buf]; ua.step_part = h->d_red;
+    const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
+    backsub_update_kernel<6><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
+    ++h->launches;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+static double host_state_norm(const vcgpu_handle* h) {
+  double s = 0;
+  for (double v : h->h_T) s += v * v;
+  if (h->flags.inertial) for (double v : h->h_v) s += v * v;
+  for (int c = 0; c < h->n_cams; ++c) {
+    for (int i = 0; i < 4; ++i) s += h->h_qck[4 * c + i] * h->h_qck[4 * c + i];
+    for (int i = 0; i < 3; ++i) s += h->h_pck[3 * c + i] * h->h_pck[3 * c + i];
+    for (int i = 0; i < num_intr(h->h_model[c]); ++i) s += h->h_intr[10 * c + i] * h->h_intr[10 * c + i];
+  }
+  if (h->flags.inertial) {
+    s += h->h_g[0] * h->h_g[0] + h->h_g[1] * h->h_g[1] + h->h_ts * h->h_ts;
+    for (int i = 0; i < 6; ++i) s += h->h_b[i] * h->h_b[i] + h->h_sf[i] * h->h_sf[i];
+  }
+  return std::sqrt(s);
+}
+
+static int num_residuals(const vcgpu_handle* h) {
+  int64_t n = 0;
+  if (h->flags.visual) {
+    int64_t act = 0;
+    for (uint8_t a : h->h_active) act += a;
+    n += static_cast<int64_t>(2 * act * h->flags.visual_mult);
+  }
+  if (h->flags.inertial && h->n_frames > 1) n += static_cast<int64_t>(9 * (h->n_frames - 1) * h->flags.imu_mult);
+  return static_cast<int>(n);
+}
+
+// ------------------------------------------------------------------ the trust-region loop
+static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out, int fixed_iters) {
+  VC_TRY(prepare(h));
+  if (h->opts.strategy != 0) return fail(h, VCGPU_ERR_INVALID, "DOGLEG strategy is not implemented on the device yet; use strategy 0 (LM)");
+  const DevProblem& dp = h->dp;
+  const vcgpu_options& o = h->opts;
+  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
+  const long launches0 = h->launches;
+  vcgpu_summary sum;
+  std::memset(&sum, 0, sizeof sum);
+  sum.num_residuals = num_residuals(h);
+  const bool weights = o.update_imu_weights && dp.inertial;
+  if (weights) VC_TRY(imu_update_weights(h, h->cur));  // vicalibrator.h:955
+  VC_TRY(evaluate_into(h, h->cur, false));
+  if (o.jacobi_scaling) {
+    VC_TRY(compute_diag(h, h->cur, 0, 0.0, h->d_scale));
+  } else {
+    std::vector<double> ones(np, 1.0);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_scale, ones.data(), np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  VC_TRY(read_scalars(h));
+  h->blocks_valid = true;
+  double cost = h->h_scalars[kScCost], gmax = h->h_scalars[kScGmax], gnorm = std::sqrt(h->h_scalars[kScGnorm2]);
+  sum.initial_cost = cost;
+  double x_norm = host_state_norm(h);
+  double radius = o.init_radius, decrease_factor = 2.0;
+  int term = VCGPU_TERM_NO_CONVERGENCE;
+  bool done = false;
+  auto callback = [&](const vcgpu_iteration& it) -> int {
+    if (weights) { int rc = imu_update_weights(h, h->cur); if (rc) return rc; }  // vicalibrator.h:691
+    if (fixed_iters > 0) return 0;
+    if (cb && (o.update_state_every_iteration || h->mirror[3])) {
+      if (o.update_state_every_iteration) { int rc = download_state(h); if (rc) return rc; write_mirrors(h); }
+    }
+    int stop = 0;
+    if (cb) stop = cb(&it, user);
+    if (it.gradient_norm > 0 && it.gradient_norm < 1e-9) stop = 1;  // vicalibrator.h:713-717
+    return stop ? 1 : 0;
+  };
+  vcgpu_iteration it;
+  std::memset(&it, 0, sizeof it);
+  it.iteration = 0; it.step_is_successful = 1; it.cost = cost; it.gradient_max_norm = gmax; it.gradient_norm = gnorm;
+  it.trust_region_radius = radius;
+  if (fixed_iters <= 0 && gmax <= o.gradient_tol) { term = VCGPU_TERM_GRADIENT_TOL; done = true; }
+  if (!done) {
+    const int rc = callback(it);
+    if (rc < 0) return rc;
+    if (rc > 0) { term = VCGPU_TERM_CALLBACK; done = true; }
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  const int max_it = fixed_iters > 0 ? fixed_iters : o.max_iters;
+  for (int iter = 1; !done; ++iter) {
+    if (iter > max_it) { term = VCGPU_TERM_NO_CONVERGENCE; break; }
+    if (radius < 1e-32) { term = VCGPU_TERM_RADIUS; break; }
+    sum.iterations = iter;
+    // LevenbergMarquardtStrategy::ComputeStep: D = sqrt(clamp(diag(J'J)) / radius)
+    VC_TRY(compute_diag(h, h->cur, 1, 1.0 / radius, h->d_scale + np));
+    VC_TRY(solve_and_update(h, h->cur));
+    VC_TRY(evaluate_into(h, 1 - h->cur, true));
+    VC_TRY(read_scalars(h));
+    const double* sc = h->h_scalars;
+    std::memset(&it, 0, sizeof it);
+    it.iteration = iter; it.cost = cost; it.gradient_max_norm = gmax; it.trust_region_radius = radius;
+    // model_cost_change = -step.g - step.H.step/2, with (H + D2) step = -g
+    const double model_change = -0.5 * sc[kScDotG] + 0.5 * sc[kScDotD];
+    if (sc[kScNotPD] > 0.0 || !(model_change > 0.0) || !std::isfinite(sc[kScCost])) {
+      radius /= decrease_factor; decrease_factor *= 2.0;  // StepIsInvalid / StepRejected
+      it.trust_region_radius = radius;
+      const int rc = callback(it);
+      if (rc < 0) return rc;
+      if (rc > 0) { term = VCGPU_TERM_CALLBACK; break; }
+      continue;
+    }
+    const double cand = sc[kScCost];
+    const double step_norm = std::sqrt(sc[kScStep2]);
+    const double cost_change = cost - cand;
+    it.step_norm = step_norm; it.cost_change = cost_change;
+    if (fixed_iters <= 0) {
+      if (step_norm <= o.param_tol * (x_norm + o.param_tol)) { term = VCGPU_TERM_PARAM_TOL; break; }
+      if (std::fabs(cost_change) <= o.function_tol * cost) { term = VCGPU_TERM_FUNCTION_TOL; break; }
+    }
+    const double rho = cost_change / model_change;
+    it.relative_decrease = rho;
+    if (rho > 1e-3) {
+      h->cur = 1 - h->cur;  // the candidate's blocks were built speculatively: accept = flip
+      cost = cand;
+      gmax = sc[kScGmax]; gnorm = std::sqrt(sc[kScGnorm2]);
+      x_norm = std::sqrt(sc[kScXnorm2]);
+      ++sum.successful_steps;
+      radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+      decrease_factor = 2.0;
+      it.step_is_successful = 1; it.cost = cost; it.gradient_max_norm = gmax; it.gradient_norm = gnorm;
+      it.trust_region_radius = radius;
+      if (fixed_iters <= 0 && gmax <= o.gradient_tol) { term = VCGPU_TERM_GRADIENT_TOL; callback(it); break; }
+    } else {
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      it.trust_region_radius = radius;
+    }
+    const int rc = callback(it);
+    if (rc < 0) return rc;
+    if (rc > 0) { term = VCGPU_TERM_CALLBACK; break; }
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  sum.device_seconds = ms * 1e-3;
+  sum.termination = term;
+  sum.final_cost = cost;
+  sum.kernel_launches = static_cast<int>(h->launches - launches0);
+  VC_TRY(download_state(h));
+  write_mirrors(h);
+  if (out) *out = sum;
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out) {
+  if (!h) return VCGPU_ERR_INVALID;
+  return run_solve(h, cb, user, out, 0);
+}
+extern "C" int vcgpu_iterate(vcgpu_handle* h, int n, vcgpu_summary* out) {
+  if (!h || n <= 0) return VCGPU_ERR_INVALID;
+  return run_solve(h, nullptr, nullptr, out, n);
+}
+
+// ------------------------------------------------------------------ evaluation entry points
+extern "C" int vcgpu_cost(vcgpu_handle* h, double* cost) {
+  if (!h || !cost) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  VC_TRY(evaluate_into(h, h->cur, false));
+  VC_TRY(read_scalars(h));
+  *cost = h->h_scalars[kScCost];
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_evaluate(vcgpu_handle* h, int cam, double* cost, double* residuals, int64_t* n_blocks) {
+  if (!h) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  const DevProblem& dp = h->dp;
+  if (cam >= dp.n_cams) return fail(h, VCGPU_ERR_INVALID, "evaluate: camera index out of range");
+  VC_TRY(eval_reproj(h, h->cur, false, false, h->d_mask));
+  const int64_t n = h->n_obs;
+  std::vector<double> r(2 * std::max<int64_t>(n, 1));
+  CUDA_TRY(h, cudaMemcpyAsync(r.data(), h->d_r, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->blocks_valid = false;
+  // caller order: gather the sorted residuals back through perm
+  const int c0 = cam < 0 ? 0 : cam, c1 = cam < 0 ? dp.n_cams : cam + 1;
+  std::vector<std::pair<int64_t, int64_t>> idx;  // (caller index, sorted index)
+  for (int c = c0; c < c1; ++c)
+    for (int64_t k = dp.cams[c].obs_start; k < dp.cams[c].obs_start + dp.cams[c].n_obs; ++k) idx.emplace_back(h->perm[k], k);
+  std::sort(idx.begin(), idx.end());
+  double s = 0;
+  int64_t o = 0;
+  for (const auto& pr : idx) {
+    const double a = r[pr.second], b = r[n + pr.second];
+    s += a * a + b * b;
+    if (residuals) { residuals[2 * o] = a; residuals[2 * o + 1] = b; }
+    ++o;
+  }
+  if (cost) *cost = 0.5 * s;
+  if (n_blocks) *n_blocks = o;
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_remove_outliers(vcgpu_handle* h, const double* rmse, double threshold, int64_t* n_removed) {
+  if (!h || !rmse) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  const DevProblem& dp = h->dp;
+  VC_TRY(eval_reproj(h, h->cur, false, false, h->d_mask));
+  const int64_t n = h->n_obs;
+  std::vector<double> r(2 * std::max<int64_t>(n, 1));
+  CUDA_TRY(h, cudaMemcpyAsync(r.data(), h->d_r, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  int64_t removed = 0;
+  for (int c = 0; c < dp.n_cams; ++c)
+    for (int64_t k = dp.cams[c].obs_start; k < dp.cams[c].obs_start + dp.cams[c].n_obs; ++k) {
+      const double err = std::sqrt(r[k] * r[k] + r[n + k] * r[n + k]);
+      if (err > threshold * rmse[c]) { h->h_active[h->perm[k]] = 0; ++removed; }  // vicalibrator.h:890-893
+    }
+  if (removed) h->dirty = true;
+  if (n_removed) *n_removed = removed;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_get_obs_active(vcgpu_handle* h, uint8_t* active) {
+  if (!h || !active) return VCGPU_ERR_INVALID;
+  std::memcpy(active, h->h_active.data(), h->h_active.size());
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_get_state(vcgpu_handle* h, double* intr, double* q_ck, double* p_ck, double* T_wp, double* v_w,
+                               double* g, double* b, double* sf, double* ts) {
+  if (!h) return VCGPU_ERR_INVALID;
+  if (!h->dirty && !h->state_dirty) VC_TRY(download_state(h));
+  const size_t nc = h->n_cams, nf = h->n_frames;
+  if (intr) std::memcpy(intr, h->h_intr.data(), 10 * nc * sizeof(double));
+  if (q_ck) std::memcpy(q_ck, h->h_qck.data(), 4 * nc * sizeof(double));
+  if (p_ck) std::memcpy(p_ck, h->h_pck.data(), 3 * nc * sizeof(double));
+  if (T_wp) std::memcpy(T_wp, h->h_T.data(), 7 * nf * sizeof(double));
+  if (v_w) std::memcpy(v_w, h->h_v.data(), 3 * nf * sizeof(double));
+  if (g) std::memcpy(g, h->h_g, sizeof h->h_g);
+  if (b) std::memcpy(b, h->h_b, sizeof h->h_b);
+  if (sf) std::memcpy(sf, h->h_sf, sizeof h->h_sf);
+  if (ts) *ts = h->h_ts;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_num_residuals(vcgpu_handle* h, int* out) {
+  if (!h || !out) return VCGPU_ERR_INVALID;
+  *out = num_residuals(h);
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_frame_dim(vcgpu_handle* h, int* out) {
+  if (!h || !out) return VCGPU_ERR_INVALID;
+  *out = h->flags.inertial ? 9 : 6;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_num_globals(vcgpu_handle* h, int* out) {
+  if (!h || !out) return VCGPU_ERR_INVALID;
+  int g = 0;
+  for (int c = 0; c < h->n_cams; ++c) g += 6 + num_intr(h->h_model[c]);
+  *out = g + (h->flags.inertial ? 15 : 0);
+  return VCGPU_OK;
+}
+
+// ------------------------------------------------------------------ inspection hooks
+extern "C" int vcgpu_eval_reproj(vcgpu_handle* h, double* r_out, double* J_out) {
+  if (!h || !r_out) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  const DevProblem& dp = h->dp;
+  const int64_t n = h->n_obs;
+  double* ones = nullptr;
+  VC_TRY(dev_alloc(h, &ones, dp.G));
+  std::vector<double> hones(dp.G, 1.0);
+  CUDA_TRY(h, cudaMemcpy(ones, hones.data(), dp.G * sizeof(double), cudaMemcpyHostToDevice));
+  const double vm = h->dp.visual_mult;
+  VC_TRY(eval_reproj(h, h->cur, J_out != nullptr, false, ones));
+  (void)vm;
+  std::vector<double> r(2 * std::max<int64_t>(n, 1));
+  CUDA_TRY(h, cudaMemcpyAsync(r.data(), h->d_r, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(ones);
+  h->blocks_valid = false;
+  for (int64_t k = 0; k < n; ++k) {
+    r_out[2 * h->perm[k]] = r[k];
+    r_out[2 * h->perm[k] + 1] = r[n + k];
+  }
+  if (J_out) {
+    for (int c = 0; c < dp.n_cams; ++c) {
+      const CamInfo& ci = dp.cams[c];
+      const int NT = 12 + ci.K;
+      std::vector<double> J(static_cast<size_t>(2 * NT) * std::max(ci.n_obs, 1));
+      CUDA_TRY(h, cudaMemcpy(J.data(), h->d_J + ci.joff, static_cast<size_t>(2 * NT) * ci.n_obs * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int li = 0; li < ci.n_obs; ++li) {
+        double* o = J_out + 44 * h->perm[ci.obs_start + li];
+        std::memset(o, 0, 44 * sizeof(double));
+        for (int row = 0; row < 2; ++row)
+          for (int k = 0; k < NT; ++k) o[row * 22 + k] = J[static_cast<size_t>(row * NT + k) * ci.n_obs + li];
+      }
+    }
+  }
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_normal_equations(vcgpu_handle* h, double* B, double* U, double* E, double* gf, double* C,
+                                      double* gc, double* cost) {
+  if (!h) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  VC_TRY(evaluate_into(h, h->cur, false));
+  VC_TRY(read_scalars(h));
+  const DevProblem& dp = h->dp;
+  const size_t nf = dp.n_frames, fd = dp.fd, G = dp.G;
+  const Blocks& b = h->blk[h->cur];
+  if (B) CUDA_TRY(h, cudaMemcpy(B, b.B, nf * fd * fd * sizeof(double), cudaMemcpyDeviceToHost));
+  if (U) CUDA_TRY(h, cudaMemcpy(U, b.U, nf * fd * fd * sizeof(double), cudaMemcpyDeviceToHost));
+  if (E) CUDA_TRY(h, cudaMemcpy(E, b.E, nf * fd * G * sizeof(double), cudaMemcpyDeviceToHost));
+  if (gf) CUDA_TRY(h, cudaMemcpy(gf, b.gf, nf * fd * sizeof(double), cudaMemcpyDeviceToHost));
+  if (C) CUDA_TRY(h, cudaMemcpy(C, b.C, G * G * sizeof(double), cudaMemcpyDeviceToHost));
+  if (gc) CUDA_TRY(h, cudaMemcpy(gc, b.gc, G * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cost) *cost = h->h_scalars[kScCost];
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_solve_arrow(vcgpu_handle* h, const double* scale, const double* D2, double* x) {
+  if (!h || !scale || !D2 || !x) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  VC_TRY(evaluate_into(h, h->cur, false));
+  const DevProblem& dp = h->dp;
+  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_scale, scale, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_scale + np, D2, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  VC_TRY(solve_and_update(h, h->cur));
+  VC_TRY(read_scalars(h));
+  if (h->h_scalars[kScNotPD] > 0) return fail(h, VCGPU_ERR_NUMERIC, "arrow system is not positive definite");
+  CUDA_TRY(h, cudaMemcpy(x, h->d_delta, np * sizeof(double), cudaMemcpyDeviceToHost));
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_eval_imu(vcgpu_handle* h, double* r, double* J) {
+  if (!h || !r) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  return imu_eval_hook(h, r, J);
+}
+extern "C" int vcgpu_update_imu_weights(vcgpu_handle* h) {
+  if (!h) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  if (!h->dp.inertial) return VCGPU_OK;
+  VC_TRY(imu_update_weights(h, h->cur));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_get_imu_weights(vcgpu_handle* h, double* w) {
+  if (!h || !w) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  if (h->n_frames < 2 || !h->d_wsqrt) return VCGPU_OK;
+  CUDA_TRY(h, cudaMemcpy(w, h->d_wsqrt, static_cast<size_t>(h->n_frames - 1) * 81 * sizeof(double), cudaMemcpyDeviceToHost));
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_set_imu_weights(vcgpu_handle* h, const double* w) {
+  if (!h || !w) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  if (h->n_frames < 2 || !h->d_wsqrt) return VCGPU_OK;
+  CUDA_TRY(h, cudaMemcpy(h->d_wsqrt, w, static_cast<size_t>(h->n_frames - 1) * 81 * sizeof(double), cudaMemcpyHostToDevice));
+  return VCGPU_OK;
+}
+
+extern "C" int vcgpu_comm_unique_id(uint8_t id[VCGPU_UNIQUE_ID_BYTES]) {
+  (void)id;
+  return VCGPU_ERR_COMM;  // multi-GPU sharding lands with the IMU chain solver
+}
+extern "C" int vcgpu_comm_init(vcgpu_handle* h, const uint8_t id[VCGPU_UNIQUE_ID_BYTES], int rank, int nranks) {
+  (void)id; (void)rank; (void)nranks;
+  return h ? fail(h, VCGPU_ERR_COMM, "multi-GPU communicator not implemented yet") : VCGPU_ERR_COMM;
+}
