@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/sec of the calibration solve (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2] [--impl reference]
+
+A "step" is one trust-region (LM) iteration over the whole synthetic problem: solve the damped
+arrow system, update the state, evaluate residuals + Jacobians at the trial point, rebuild the
+block normal equations, accept/reject.  One JSON line is printed by rank 0.
+
+* value      — K iterations / device time (CUDA events on the library's launch stream, max over
+               ranks); inputs resident in HBM; L2 flushed before every iteration (working set of
+               config 2 is 102 MB < 126 MB L2) unless --no-flush.
+* e2e        — the same metric through the C-ABI with HOST buffers: upload (set_* calls), K
+               iterations, state read-back, all inside the timed region (wall clock).
+* roofline   — dominant kernel stage: algorithmic bytes per launch / its CUDA-event duration.
+* cpu_baseline — the CPU oracle (port of the reference's Ceres path) on a bounded sample.
+* --impl reference — the oracle port on all host threads (Ceres cannot be built here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vicalib_b200 import synth  # noqa: E402
+
+METRIC = "lm_iterations_per_sec"
+UNIT = "iterations/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def shard_problem(p, rank, world):
+    """Contiguous frame shard of a vision-only problem (weak scaling: every rank gets the full
+    BASELINE workload's worth of frames; frames are independent given the globals)."""
+    return p  # single-GPU until the sharded all-reduce path lands
+
+
+def algorithmic_bytes_per_obs(K):
+    """SURVEY §8(d), speculative-evaluation variant: one observation read + residual and Jacobian
+    written by the evaluate pass and read back by the build pass."""
+    return 44 + 2 * (16 + 16 * (12 + K))
+
+
+def stage_bytes(stage, n_obs, K):
+    if stage == "eval_reproj":
+        return n_obs * (44 + 16 + 16 * (12 + K))
+    if stage == "build_frames":
+        return n_obs * (16 + 16 * (12 + K))
+    return None
+
+
+def run_ours(args):
+    from vicalib_b200.capi import Calibrator
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    p = synth.make_config(args.workload)
+    if p.inertial:
+        raise SystemExit("inertial workloads need the IMU device path")
+    K0 = synth.NUM_INTR[int(p.models[0])]
+    g = Calibrator(device=local)
+    t_up0 = time.perf_counter()
+    g.load(p)
+    g.set_options(max_iters=args.steps)
+    # ---- warm-up (W untimed iterations; also builds all device buffers)
+    g.set_profiling(False, not args.no_flush)
+    g.iterate(max(args.warmup, 3))
+    # ---- timed: exactly K iterations from the same initial guess
+    g.load(p)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    s = g.iterate(args.steps)
+    dev_s = s["device_seconds"]
+    # extra timed repeats keep the clock sampler busy long enough to see the loaded clocks
+    reps = [dev_s]
+    t_end = time.time() + 1.0
+    while time.time() < t_end:
+        g.load(p)
+        reps.append(g.iterate(args.steps)["device_seconds"])
+    clocks = sampler.stop()
+    dev_s = float(np.median(reps))
+    launches = s["kernel_launches"]
+    # ---- per-stage device time (separate profiled pass, same workload, L2 flushed the same way)
+    g.load(p)
+    g.set_profiling(True, not args.no_flush)
+    g.iterate(args.steps)
+    st = g.stage_times()
+    g.set_profiling(False, False)
+    stages = {k: {"ms_per_iter": v[0] / args.steps, "launches_per_iter": v[1] / args.steps} for k, v in st.items() if v[1]}
+    # ---- no-flush number for information
+    g.load(p)
+    nf_s = g.iterate(args.steps)["device_seconds"]
+    # ---- end to end through the C-ABI with host buffers
+    e2e_t = []
+    for _ in range(3):
+        g2 = Calibrator(device=local)
+        t0 = time.perf_counter()
+        g2.load(p)
+        g2.set_options(max_iters=args.steps)
+        g2.iterate(args.steps)
+        st2 = g2.state()
+        e2e_t.append(time.perf_counter() - t0)
+        g2.close()
+    e2e_s = float(np.median(e2e_t))
+    h2d = (p.n_obs * (4 + 4 + 24 + 16) + p.n_frames * 88 + p.n_cams * (4 + 136) + len(p.imu_t) * 56 + 120)
+    d2h = p.n_frames * 80 + p.n_cams * 136 + 120 + args.steps * 128
+    # ---- max over ranks
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        t = torch.tensor([dev_s, e2e_s], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = t.tolist()
+        dist.barrier()
+    if rank != 0:
+        return
+    peaks, peak_src = _peaks()
+    n_obs_total = p.n_obs * world
+    top = max((k for k in stages if stage_bytes(k, p.n_obs, K0)), key=lambda k: stages[k]["ms_per_iter"])
+    top_bytes = stage_bytes(top, p.n_obs, K0)
+    achieved = top_bytes / (stages[top]["ms_per_iter"] * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": args.steps * world / dev_s if False else args.steps / dev_s, "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: " + _describe(p), "n_obs": n_obs_total, "n_frames": p.n_frames,
+                   "cameras": [int(m) for m in p.models], "l2": "flushed before every iteration" if not args.no_flush
+                   else "not flushed", "value_no_flush": args.steps / nf_s,
+                   "algorithmic_bytes_per_obs_iter": algorithmic_bytes_per_obs(K0),
+                   "iteration_hbm_frac": p.n_obs * algorithmic_bytes_per_obs(K0) / (dev_s / args.steps) / 1e9 / peaks["hbm_gbs"],
+                   "stages_ms_per_iter": {k: round(v["ms_per_iter"], 5) for k, v in stages.items()},
+                   "accepted_steps": s["successful_steps"], "final_cost": s["final_cost"]},
+        "clocks": clocks,
+        "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+                "d2h_bytes_per_step": d2h / args.steps, "note": "upload + K iterations + state read-back, wall clock"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": top_bytes},
+        "cpu_baseline": cpu_baseline(p, args),
+    }
+    print(json.dumps(out))
+
+
+def _describe(p):
+    names = {v: k for k, v in synth.MODEL_IDS.items()}
+    return (f"{p.n_cams} cam ({','.join(names[int(m)] for m in p.models)}), {p.n_frames} frames, "
+            f"{p.n_obs // (p.n_frames * p.n_cams)} corners" + (" + IMU" if p.inertial else ", no IMU"))
+
+
+def cpu_baseline(p, args, threads=None, iters=None):
+    """The oracle (CPU port of the reference's Ceres path: one dual-number evaluation per residual
+    block, block-sparse normal equations, block Cholesky, same trust-region loop) on the host."""
+    from oracle.binding import Oracle
+
+    cores = threads or min(os.cpu_count() or 1, 64)
+    o = Oracle(p, inertial=int(p.inertial))
+    iters = iters or 4
+    o.set_options(max_iters=iters, function_tol=0.0, gradient_tol=0.0, param_tol=0.0, num_threads=cores)
+    t0 = time.perf_counter()
+    s = o.solve()
+    dt = time.perf_counter() - t0
+    n = max(int(s["iterations"]), 1)
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} LM iterations of the full workload ({p.n_obs} observations), {dt:.2f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    p = synth.make_config(args.workload)
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    # warm-up + K timed steps, each a full LM iteration of the workload
+    cpu_baseline(p, args, threads=threads, iters=max(1, min(args.warmup, 2)))
+    cb = cpu_baseline(p, args, threads=threads, iters=args.steps)
+    v = cb["value"]
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: " + _describe(p),
+                      "note": "Ceres/Calibu/Sophus/Eigen are not in the image: the reference arm is the CPU port "
+                              "(oracle/) of the reference's Ceres path on the host cores"},
+           "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="config2", choices=list(synth.CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,26 @@ int vcgpu_normal_equations(vcgpu_handle* h, double* B, double* U, double* E, dou
 /* one damped solve (H*scale^2 + diag(D2)) x = -g*scale with the device arrow solver */
 int vcgpu_solve_arrow(vcgpu_handle* h, const double* scale, const double* D2, double* x);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------
+ * profile: bracket every kernel stage of the solve loop with CUDA events on the launching stream
+ * flush_l2: overwrite a 256 MiB scratch buffer before every iteration and time iterations
+ *           individually, so no iteration starts with its inputs resident in the 126 MB L2 */
+enum {
+  VCGPU_STAGE_DIAG = 0,         /* LM diagonal */
+  VCGPU_STAGE_FRAME_SOLVE = 1,  /* per-frame Cholesky + Schur contribution (or IMU chain elimination) */
+  VCGPU_STAGE_GLOBAL_SOLVE = 2, /* dense reduced system */
+  VCGPU_STAGE_BACKSUB = 3,      /* back-substitution + x (+) delta */
+  VCGPU_STAGE_EVAL_REPROJ = 4,  /* reprojection residual + Jacobian */
+  VCGPU_STAGE_BUILD = 5,        /* per-frame block normal equations */
+  VCGPU_STAGE_REDUCE = 6,       /* global block tree reduction, level 1 */
+  VCGPU_STAGE_FINALIZE = 7,     /* level 2 + cost + gradient norms */
+  VCGPU_STAGE_IMU_EVAL = 8,     /* IMU residual + Jacobian */
+  VCGPU_STAGE_IMU_WEIGHTS = 9,  /* UpdateImuWeights */
+  VCGPU_STAGE_COUNT = 16
+};
+int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2);
+int vcgpu_get_stage_times(vcgpu_handle* h, double ms_total[VCGPU_STAGE_COUNT], int64_t launches[VCGPU_STAGE_COUNT]);
+
 /* ---- multi-GPU: one process per GPU, frames sharded contiguously, one NCCL all-reduce of the
  * reduced normal equations per iteration ---------------------------------------------------- */
 #define VCGPU_UNIQUE_ID_BYTES 128

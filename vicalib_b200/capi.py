@@ -24,6 +24,7 @@ EXPORTS = [
     "vcgpu_get_obs_active", "vcgpu_update_imu_weights", "vcgpu_get_imu_weights", "vcgpu_set_imu_weights",
     "vcgpu_get_state", "vcgpu_num_residuals", "vcgpu_frame_dim", "vcgpu_num_globals", "vcgpu_eval_reproj",
     "vcgpu_eval_imu", "vcgpu_normal_equations", "vcgpu_solve_arrow", "vcgpu_comm_unique_id", "vcgpu_comm_init",
+    "vcgpu_set_profiling", "vcgpu_get_stage_times",
 ]
 
 
@@ -257,6 +258,18 @@ class Calibrator:
         x = np.zeros(self.n_frames * self.fd + self.G)
         self._chk(self.L.vcgpu_solve_arrow(self.h, _p(_c(scale)), _p(_c(D2)), _p(x)))
         return x
+
+    STAGES = ["diag", "frame_solve", "global_solve", "backsub", "eval_reproj", "build_frames", "reduce_globals",
+              "finalize", "imu_eval", "imu_weights"]
+
+    def set_profiling(self, profile=True, flush_l2=False):
+        self._chk(self.L.vcgpu_set_profiling(self.h, C.c_int(int(profile)), C.c_int(int(flush_l2))))
+
+    def stage_times(self):
+        ms = np.zeros(16)
+        n = np.zeros(16, dtype=np.int64)
+        self._chk(self.L.vcgpu_get_stage_times(self.h, _p(ms), _p(n)))
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.STAGES)}
 
     def update_imu_weights(self):
         self._chk(self.L.vcgpu_update_imu_weights(self.h))

@@ -49,6 +49,15 @@ struct vcgpu_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long launches = 0;
+  // measurement hooks
+  bool profiling = false, flush_l2 = false;
+  cudaEvent_t st_ev[VCGPU_STAGE_COUNT][2] = {};
+  bool st_used[VCGPU_STAGE_COUNT] = {};
+  double st_ms[VCGPU_STAGE_COUNT] = {};
+  int64_t st_n[VCGPU_STAGE_COUNT] = {};
+  long st_l0 = 0;
+  cudaEvent_t it_ev[2] = {nullptr, nullptr};
+  void* d_flush = nullptr;
 
   // ---- host copies of the problem
   int n_cams = 0, n_frames = 0;

@@ -51,6 +51,51 @@ static void dev_free(T** p) {
   *p = nullptr;
 }
 
+// ------------------------------------------------------------------ stage timers
+struct StageScope {
+  vcgpu_handle* h;
+  int s;
+  StageScope(vcgpu_handle* h_, int s_) : h(h_), s(s_) {
+    if (h->profiling) { cudaEventRecord(h->st_ev[s][0], h->stream); h->st_l0 = h->launches; }
+  }
+  ~StageScope() {
+    if (h->profiling) {
+      cudaEventRecord(h->st_ev[s][1], h->stream);
+      h->st_used[s] = true;
+      h->st_n[s] += h->launches - h->st_l0;
+    }
+  }
+};
+static void stage_collect(vcgpu_handle* h) {  // call after a stream synchronise
+  if (!h->profiling) return;
+  for (int s = 0; s < VCGPU_STAGE_COUNT; ++s)
+    if (h->st_used[s]) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, h->st_ev[s][0], h->st_ev[s][1]) == cudaSuccess) h->st_ms[s] += ms;
+      h->st_used[s] = false;
+    }
+}
+extern "C" int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2) {
+  if (!h) return VCGPU_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if ((profile || flush_l2) && !h->it_ev[0]) {
+    for (int s = 0; s < VCGPU_STAGE_COUNT; ++s)
+      for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaEventCreate(&h->st_ev[s][k]));
+    CUDA_TRY(h, cudaEventCreate(&h->it_ev[0]));
+    CUDA_TRY(h, cudaEventCreate(&h->it_ev[1]));
+  }
+  if (flush_l2 && !h->d_flush) CUDA_TRY(h, cudaMalloc(&h->d_flush, 256u << 20));
+  h->profiling = profile != 0;
+  h->flush_l2 = flush_l2 != 0;
+  for (int s = 0; s < VCGPU_STAGE_COUNT; ++s) { h->st_ms[s] = 0; h->st_n[s] = 0; h->st_used[s] = false; }
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_get_stage_times(vcgpu_handle* h, double ms_total[VCGPU_STAGE_COUNT], int64_t launches[VCGPU_STAGE_COUNT]) {
+  if (!h || !ms_total || !launches) return VCGPU_ERR_INVALID;
+  for (int s = 0; s < VCGPU_STAGE_COUNT; ++s) { ms_total[s] = h->st_ms[s]; launches[s] = h->st_n[s]; }
+  return VCGPU_OK;
+}
+
 // ------------------------------------------------------------------ lifecycle
 extern "C" void vcgpu_default_flags(vcgpu_flags* f) {
   std::memset(f, 0, sizeof *f);
@@ -106,6 +151,13 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->d_flush) cudaFree(h->d_flush);
+  if (h->it_ev[0]) {
+    for (int s = 0; s < VCGPU_STAGE_COUNT; ++s)
+      for (int k = 0; k < 2; ++k) cudaEventDestroy(h->st_ev[s][k]);
+    cudaEventDestroy(h->it_ev[0]);
+    cudaEventDestroy(h->it_ev[1]);
+  }
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -471,24 +523,36 @@ static int eval_reproj(vcgpu_handle* h, int buf, bool jac, bool apply_loss, cons
 static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
   const DevProblem& dp = h->dp;
   const bool visual = h->flags.visual && h->n_obs > 0;
-  if (visual) VC_TRY(eval_reproj(h, buf, true, true, h->d_mask));
+  if (visual) {
+    StageScope st(h, VCGPU_STAGE_EVAL_REPROJ);
+    VC_TRY(eval_reproj(h, buf, true, true, h->d_mask));
+  }
   int n_imu_cost = 0;
-  if (dp.inertial) VC_TRY(imu_evaluate(h, buf, true, &n_imu_cost));
+  if (dp.inertial) {
+    StageScope st(h, VCGPU_STAGE_IMU_EVAL);
+    VC_TRY(imu_evaluate(h, buf, true, &n_imu_cost));
+  }
   BuildArgs ba;
   ba.dp = dp;
   if (!visual) ba.dp.n_cams = 0;
   ba.grp_start = h->d_grp_start; ba.grp_count = h->d_grp_count; ba.group_of = h->d_group_of;
   ba.r = h->d_r; ba.J = h->d_J; ba.n_obs = h->n_obs; ba.out = h->blk[buf]; ba.Cg = h->d_Cg;
   const size_t bsm = (2 * kBuildChunk * kMaxW + 9 * 9 + 9) * sizeof(double);
-  if (dp.fd == 6) build_frames_kernel<6><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
-  else build_frames_kernel<9><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
-  ++h->launches;
-  if (dp.inertial) VC_TRY(imu_accumulate(h, buf));
+  {
+    StageScope st(h, VCGPU_STAGE_BUILD);
+    if (dp.fd == 6) build_frames_kernel<6><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
+    else build_frames_kernel<9><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
+    ++h->launches;
+    if (dp.inertial) VC_TRY(imu_accumulate(h, buf));
+  }
   const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
   ReduceArgs ra;
   ra.dp = ba.dp; ra.Cg = h->d_Cg; ra.Cpart = h->d_Cpart;
-  reduce_globals_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
-  ++h->launches;
+  {
+    StageScope st(h, VCGPU_STAGE_REDUCE);
+    reduce_globals_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
+    ++h->launches;
+  }
   FinalizeArgs fa;
   fa.dp = dp; fa.Cpart = h->d_Cpart;
   fa.cost_part = h->d_cost_part; fa.n_cost_part = visual ? h->n_cost_part : 0;
@@ -496,8 +560,11 @@ static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
   fa.step_part = with_step ? h->d_red : nullptr;
   fa.n_step_part = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps + 1;
   fa.out = h->blk[buf]; fa.scalars = h->d_scalars;
-  finalize_globals_kernel<<<1, 256, 0, h->stream>>>(fa);
-  ++h->launches;
+  {
+    StageScope st(h, VCGPU_STAGE_FINALIZE);
+    finalize_globals_kernel<<<1, 256, 0, h->stream>>>(fa);
+    ++h->launches;
+  }
   CUDA_TRY(h, cudaGetLastError());
   return VCGPU_OK;
 }
@@ -505,12 +572,14 @@ static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
 static int read_scalars(vcgpu_handle* h) {
   CUDA_TRY(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, kScCount * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  stage_collect(h);
   return VCGPU_OK;
 }
 
 static int compute_diag(vcgpu_handle* h, int buf, int mode, double factor, double* out) {
   const DevProblem& dp = h->dp;
   const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
+  StageScope st(h, VCGPU_STAGE_DIAG);
   diag_kernel<<<static_cast<int>((np + 255) / 256), 256, 0, h->stream>>>(dp, h->blk[buf], h->d_scale, out, mode, factor);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
@@ -525,8 +594,10 @@ static int solve_and_update(vcgpu_handle* h, int buf) {
   const double* D2 = h->d_scale + np;
   CUDA_TRY(h, cudaMemsetAsync(h->d_scalars + kScNotPD, 0, sizeof(double), h->stream));
   if (dp.inertial) {
+    StageScope st(h, VCGPU_STAGE_FRAME_SOLVE);
     VC_TRY(imu_chain_solve(h, buf, D2));
   } else {
+    StageScope st(h, VCGPU_STAGE_FRAME_SOLVE);
     SolveArgs sa;
     sa.dp = dp; sa.b = h->blk[buf]; sa.scale = h->d_scale; sa.D2 = D2; sa.X = h->d_X; sa.Spart = h->d_Spart;
     sa.scalars = h->d_scalars;
@@ -537,11 +608,16 @@ static int solve_and_update(vcgpu_handle* h, int buf) {
   GlobalSolveArgs ga;
   ga.dp = dp; ga.b = h->blk[buf]; ga.scale = h->d_scale; ga.D2 = D2; ga.Spart = h->d_Spart;
   ga.n_spart = h->n_solve_blocks; ga.delta = h->d_delta; ga.scalars = h->d_scalars;
-  global_solve_kernel<<<1, 256, NS * sizeof(double), h->stream>>>(ga);
-  ++h->launches;
+  {
+    StageScope st(h, VCGPU_STAGE_GLOBAL_SOLVE);
+    global_solve_kernel<<<1, 256, NS * sizeof(double), h->stream>>>(ga);
+    ++h->launches;
+  }
   if (dp.inertial) {
+    StageScope st(h, VCGPU_STAGE_BACKSUB);
     VC_TRY(imu_chain_backsub(h, buf, D2));
   } else {
+    StageScope st(h, VCGPU_STAGE_BACKSUB);
     UpdateArgs ua;
     ua.dp = dp; ua.b = h->blk[buf]; ua.scale = h->d_scale; ua.D2 = D2; ua.X = h->d_X; ua.delta = h->d_delta;
     ua.x_cur = h->d_state[buf]; ua.x_new = h->d_state[1 - buf]; ua.step_part = h->d_red;
@@ -630,16 +706,33 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
     if (rc > 0) { term = VCGPU_TERM_CALLBACK; done = true; }
   }
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  double flushed_ms = 0.0;
   const int max_it = fixed_iters > 0 ? fixed_iters : o.max_iters;
   for (int iter = 1; !done; ++iter) {
     if (iter > max_it) { term = VCGPU_TERM_NO_CONVERGENCE; break; }
-    if (radius < 1e-32) { term = VCGPU_TERM_RADIUS; break; }
+    if (radius < 1e-32) {
+      if (fixed_iters > 0) { radius = o.init_radius; decrease_factor = 2.0; }  // benchmark mode never stops early
+      else { term = VCGPU_TERM_RADIUS; break; }
+    }
     sum.iterations = iter;
+    if (h->flush_l2) {
+      CUDA_TRY(h, cudaMemsetAsync(h->d_flush, iter & 0xff, 256u << 20, h->stream));
+      CUDA_TRY(h, cudaEventRecord(h->it_ev[0], h->stream));
+    }
     // LevenbergMarquardtStrategy::ComputeStep: D = sqrt(clamp(diag(J'J)) / radius)
     VC_TRY(compute_diag(h, h->cur, 1, 1.0 / radius, h->d_scale + np));
     VC_TRY(solve_and_update(h, h->cur));
     VC_TRY(evaluate_into(h, 1 - h->cur, true));
+    if (h->flush_l2) {
+      CUDA_TRY(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, kScCount * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaEventRecord(h->it_ev[1], h->stream));
+    }
     VC_TRY(read_scalars(h));
+    if (h->flush_l2) {
+      float ims = 0;
+      CUDA_TRY(h, cudaEventElapsedTime(&ims, h->it_ev[0], h->it_ev[1]));
+      flushed_ms += ims;
+    }
     const double* sc = h->h_scalars;
     std::memset(&it, 0, sizeof it);
     it.iteration = iter; it.cost = cost; it.gradient_max_norm = gmax; it.trust_region_radius = radius;
@@ -686,7 +779,7 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
   CUDA_TRY(h, cudaEventSynchronize(h->ev1));
   float ms = 0;
   CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  sum.device_seconds = ms * 1e-3;
+  sum.device_seconds = (h->flush_l2 ? flushed_ms : ms) * 1e-3;
   sum.termination = term;
   sum.final_cost = cost;
   sum.kernel_launches = static_cast<int>(h->launches - launches0);
