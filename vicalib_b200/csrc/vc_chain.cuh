@@ -1,0 +1,375 @@
+// Block-tridiagonal + arrow solve for the inertial problem.
+//
+// With IMU factors the frame block of J^T J is block tridiagonal (each factor couples frames j-1, j;
+// vicalibrator.h:628-632) and every frame also couples to the dense global block.  The reference
+// hands this to a sparse Cholesky inside ceres::Solve.  Here the chain is eliminated by recursive
+// partitioning: every c-th node of a level is a separator, the c-1 nodes between two separators are
+// eliminated by one CTA (block Thomas sweep with the couplings to both separators, the global columns
+// and the gradient as right-hand sides), which leaves a chain of separators c times shorter.  After
+// ~log_c(n) levels the few remaining nodes join the globals in one dense Cholesky; back-substitution
+// walks the levels in reverse.  The same structure shards across GPUs (a rank's first frame is a
+// separator at every level), which is why it is preferred to a sequential sweep.
+#pragma once
+#include "vc_internal.h"
+
+namespace vc {
+
+struct ChainLevel {
+  int n;
+  double *A, *U, *E, *g;        // node blocks: A[n][FD*FD], U[i] = H[i-1,i], E[n][FD*G], g[n][FD]
+  double *addA, *addE, *addg;   // Schur contributions from the chunk on the node's left (null on level 0)
+  double* Z;                    // [n][FD][2FD+G+1]: eliminated nodes' solutions against [L | R | E | g]
+  int32_t* orig;                // original frame index of each node
+};
+
+constexpr int kChainThreads = 128;
+
+// level 0 from the block normal equations: scaled + damped
+template <int FD>
+__global__ void chain_init_kernel(DevProblem dp, Blocks b, const double* scale, const double* D2, ChainLevel L) {
+  const int G = dp.G, f = blockIdx.x, tid = threadIdx.x;
+  const double* sf = scale + static_cast<int64_t>(f) * FD;
+  const double* sc = scale + static_cast<int64_t>(dp.n_frames) * FD;
+  for (int e = tid; e < FD * FD; e += blockDim.x) {
+    const int r = e / FD, c = e - r * FD;
+    double v = b.B[static_cast<int64_t>(f) * FD * FD + e] * sf[r] * sf[c];
+    if (r == c) v += D2[static_cast<int64_t>(f) * FD + r];
+    L.A[static_cast<int64_t>(f) * FD * FD + e] = v;
+    double u = 0.0;
+    if (f > 0) u = b.U[static_cast<int64_t>(f) * FD * FD + e] * scale[static_cast<int64_t>(f - 1) * FD + r] * sf[c];
+    L.U[static_cast<int64_t>(f) * FD * FD + e] = u;
+  }
+  for (int e = tid; e < FD * G; e += blockDim.x) {
+    const int r = e / G, c = e - r * G;
+    L.E[static_cast<int64_t>(f) * FD * G + e] = b.E[static_cast<int64_t>(f) * FD * G + e] * sf[r] * sc[c];
+  }
+  for (int e = tid; e < FD; e += blockDim.x) L.g[static_cast<int64_t>(f) * FD + e] = b.gf[static_cast<int64_t>(f) * FD + e] * sf[e];
+  if (tid == 0) L.orig[f] = f;
+}
+
+struct ElimArgs {
+  int G, c;
+  ChainLevel cur, next;
+  double* Spart;  // [gridDim][G*G+G]
+  double* scalars;
+};
+
+template <int FD>
+__global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs a) {
+  extern __shared__ double sm[];
+  const int G = a.G, c = a.c, tid = threadIdx.x, NS = G * G + G;
+  const int w = 2 * FD + G + 1, VW = FD + w;
+  const int oL = FD, oR = 2 * FD, oE = 3 * FD, og = 3 * FD + G;  // column offsets inside a V row
+  double* Sacc = sm;                       // [NS]
+  double* Al = Sacc + NS;                  // [FD*FD]
+  double* El = Al + FD * FD;               // [FD*G]
+  double* gl = El + FD * G;                // [FD]
+  double* Ap = gl + FD;                    // [FD*FD] pivot / its Cholesky factor
+  double* Uc = Ap + FD * FD;               // [FD*FD] U[p]
+  double* V = Uc + FD * FD;                // [(c-1)][FD][VW]
+  __shared__ int bad;
+  const ChainLevel& L = a.cur;
+  const int j = blockIdx.x, s = j * c, n = L.n;
+  const bool hasR = s + c < n;
+  const int m = min(c - 1, n - 1 - s);
+  const bool add = L.addA != nullptr;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < NS; e += kChainThreads) Sacc[e] = 0.0;
+  for (int e = tid; e < FD * FD; e += kChainThreads)
+    Al[e] = L.A[static_cast<int64_t>(s) * FD * FD + e] + (add ? L.addA[static_cast<int64_t>(s) * FD * FD + e] : 0.0);
+  for (int e = tid; e < FD * G; e += kChainThreads)
+    El[e] = L.E[static_cast<int64_t>(s) * FD * G + e] + (add ? L.addE[static_cast<int64_t>(s) * FD * G + e] : 0.0);
+  for (int e = tid; e < FD; e += kChainThreads)
+    gl[e] = L.g[static_cast<int64_t>(s) * FD + e] + (add ? L.addg[static_cast<int64_t>(s) * FD + e] : 0.0);
+  __syncthreads();
+  // ---- forward sweep
+  for (int i = 0; i < m; ++i) {
+    const int64_t p = s + 1 + i;
+    double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+    for (int e = tid; e < FD * FD; e += kChainThreads) {
+      const int r = e / FD, q = e - r * FD;
+      Ap[e] = L.A[p * FD * FD + e] + (add ? L.addA[p * FD * FD + e] : 0.0);
+      Uc[e] = L.U[p * FD * FD + e];
+      const bool lastI = i == m - 1;
+      const double unext = (!lastI || hasR) ? L.U[(p + 1) * FD * FD + e] : 0.0;  // H[p, p+1]
+      Vi[r * VW + q] = lastI ? 0.0 : unext;
+      Vi[r * VW + oR + q] = (lastI && hasR) ? unext : 0.0;
+      Vi[r * VW + oL + q] = i == 0 ? L.U[p * FD * FD + q * FD + r] : 0.0;  // H[p0, s] = U[p0]^T
+    }
+    for (int e = tid; e < FD * G; e += kChainThreads) {
+      const int r = e / G, q = e - r * G;
+      Vi[r * VW + oE + q] = L.E[p * FD * G + e] + (add ? L.addE[p * FD * G + e] : 0.0);
+    }
+    for (int e = tid; e < FD; e += kChainThreads) Vi[e * VW + og] = L.g[p * FD + e] + (add ? L.addg[p * FD + e] : 0.0);
+    __syncthreads();
+    if (i > 0) {
+      const double* Vp = V + static_cast<int64_t>(i - 1) * FD * VW;
+      // A'_i = A_i - U^T V_U(i-1);  R'_i = R_i - U^T V_R(i-1)
+      for (int e = tid; e < FD * VW; e += kChainThreads) {
+        const int r = e / VW, q = e - r * VW;
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < FD; ++k) sum += Uc[k * FD + r] * Vp[k * VW + q];
+        if (q < FD) Ap[r * FD + q] -= sum;
+        else Vi[r * VW + q] -= sum;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      for (int jj = 0; jj < FD; ++jj) {
+        double d = Ap[jj * FD + jj];
+        for (int k = 0; k < jj; ++k) d -= Ap[jj * FD + k] * Ap[jj * FD + k];
+        if (!(d > 0.0)) { bad = 1; d = 1.0; }
+        d = sqrt(d);
+        Ap[jj * FD + jj] = d;
+        for (int ii = jj + 1; ii < FD; ++ii) {
+          double t = Ap[ii * FD + jj];
+          for (int k = 0; k < jj; ++k) t -= Ap[ii * FD + k] * Ap[jj * FD + k];
+          Ap[ii * FD + jj] = t / d;
+        }
+      }
+    }
+    __syncthreads();
+    for (int q = tid; q < VW; q += kChainThreads) {
+      double x[FD];
+#pragma unroll
+      for (int ii = 0; ii < FD; ++ii) {
+        double t = Vi[ii * VW + q];
+#pragma unroll
+        for (int k = 0; k < ii; ++k) t -= Ap[ii * FD + k] * x[k];
+        x[ii] = t / Ap[ii * FD + ii];
+      }
+#pragma unroll
+      for (int ii = FD - 1; ii >= 0; --ii) {
+        double t = x[ii];
+#pragma unroll
+        for (int k = ii + 1; k < FD; ++k) t -= Ap[k * FD + ii] * x[k];
+        x[ii] = t / Ap[ii * FD + ii];
+      }
+#pragma unroll
+      for (int ii = 0; ii < FD; ++ii) Vi[ii * VW + q] = x[ii];
+    }
+    __syncthreads();
+  }
+  // ---- backward sweep: X_i = V_R(i) - V_U(i) X_{i+1}
+  for (int i = m - 2; i >= 0; --i) {
+    double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+    const double* Vn = V + static_cast<int64_t>(i + 1) * FD * VW;
+    for (int e = tid; e < FD * w; e += kChainThreads) {
+      const int r = e / w, q = FD + (e - r * w);
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < FD; ++k) sum += Vi[r * VW + k] * Vn[k * VW + q];
+      Vi[r * VW + q] -= sum;
+    }
+    __syncthreads();
+  }
+  // ---- store Z, accumulate the Schur terms
+  for (int i = 0; i < m; ++i) {
+    const int64_t p = s + 1 + i;
+    const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+    for (int e = tid; e < FD * w; e += kChainThreads) {
+      const int r = e / w, q = e - r * w;
+      L.Z[(p * FD + r) * w + q] = Vi[r * VW + FD + q];
+    }
+    // S += E_i^T X_i[E], rhs += E_i^T X_i[g]  (E_i = the node's own global coupling)
+    for (int e = tid; e < NS; e += kChainThreads) {
+      const int ra = e < G * G ? e / G : e - G * G;
+      const int cb = e < G * G ? oE + (e - ra * G) : og;
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < FD; ++k) {
+        const double ek = L.E[p * FD * G + k * G + ra] + (add ? L.addE[p * FD * G + k * G + ra] : 0.0);
+        sum += ek * Vi[k * VW + cb];
+      }
+      Sacc[e] += sum;
+    }
+  }
+  if (m > 0) {
+    const double* X0 = V;                                          // node s+1
+    const double* Xl = V + static_cast<int64_t>(m - 1) * FD * VW;  // last interior node
+    const double* U0 = L.U + static_cast<int64_t>(s + 1) * FD * FD;  // H[s, s+1]
+    const double* Ur = hasR ? L.U + static_cast<int64_t>(s + c) * FD * FD : nullptr;  // H[s+c-1, s+c]
+    __syncthreads();
+    for (int e = tid; e < FD * w; e += kChainThreads) {
+      const int r = e / w, q = e - r * w;  // q indexes [L | R | E | g]
+      double sl = 0.0, sr = 0.0;
+#pragma unroll
+      for (int k = 0; k < FD; ++k) {
+        sl += U0[r * FD + k] * X0[k * VW + FD + q];
+        if (hasR) sr += Ur[k * FD + r] * Xl[k * VW + FD + q];
+      }
+      if (q < FD) {
+        Al[r * FD + q] -= sl;                                        // A_s -= H[s,p0] Z_L
+      } else if (q < 2 * FD) {
+        if (hasR) {
+          a.next.U[static_cast<int64_t>(j + 1) * FD * FD + r * FD + (q - FD)] = -sl;     // fill H[s, s+c]
+          a.next.addA[static_cast<int64_t>(j + 1) * FD * FD + r * FD + (q - FD)] = -sr;  // A_{s+c} -= H[r,pl] Z_R
+        }
+      } else if (q < 2 * FD + G) {
+        El[r * G + (q - 2 * FD)] -= sl;
+        if (hasR) a.next.addE[static_cast<int64_t>(j + 1) * FD * G + r * G + (q - 2 * FD)] = -sr;
+      } else {
+        gl[r] -= sl;
+        if (hasR) a.next.addg[static_cast<int64_t>(j + 1) * FD + r] = -sr;
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < FD * FD; e += kChainThreads) {
+    a.next.A[static_cast<int64_t>(j) * FD * FD + e] = Al[e];
+    if (j == 0) { a.next.U[e] = 0.0; a.next.addA[e] = 0.0; }
+  }
+  for (int e = tid; e < FD * G; e += kChainThreads) {
+    a.next.E[static_cast<int64_t>(j) * FD * G + e] = El[e];
+    if (j == 0) a.next.addE[e] = 0.0;
+  }
+  for (int e = tid; e < FD; e += kChainThreads) {
+    a.next.g[static_cast<int64_t>(j) * FD + e] = gl[e];
+    if (j == 0) a.next.addg[e] = 0.0;
+  }
+  if (tid == 0) {
+    a.next.orig[j] = L.orig[s];
+    if (bad) a.scalars[7] = 1.0;  // kScNotPD
+  }
+  double* out = a.Spart + static_cast<int64_t>(j) * NS;
+  for (int e = tid; e < NS; e += kChainThreads) out[e] = Sacc[e];
+}
+
+// sum of the per-CTA Schur partials (coalesced across entries)
+__global__ void sum_partials_kernel(const double* part, int n_part, int NS, double* out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NS) return;
+  double s = 0.0;
+  for (int b = 0; b < n_part; ++b) s += part[static_cast<int64_t>(b) * NS + e];
+  out[e] = s;
+}
+
+// dense solve of [globals | top-level chain nodes]
+struct DenseArgs {
+  DevProblem dp;
+  Blocks b;
+  const double* scale;
+  const double* D2;
+  const double* Ssum;  // [G*G+G] summed Schur partials
+  ChainLevel top;      // n may be 0
+  double* delta;
+  double* scalars;
+};
+template <int FD>
+__global__ void __launch_bounds__(256) dense_solve_kernel(DenseArgs a) {
+  extern __shared__ double sm[];
+  const int G = a.dp.G, nt = a.top.n, N = G + nt * FD, tid = threadIdx.x;
+  double* S = sm;          // [N*N]
+  double* rhs = sm + N * N;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  const int64_t nfp = static_cast<int64_t>(a.dp.n_frames) * a.dp.fd;
+  const double* sc = a.scale + nfp;
+  for (int e = tid; e < N * N; e += 256) S[e] = 0.0;
+  __syncthreads();
+  for (int e = tid; e < G * G + G; e += 256) {
+    if (e < G * G) {
+      const int r = e / G, c = e - r * G;
+      double v = a.b.C[e] * sc[r] * sc[c] - a.Ssum[e];
+      if (r == c) v += a.D2[nfp + r];
+      S[r * N + c] = v;
+    } else {
+      const int r = e - G * G;
+      rhs[r] = -a.b.gc[r] * sc[r] + a.Ssum[e];
+    }
+  }
+  const bool add = a.top.addA != nullptr;
+  for (int t = 0; t < nt; ++t) {
+    const int o = G + t * FD;
+    for (int e = tid; e < FD * FD; e += 256) {
+      const int r = e / FD, c = e - r * FD;
+      S[(o + r) * N + o + c] = a.top.A[static_cast<int64_t>(t) * FD * FD + e] + (add ? a.top.addA[static_cast<int64_t>(t) * FD * FD + e] : 0.0);
+      if (t > 0) {
+        const double u = a.top.U[static_cast<int64_t>(t) * FD * FD + e];  // H[t-1, t]
+        S[(o - FD + r) * N + o + c] = u;
+        S[(o + c) * N + o - FD + r] = u;
+      }
+    }
+    for (int e = tid; e < FD * G; e += 256) {
+      const int r = e / G, c = e - r * G;
+      const double v = a.top.E[static_cast<int64_t>(t) * FD * G + e] + (add ? a.top.addE[static_cast<int64_t>(t) * FD * G + e] : 0.0);
+      S[(o + r) * N + c] = v;
+      S[c * N + o + r] = v;
+    }
+    for (int e = tid; e < FD; e += 256)
+      rhs[o + e] = -(a.top.g[static_cast<int64_t>(t) * FD + e] + (add ? a.top.addg[static_cast<int64_t>(t) * FD + e] : 0.0));
+  }
+  __syncthreads();
+  for (int j = 0; j < N; ++j) {
+    if (tid == 0) {
+      double d = S[j * N + j];
+      if (!(d > 0.0)) { bad = 1; d = 1.0; }
+      S[j * N + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double dj = S[j * N + j];
+    for (int i = j + 1 + tid; i < N; i += 256) S[i * N + j] /= dj;
+    __syncthreads();
+    const int rem = N - j - 1;
+    for (int e = tid; e < rem * rem; e += 256) {
+      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+      if (k <= i) S[i * N + k] -= S[i * N + j] * S[k * N + j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < N; ++i) {
+      double s = rhs[i];
+      for (int k = 0; k < i; ++k) s -= S[i * N + k] * rhs[k];
+      rhs[i] = s / S[i * N + i];
+    }
+    for (int i = N - 1; i >= 0; --i) {
+      double s = rhs[i];
+      for (int k = i + 1; k < N; ++k) s -= S[k * N + i] * rhs[k];
+      rhs[i] = s / S[i * N + i];
+    }
+    if (bad) a.scalars[7] = 1.0;
+  }
+  __syncthreads();
+  for (int i = tid; i < G; i += 256) a.delta[nfp + i] = bad ? 0.0 : rhs[i];
+  for (int e = tid; e < nt * FD; e += 256) {
+    const int t = e / FD, r = e - t * FD;
+    a.delta[static_cast<int64_t>(a.top.orig[t]) * FD + r] = bad ? 0.0 : rhs[G + e];
+  }
+}
+
+// back-substitution of one level: x_p = -Z_g - Z_L x_left - Z_R x_right - Z_E dc
+struct BacksubArgs {
+  int G, c, nfp_off;  // nfp_off unused
+  ChainLevel cur;
+  double* delta;
+  int64_t nfp;
+};
+template <int FD>
+__global__ void __launch_bounds__(128) chain_backsub_kernel(BacksubArgs a) {
+  const int G = a.G, c = a.c, w = 2 * FD + G + 1;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 4 + (threadIdx.x >> 5);  // node index at this level
+  if (p >= a.cur.n || p % c == 0) return;              // separators are solved at the next level
+  const int s = (p / c) * c, r = s + c;
+  const double* xl = a.delta + static_cast<int64_t>(a.cur.orig[s]) * FD;
+  const double* xr = r < a.cur.n ? a.delta + static_cast<int64_t>(a.cur.orig[r]) * FD : nullptr;
+  const double* dc = a.delta + a.nfp;
+  const double* Z = a.cur.Z + static_cast<int64_t>(p) * FD * w;
+  double* out = a.delta + static_cast<int64_t>(a.cur.orig[p]) * FD;
+#pragma unroll
+  for (int rr = 0; rr < FD; ++rr) {
+    const double* z = Z + rr * w;
+    double sum = 0.0;
+    for (int q = lane; q < w - 1; q += 32) {
+      const double x = q < FD ? xl[q] : q < 2 * FD ? (xr ? xr[q - FD] : 0.0) : dc[q - 2 * FD];
+      sum += z[q] * x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) out[rr] = -z[w - 1] - sum;
+  }
+}
+
+}  // namespace vc

@@ -1,0 +1,238 @@
+// Host-side orchestration of the inertial path (included by vcgpu.cu after its helper macros).
+
+struct ImuDevHost {
+  double* cost = nullptr;   // [ni] per-interval robust cost
+  double* Cg = nullptr;     // [nf][kImuCgStride] per-interval global blocks
+  double* ftime = nullptr;  // [nf]
+  vc::imu::ImuBuf buf{};
+  std::vector<vc::ChainLevel> levels;
+  double* pool = nullptr;
+  int32_t* ipool = nullptr;
+  double* Ssum = nullptr;
+  int n_part = 0;
+};
+namespace vc { using ImuDev = ::ImuDevHost; }
+
+constexpr int kChainC = 4;    // chunk length: every 4th node of a level is a separator
+constexpr int kChainTop = 4;  // levels with <= this many nodes join the dense solve
+
+static vc::ImuDev* imu_dev(vcgpu_handle* h) { return static_cast<vc::ImuDev*>(h->imu); }
+
+static void imu_free(vcgpu_handle* h) {
+  vc::ImuDev* d = imu_dev(h);
+  if (!d) return;
+  dev_free(&d->cost); dev_free(&d->Cg); dev_free(&d->ftime); dev_free(&d->pool); dev_free(&d->ipool);
+  dev_free(&d->Ssum);
+  delete d;
+  h->imu = nullptr;
+}
+
+static int imu_prepare(vcgpu_handle* h) {
+  imu_free(h);
+  const DevProblem& dp = h->dp;
+  if (!dp.inertial) return VCGPU_OK;
+  if (dp.n_frames < 2) return fail(h, VCGPU_ERR_INVALID, "inertial terms need at least two frames");
+  vc::ImuDev* d = new vc::ImuDev();
+  h->imu = d;
+  const int nf = dp.n_frames, ni = nf - 1, G = dp.G, FD = 9;
+  const int n = static_cast<int>(h->h_imu_t.size());
+  // IMU samples SoA + the reference's running statistics (interpolation-buffer.h:70-85)
+  std::vector<double> buf(7 * std::max(n, 1));
+  double avg = 0.0;
+  for (int i = 0; i < n; ++i) {
+    buf[i] = h->h_imu_t[i];
+    for (int k = 0; k < 3; ++k) {
+      buf[static_cast<size_t>(1 + k) * n + i] = h->h_imu_w[3 * i + k];
+      buf[static_cast<size_t>(4 + k) * n + i] = h->h_imu_a[3 * i + k];
+    }
+    const double dt = i > 0 ? h->h_imu_t[i] - h->h_imu_t[i - 1] : 0.0;
+    avg = (avg * i + dt) / (i + 1);
+  }
+  VC_TRY(dev_alloc(h, &h->d_imu, buf.size()));
+  CUDA_TRY(h, cudaMemcpy(h->d_imu, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h->n_imu = n;
+  d->buf.d = h->d_imu;
+  d->buf.n = n;
+  d->buf.start_time = n ? h->h_imu_t.front() : -1.0;
+  d->buf.end_time = n ? h->h_imu_t.back() : -1.0;
+  d->buf.average_dt = avg;
+  VC_TRY(dev_alloc(h, &d->ftime, nf));
+  CUDA_TRY(h, cudaMemcpy(d->ftime, h->h_time.data(), nf * sizeof(double), cudaMemcpyHostToDevice));
+  // weights start at 500*I (vicalibrator.h:616)
+  std::vector<double> w(static_cast<size_t>(ni) * 81, 0.0);
+  for (int k = 0; k < ni; ++k)
+    for (int i = 0; i < 9; ++i) w[static_cast<size_t>(k) * 81 + i * 10] = 500.0;
+  VC_TRY(dev_alloc(h, &h->d_wsqrt, w.size()));
+  CUDA_TRY(h, cudaMemcpy(h->d_wsqrt, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+  VC_TRY(dev_alloc(h, &h->d_imu_r, static_cast<size_t>(ni) * 9));
+  VC_TRY(dev_alloc(h, &h->d_imu_J, static_cast<size_t>(ni) * 297));
+  VC_TRY(dev_alloc(h, &d->cost, ni));
+  VC_TRY(dev_alloc(h, &d->Cg, static_cast<size_t>(nf) * kImuCgStride));
+  CUDA_TRY(h, cudaMemset(d->Cg, 0, static_cast<size_t>(nf) * kImuCgStride * sizeof(double)));
+  // chain levels
+  const size_t w_cols = 2 * FD + G + 1;
+  std::vector<int> sizes;
+  for (int m = nf;; m = (m + kChainC - 1) / kChainC) {
+    sizes.push_back(m);
+    if (m <= kChainTop) break;
+  }
+  size_t total = 0, itotal = 0;
+  int n_part = 0;
+  for (size_t l = 0; l < sizes.size(); ++l) {
+    const size_t m = sizes[l];
+    total += m * (2 * FD * FD + FD * G + FD);
+    if (l > 0) total += m * (FD * FD + FD * G + FD);
+    if (l + 1 < sizes.size()) { total += m * FD * w_cols; n_part += (static_cast<int>(m) + kChainC - 1) / kChainC; }
+    itotal += m;
+  }
+  VC_TRY(dev_alloc(h, &d->pool, total));
+  VC_TRY(dev_alloc(h, &d->ipool, itotal));
+  double* p = d->pool;
+  int32_t* ip = d->ipool;
+  d->levels.resize(sizes.size());
+  for (size_t l = 0; l < sizes.size(); ++l) {
+    const size_t m = sizes[l];
+    vc::ChainLevel& L = d->levels[l];
+    L.n = static_cast<int>(m);
+    L.A = p; p += m * FD * FD;
+    L.U = p; p += m * FD * FD;
+    L.E = p; p += m * FD * G;
+    L.g = p; p += m * FD;
+    L.addA = L.addE = L.addg = nullptr;
+    if (l > 0) {
+      L.addA = p; p += m * FD * FD;
+      L.addE = p; p += m * FD * G;
+      L.addg = p; p += m * FD;
+    }
+    L.Z = nullptr;
+    if (l + 1 < sizes.size()) { L.Z = p; p += m * FD * w_cols; }
+    L.orig = ip; ip += m;
+  }
+  d->n_part = n_part;
+  const size_t NS = static_cast<size_t>(G) * G + G;
+  if (static_cast<size_t>(std::max(n_part, 1)) > static_cast<size_t>(h->n_solve_blocks)) {
+    VC_TRY(dev_alloc(h, &h->d_Spart, static_cast<size_t>(n_part) * NS));
+  }
+  VC_TRY(dev_alloc(h, &d->Ssum, NS));
+  return VCGPU_OK;
+}
+
+static int imu_evaluate(vcgpu_handle* h, int buf, bool apply_loss, int* n_cost, const double* mask_dev = nullptr) {
+  vc::ImuDev* d = imu_dev(h);
+  const DevProblem& dp = h->dp;
+  const int ni = dp.n_frames - 1;
+  ImuEvalArgs a;
+  a.dp = dp; a.buf = d->buf; a.state = h->d_state[buf]; a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
+  a.mask = (mask_dev ? mask_dev : h->d_mask) + dp.imu_goff;
+  a.r = h->d_imu_r; a.J = h->d_imu_J; a.cost = d->cost; a.ni = ni; a.apply_loss = apply_loss ? 1 : 0;
+  a.mult = dp.imu_mult;
+  imu_eval_kernel<<<(ni + kImuWarps - 1) / kImuWarps, 32 * kImuWarps, 0, h->stream>>>(a);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  *n_cost = ni;
+  return VCGPU_OK;
+}
+static const double* imu_cost_part(vcgpu_handle* h) { return imu_dev(h) ? imu_dev(h)->cost : nullptr; }
+
+static int imu_accumulate(vcgpu_handle* h, int buf) {
+  vc::ImuDev* d = imu_dev(h);
+  ImuAccArgs a;
+  a.dp = h->dp; a.r = h->d_imu_r; a.J = h->d_imu_J; a.out = h->blk[buf]; a.Cg = d->Cg; a.ni = h->dp.n_frames - 1;
+  imu_accumulate_kernel<<<h->dp.n_frames, 128, 0, h->stream>>>(a);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+static int imu_reduce_globals(vcgpu_handle* h) {
+  vc::ImuDev* d = imu_dev(h);
+  ImuReduceArgs a;
+  a.dp = h->dp; a.Cg = d->Cg; a.Cpart = h->d_Cpart; a.ni = h->dp.n_frames - 1;
+  imu_reduce_globals_kernel<<<kReduceBlocks, 256, 0, h->stream>>>(a);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+// forward elimination of the frame chain + dense solve; the step lands in d_delta
+static int imu_chain_solve(vcgpu_handle* h, int buf, const double* D2) {
+  vc::ImuDev* d = imu_dev(h);
+  const DevProblem& dp = h->dp;
+  constexpr int FD = 9;
+  const int G = dp.G;
+  const size_t NS = static_cast<size_t>(G) * G + G;
+  chain_init_kernel<FD><<<dp.n_frames, 128, 0, h->stream>>>(dp, h->blk[buf], h->d_scale, D2, d->levels[0]);
+  ++h->launches;
+  const size_t w_cols = 2 * FD + G + 1;
+  const size_t esm = (NS + 3 * FD * FD + FD * G + FD + static_cast<size_t>(kChainC - 1) * FD * (FD + w_cols)) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(h, cudaFuncSetAttribute(chain_eliminate_kernel<FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(h, cudaFuncSetAttribute(dense_solve_kernel<FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  int part = 0;
+  for (size_t l = 0; l + 1 < d->levels.size(); ++l) {
+    ElimArgs ea;
+    ea.G = G; ea.c = kChainC; ea.cur = d->levels[l]; ea.next = d->levels[l + 1];
+    ea.Spart = h->d_Spart + static_cast<size_t>(part) * NS; ea.scalars = h->d_scalars;
+    const int nsep = d->levels[l + 1].n;
+    chain_eliminate_kernel<FD><<<nsep, kChainThreads, esm, h->stream>>>(ea);
+    ++h->launches;
+    part += nsep;
+  }
+  sum_partials_kernel<<<static_cast<int>((NS + 255) / 256), 256, 0, h->stream>>>(h->d_Spart, part, static_cast<int>(NS), d->Ssum);
+  ++h->launches;
+  DenseArgs da;
+  da.dp = dp; da.b = h->blk[buf]; da.scale = h->d_scale; da.D2 = D2; da.Ssum = d->Ssum; da.top = d->levels.back();
+  da.delta = h->d_delta; da.scalars = h->d_scalars;
+  const size_t N = G + static_cast<size_t>(d->levels.back().n) * FD;
+  dense_solve_kernel<FD><<<1, 256, (N * N + N) * sizeof(double), h->stream>>>(da);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+// back-substitution through the levels (top-down), then x (+) delta
+static int imu_chain_backsub(vcgpu_handle* h, int buf, const double* D2) {
+  vc::ImuDev* d = imu_dev(h);
+  const DevProblem& dp = h->dp;
+  constexpr int FD = 9;
+  for (int l = static_cast<int>(d->levels.size()) - 2; l >= 0; --l) {
+    BacksubArgs ba;
+    ba.G = dp.G; ba.c = kChainC; ba.nfp_off = 0; ba.cur = d->levels[l]; ba.delta = h->d_delta;
+    ba.nfp = static_cast<int64_t>(dp.n_frames) * FD;
+    chain_backsub_kernel<FD><<<(d->levels[l].n + 3) / 4, 128, 0, h->stream>>>(ba);
+    ++h->launches;
+  }
+  UpdateArgs ua;
+  ua.dp = dp; ua.b = h->blk[buf]; ua.scale = h->d_scale; ua.D2 = D2; ua.X = nullptr; ua.delta = h->d_delta;
+  ua.x_cur = h->d_state[buf]; ua.x_new = h->d_state[1 - buf]; ua.step_part = h->d_red;
+  const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
+  backsub_update_kernel<9><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+static int imu_update_weights(vcgpu_handle* h, int buf) {
+  (void)buf;
+  return fail(h, VCGPU_ERR_INVALID, "UpdateImuWeights is not implemented on the device yet: set update_imu_weights = 0");
+}
+
+static int imu_eval_hook(vcgpu_handle* h, double* r, double* J) {
+  const DevProblem& dp = h->dp;
+  if (!dp.inertial) return fail(h, VCGPU_ERR_INVALID, "eval_imu: inertial flag is off");
+  const int ni = dp.n_frames - 1;
+  double* ones = nullptr;
+  VC_TRY(dev_alloc(h, &ones, dp.G));
+  std::vector<double> hones(dp.G, 1.0);
+  CUDA_TRY(h, cudaMemcpy(ones, hones.data(), dp.G * sizeof(double), cudaMemcpyHostToDevice));
+  int nc = 0;
+  VC_TRY(imu_evaluate(h, h->cur, false, &nc, ones));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(ones);
+  h->blocks_valid = false;
+  CUDA_TRY(h, cudaMemcpy(r, h->d_imu_r, static_cast<size_t>(ni) * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (J) CUDA_TRY(h, cudaMemcpy(J, h->d_imu_J, static_cast<size_t>(ni) * 297 * sizeof(double), cudaMemcpyDeviceToHost));
+  return VCGPU_OK;
+}

@@ -112,4 +112,5 @@ struct vcgpu_handle {
   double* d_wsqrt = nullptr;      // [(nf-1)][81]
   double* d_imu_r = nullptr;      // [(nf-1)][9]
   double* d_imu_J = nullptr;      // [(nf-1)][9*33]
+  void* imu = nullptr;            // ImuDevHost (vc_imu_host.inl)
 };

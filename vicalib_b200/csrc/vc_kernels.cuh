@@ -550,15 +550,20 @@ __global__ void __launch_bounds__(32 * kUpdateWarps) backsub_update_kernel(Updat
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const int f = blockIdx.x * kUpdateWarps + warp;
   if (f < nf) {
-    const double* Xf = a.X + static_cast<int64_t>(f) * FD * M;
     double d[FD];
+    if (a.X) {
+      const double* Xf = a.X + static_cast<int64_t>(f) * FD * M;
 #pragma unroll
-    for (int r = 0; r < FD; ++r) {
-      double s = 0.0;
-      for (int c = lane; c < G; c += 32) s += Xf[r * M + c] * dc[c];
+      for (int r = 0; r < FD; ++r) {
+        double s = 0.0;
+        for (int c = lane; c < G; c += 32) s += Xf[r * M + c] * dc[c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      d[r] = -Xf[r * M + G] - s;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        d[r] = -Xf[r * M + G] - s;
+      }
+    } else {  // the chain solver already wrote the frame step
+#pragma unroll
+      for (int r = 0; r < FD; ++r) d[r] = a.delta[static_cast<int64_t>(f) * FD + r];
     }
     if (lane == 0) {
       double du[FD];

@@ -15,6 +15,7 @@
 #include "vc_internal.h"
 #include "vc_kernels.cuh"
 #include "vc_imu.cuh"
+#include "vc_chain.cuh"
 
 using namespace vc;
 
@@ -50,6 +51,8 @@ static void dev_free(T** p) {
   if (*p) cudaFree(*p);
   *p = nullptr;
 }
+
+#include "vc_imu_host.inl"
 
 // ------------------------------------------------------------------ stage timers
 struct StageScope {
@@ -552,6 +555,7 @@ static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
     StageScope st(h, VCGPU_STAGE_REDUCE);
     reduce_globals_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
     ++h->launches;
+    if (dp.inertial) VC_TRY(imu_reduce_globals(h));
   }
   FinalizeArgs fa;
   fa.dp = dp; fa.Cpart = h->d_Cpart;
@@ -608,7 +612,7 @@ static int solve_and_update(vcgpu_handle* h, int buf) {
   GlobalSolveArgs ga;
   ga.dp = dp; ga.b = h->blk[buf]; ga.scale = h->d_scale; ga.D2 = D2; ga.Spart = h->d_Spart;
   ga.n_spart = h->n_solve_blocks; ga.delta = h->d_delta; ga.scalars = h->d_scalars;
-  {
+  if (!dp.inertial) {  // the chain path ends in its own dense solve (globals + top-level nodes)
     StageScope st(h, VCGPU_STAGE_GLOBAL_SOLVE);
     global_solve_kernel<<<1, 256, NS * sizeof(double), h->stream>>>(ga);
     ++h->launches;
