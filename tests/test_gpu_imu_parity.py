@@ -98,3 +98,29 @@ def test_lm_solve_with_imu_fixed_weights(models, flags):
     for k in ("T_wp", "v_w", "q_ck", "p_ck", "g", "b", "sf"):
         assert np.abs(st_g[k] - st_o[k]).max() <= 1e-6 * max(1.0, np.abs(st_o[k]).max()), k
     assert abs(st_g["ts"] - st_o["ts"]) <= 1e-8
+
+
+def test_update_imu_weights_matches_oracle():
+    """UpdateImuWeights KAT: per-interval 9x9 weight_sqrt_ for fixed inputs (vicalibrator.h:723-799)."""
+    p, o, g = _pair(models=("poly3",), n_frames=25, ts_truth=0.003)
+    o.update_imu_weights()
+    g.update_imu_weights()
+    W_o, W_g = o.imu_weights(), g.imu_weights()
+    assert np.abs(W_o - 500 * np.eye(9)).max() > 1.0  # it did change
+    for k in range(W_o.shape[0]):
+        assert np.abs(W_g[k] - W_o[k]).max() <= 1e-7 * np.abs(W_o[k]).max(), k
+    # rotation-only: weights must stay untouched (vicalibrator.h:725)
+    p, o, g = _pair(flags=STAGES[0])
+    g.update_imu_weights()
+    assert np.array_equal(g.imu_weights(), np.broadcast_to(500 * np.eye(9), (p.n_frames - 1, 9, 9)))
+
+
+def test_lm_solve_with_weight_updates():
+    p, o, g = _pair(models=("poly3", "poly3"), n_frames=40)
+    o.set_options(function_tol=1e-13, max_iters=25, update_imu_weights=1)
+    g.set_options(function_tol=1e-13, max_iters=25, update_imu_weights=1)
+    s_o, s_g = o.solve(), g.solve()
+    assert abs(s_g["final_cost"] - s_o["final_cost"]) <= 1e-6 * s_o["final_cost"]
+    st_o, st_g = o.state(), g.state()
+    for k in ("T_wp", "v_w", "q_ck", "p_ck", "g", "b", "sf", "intr"):
+        assert np.abs(st_g[k] - st_o[k]).max() <= 1e-6 * max(1.0, np.abs(st_o[k]).max()), k

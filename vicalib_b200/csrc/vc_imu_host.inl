@@ -214,9 +214,19 @@ static int imu_chain_backsub(vcgpu_handle* h, int buf, const double* D2) {
   return VCGPU_OK;
 }
 
+// UpdateImuWeights (vicalibrator.h:723-799): active only when inertial && !rotation_only (:725)
 static int imu_update_weights(vcgpu_handle* h, int buf) {
-  (void)buf;
-  return fail(h, VCGPU_ERR_INVALID, "UpdateImuWeights is not implemented on the device yet: set update_imu_weights = 0");
+  vc::ImuDev* d = imu_dev(h);
+  const DevProblem& dp = h->dp;
+  if (!dp.inertial || dp.rotation_only) return VCGPU_OK;
+  StageScope st(h, VCGPU_STAGE_IMU_WEIGHTS);
+  vc::wts::WeightArgs a;
+  a.dp = dp; a.buf = d->buf; a.state = h->d_state[buf]; a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
+  a.ni = dp.n_frames - 1; a.sigma_g = h->sigma_g; a.sigma_a = h->sigma_a;
+  vc::wts::imu_weights_kernel<<<(a.ni + vc::wts::kWtWarps - 1) / vc::wts::kWtWarps, 32 * vc::wts::kWtWarps, 0, h->stream>>>(a);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
 }
 
 static int imu_eval_hook(vcgpu_handle* h, double* r, double* J) {

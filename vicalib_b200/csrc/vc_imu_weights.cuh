@@ -1,0 +1,441 @@
+// UpdateImuWeights on the device: one warp per frame interval, small dense matrices in shared
+// memory, products shared across the lanes.
+//
+// Reference being reproduced (formulas AS WRITTEN, approximations included):
+//   ViCalibrator::UpdateImuWeights                        vicalibrator.h:723-799
+//   ImuResidualT::IntegratePose / GetPoseDerivative / IntegrateImu / IntegrateResidual
+//                                                         types.h:330-378, 380-425, 427-595, 611-687
+//   dLog_dq, dqExp_dw, dq1q2_dq2, dq1q2_dq1, dqx_dq, dt1t2_dt1, dLog_dSE3
+//                                                         vicalibrator-utils.h:106-154,187-202,214-230,234-274,307-434
+// Only values that reach an output are computed: per IMU step
+//   C <- A C A^T + G R G^T,  A = d y/d y0 (10x10), G = d y/d b (10x6) of the full RK4 step,
+// then info = (Jt C Jt^T)^-1 and W = sqrtm(info) (principal root by cyclic Jacobi, equal to
+// Eigen's MatrixFunctions sqrt for the symmetric positive definite info matrix).
+#pragma once
+#include "vc_imu_math.cuh"
+#include "vc_internal.h"
+
+namespace vc {
+namespace wts {
+
+using imu::Meas;
+using imu::Pose;
+using imu::Quat;
+using imu::Vec;
+
+// out[R x C] = alpha * A[R x K] * op(B) (+ out if acc); transB: B is stored [C x K]
+__device__ __forceinline__ void wmm(double* out, const double* A, const double* B, int R, int K, int C, int lane,
+                                    bool transB = false, bool acc = false, double alpha = 1.0) {
+  for (int e = lane; e < R * C; e += 32) {
+    const int r = e / C, c = e - r * C;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += A[r * K + k] * (transB ? B[c * K + k] : B[k * C + c]);
+    out[e] = acc ? out[e] + alpha * s : alpha * s;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void wzero(double* m, int n, int lane) {
+  for (int e = lane; e < n; e += 32) m[e] = 0.0;
+  __syncwarp();
+}
+__device__ __forceinline__ void wcopy(double* dst, const double* src, int n, int lane) {
+  for (int e = lane; e < n; e += 32) dst[e] = src[e];
+  __syncwarp();
+}
+__device__ __forceinline__ void waxpy(double* y, const double* x, double a, int n, int lane) {
+  for (int e = lane; e < n; e += 32) y[e] += a * x[e];
+  __syncwarp();
+}
+
+__device__ inline double powi(double x, int y) {  // vicalibrator-utils.h:69-82
+  double r = x;
+  for (int i = 1; i < y; ++i) r *= x;
+  return r;
+}
+
+// vicalibrator-utils.h:234-254 (3x4, row-major, ld = 4)
+__device__ inline void dqx_dq(Quat<double> q, Vec<double> v, double* o, int ld) {
+  const double x = v.x, y = v.y, z = v.z;
+  const double s1 = 2 * q.x * y, s2 = 2 * q.y * y, s3 = 2 * q.x * x, s4 = 2 * q.z * x, s5 = 2 * q.y * z, s6 = 2 * q.z * z;
+  o[0] = s2 + s6; o[1] = s1 - 4 * q.y * x + 2 * q.w * z; o[2] = 2 * q.x * z - 2 * q.w * y - 4 * q.z * x; o[3] = s5 - 2 * q.z * y;
+  o[ld + 0] = 2 * q.y * x - 4 * q.x * y - 2 * q.w * z; o[ld + 1] = s3 + s6; o[ld + 2] = s5 + 2 * q.w * x - 4 * q.z * y; o[ld + 3] = s4 - 2 * q.x * z;
+  o[2 * ld + 0] = s4 + 2 * q.w * y - 4 * q.x * z; o[2 * ld + 1] = 2 * q.z * y - 2 * q.w * x - 4 * q.y * z; o[2 * ld + 2] = s2 + s3; o[2 * ld + 3] = s1 - 2 * q.y * x;
+}
+// vicalibrator-utils.h:214-220 / 224-230 (4x4 with leading dimension ld)
+__device__ inline void dq1q2_dq2(Quat<double> q1, double* o, int ld) {
+  o[0] = q1.w; o[1] = -q1.z; o[2] = q1.y; o[3] = q1.x;
+  o[ld] = q1.z; o[ld + 1] = q1.w; o[ld + 2] = -q1.x; o[ld + 3] = q1.y;
+  o[2 * ld] = -q1.y; o[2 * ld + 1] = q1.x; o[2 * ld + 2] = q1.w; o[2 * ld + 3] = q1.z;
+  o[3 * ld] = -q1.x; o[3 * ld + 1] = -q1.y; o[3 * ld + 2] = -q1.z; o[3 * ld + 3] = q1.w;
+}
+__device__ inline void dq1q2_dq1(Quat<double> q2, double* o, int ld) {
+  o[0] = q2.w; o[1] = q2.z; o[2] = -q2.y; o[3] = q2.x;
+  o[ld] = -q2.z; o[ld + 1] = q2.w; o[ld + 2] = q2.x; o[ld + 3] = q2.y;
+  o[2 * ld] = q2.y; o[2 * ld + 1] = -q2.x; o[2 * ld + 2] = q2.w; o[2 * ld + 3] = q2.z;
+  o[3 * ld] = -q2.x; o[3 * ld + 1] = -q2.y; o[3 * ld + 2] = -q2.z; o[3 * ld + 3] = q2.w;
+}
+// vicalibrator-utils.h:187-202 (4x3)
+__device__ inline void dqExp_dw(Vec<double> w, double o[12]) {
+  const double t = sqrt(w.x * w.x + w.y * w.y + w.z * w.z);
+  const double s1 = t / 20 - 1, s2 = powi(t, 2) / 48 - 0.5;
+  const double s3 = (s1 * w.y * w.z) / 24, s4 = (s1 * w.x * w.z) / 24, s5 = (s1 * w.x * w.y) / 24, s6 = powi(t, 2);
+  o[0] = (s1 * powi(w.x, 2)) / 24 - s6 / 48 + 0.5; o[1] = s5; o[2] = s4;
+  o[3] = s5; o[4] = (s1 * powi(w.y, 2)) / 24 - s6 / 48 + 0.5; o[5] = s3;
+  o[6] = s4; o[7] = s3; o[8] = (s1 * powi(w.z, 2)) / 24 - s6 / 48 + 0.5;
+  o[9] = (s2 * w.x) / 2; o[10] = (s2 * w.y) / 2; o[11] = (s2 * w.z) / 2;
+}
+// vicalibrator-utils.h:106-154 (3x4)
+__device__ inline void dLog_dq(Quat<double> q, double o[12]) {
+  const double x = q.x, y = q.y, z = q.z, w = q.w;
+  const double vsq = powi(x, 2) + powi(y, 2) + powi(z, 2), vn = sqrt(vsq);
+  if (vn < 1e-9) {
+    const double s1 = 2 * vsq, s2 = 1.0 / powi(w, 3), s3 = (3 * s1) / powi(w, 4) - 2 / powi(w, 2), s4 = 2 / w;
+    o[0] = -4 * s2 * powi(x, 2) + s4 - s1 * s2; o[1] = -4 * x * y * s2; o[2] = -4 * x * z * s2; o[3] = x * s3;
+    o[4] = -4 * x * y * s2; o[5] = -4 * s2 * powi(y, 2) + s4 - s1 * s2; o[6] = -4 * y * z * s2; o[7] = y * s3;
+    o[8] = -4 * x * z * s2; o[9] = -4 * y * z * s2; o[10] = -4 * s2 * powi(z, 2) + s4 - s1 * s2; o[11] = z * s3;
+  } else {
+    const double s1 = vsq, s2 = 1 / (s1 / powi(w, 2) + 1), s3 = atan(sqrt(s1) / w), s4 = 1 / pow(s1, 1.5), s5 = 1 / s1,
+                 s6 = 1 / w, s7 = (2 * s3) / sqrt(s1);
+    const double s8 = 2 * y * z * s2 * s5 * s6 - 2 * y * z * s3 * s4;
+    const double s9 = 2 * x * z * s2 * s5 * s6 - 2 * x * z * s3 * s4;
+    const double s10 = 2 * x * y * s2 * s5 * s6 - 2 * x * y * s3 * s4;
+    o[0] = s7 - 2 * powi(x, 2) * s3 * s4 + 2 * powi(x, 2) * s2 * s5 * s6; o[1] = s10; o[2] = s9; o[3] = -(2 * x * s2) / powi(w, 2);
+    o[4] = s10; o[5] = s7 - 2 * powi(y, 2) * s3 * s4 + 2 * powi(y, 2) * s2 * s5 * s6; o[6] = s8; o[7] = -(2 * y * s2) / powi(w, 2);
+    o[8] = s9; o[9] = s8; o[10] = s7 - 2 * powi(z, 2) * s3 * s4 + 2 * powi(z, 2) * s2 * s5 * s6; o[11] = -(2 * z * s2) / powi(w, 2);
+  }
+}
+
+// vicalibrator-utils.h:307-434: dlog (6x7) for t = (q, tr); 7-vector = (translation 3, quaternion 4)
+__device__ inline void dLog_dSE3(Quat<double> q, Vec<double> tr, double dlog[42]) {
+  double dw_dq[12];
+  dLog_dq(q, dw_dq);
+  const double x = tr.x, y = tr.y, z = tr.z;
+  double theta;
+  const Vec<double> w = imu::so3_log<double>(q, &theta);
+  const double wx = w.x, wy = w.y, wz = w.z;
+  const bool close_to_zero = fabs(theta) < kSophusEps;
+  const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+  double O2[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += O[i * 3 + k] * O[k * 3 + j];
+      O2[i * 3 + j] = s;
+    }
+  const double cc = close_to_zero ? 1. / 12. : (1.0 - theta / (2.0 * tan(theta / 2.0))) / (theta * theta);
+  for (int i = 0; i < 42; ++i) dlog[i] = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) dlog[i * 7 + j] = (i == j ? 1.0 : 0.0) - 0.5 * O[i * 3 + j] + cc * O2[i * 3 + j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) dlog[(3 + i) * 7 + 3 + j] = dw_dq[i * 4 + j];
+  double d[9];
+  if (close_to_zero) {
+    const double div_12 = 1. / 12, div_6 = 1. / 6.;
+    const double wx_x = wx * x, wy_x = wy * x, wz_x = wz * x, wx_y = wx * y, wy_y = wy * y, wz_y = wz * y, wx_z = wx * z,
+                 wy_z = wy * z, wz_z = wz * z;
+    d[0] = div_12 * (wy_y + wz_z); d[1] = div_12 * wx_y - div_6 * wy_x - 0.5 * z; d[2] = 0.5 * y - div_6 * wz_x + div_12 * wx_z;
+    d[3] = 0.5 * z + div_12 * wy_x - div_6 * wx_y; d[4] = div_12 * (wx_x + wz_z); d[5] = div_12 * wy_z - div_6 * wz_y - 0.5 * x;
+    d[6] = div_12 * wz_x - div_6 * wx_z - 0.5 * y; d[7] = 0.5 * x + div_12 * wz_y - div_6 * wy_z; d[8] = div_12 * (wx_x * wy_y);
+  } else {
+    const double s1 = powi(wx, 2) + powi(wy, 2) + powi(wz, 2);
+    const double s2 = tan(sqrt(s1) / 2);
+    const double s3 = sqrt(s1) / (2 * s2) - 1;
+    const double s4 = wz / (2 * sqrt(s1) * s2) - (wz * (powi(s2, 2) + 1)) / (4 * powi(s2, 2));
+    const double s5 = wy / (2 * sqrt(s1) * s2) - (wy * (powi(s2, 2) + 1)) / (4 * powi(s2, 2));
+    const double s6 = wx / (2 * sqrt(s1) * s2) - (wx * (powi(s2, 2) + 1)) / (4 * powi(s2, 2));
+    const double s7 = 1 / s1, s8 = 1 / powi(s1, 2);
+    const double s9 = powi(wx, 2) + powi(wy, 2), s10 = powi(wx, 2) + powi(wz, 2), s11 = powi(wy, 2) + powi(wz, 2);
+    const double s12 = 2 * s3 * s8 * wx * wy * wz;
+    const double s13 = -2 * s3 * s8 * wy * powi(wz, 2) + s4 * s7 * wy * wz + s3 * s7 * wy;
+    const double s14 = -2 * s3 * s8 * wx * powi(wz, 2) + s4 * s7 * wx * wz + s3 * s7 * wx;
+    const double s15 = -2 * s3 * s8 * wz * powi(wy, 2) + s5 * s7 * wz * wy + s3 * s7 * wz;
+    const double s16 = -2 * s3 * s8 * wz * powi(wx, 2) + s6 * s7 * wz * wx + s3 * s7 * wz;
+    const double s17 = -2 * s3 * s8 * wx * powi(wy, 2) + s5 * s7 * wx * wy + s3 * s7 * wx;
+    const double s18 = -2 * s3 * s8 * wy * powi(wx, 2) + s6 * s7 * wy * wx + s3 * s7 * wy;
+    const double s19 = 2 * s3 * s7 * wy, s20 = 2 * s3 * s7 * wx;
+    d[0] = x * (s6 * s7 * s11 - 2 * s3 * s8 * s11 * wx) - s18 * y - s16 * z;
+    d[1] = x * (s19 + s5 * s7 * s11 - 2 * s3 * s8 * s11 * wy) - s17 * y - z * (s5 * s7 * wx * wz - 2 * s3 * s8 * wx * wy * wz + 0.5);
+    d[2] = x * (s4 * s7 * s11 + 2 * s3 * s7 * wz - 2 * s3 * s8 * s11 * wz) - s14 * z + y * (s12 - s4 * s7 * wx * wy + 0.5);
+    d[3] = y * (s20 + s6 * s7 * s10 - 2 * s3 * s8 * s10 * wx) - s18 * x + z * (s12 - s6 * s7 * wy * wz + 0.5);
+    d[4] = y * (s5 * s7 * s10 - 2 * s3 * s8 * s10 * wy) - s17 * x - s15 * z;
+    d[5] = y * (s4 * s7 * s10 + 2 * s3 * s7 * wz - 2 * s3 * s8 * s10 * wz) - s13 * z - x * (s4 * s7 * wx * wy - s12 + 0.5);
+    d[6] = z * (s20 + s6 * s7 * s9 - 2 * s3 * s8 * s9 * wx) - s16 * x - y * (s6 * s7 * wy * wz - s12 + 0.5);
+    d[7] = z * (s19 + s5 * s7 * s9 - 2 * s3 * s8 * s9 * wy) - s15 * y + x * (s12 - s5 * s7 * wx * wz + 0.5);
+    d[8] = z * (s4 * s7 * s9 - 2 * s3 * s8 * s9 * wz) - s14 * x - s13 * y;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += d[i * 3 + k] * dw_dq[k * 4 + j];
+      dlog[i * 7 + 3 + j] = s;
+    }
+}
+
+// per-warp shared workspace (doubles)
+struct Work {
+  double C[100], dy_db[60], dy_dy0[100], dk_db[54], dk_dy[90], dy_dk[90], dy_dy[100];
+  double T_db[54], T_dy[90], tot_db[54], tot_dy[90], t1[100], t2[100];
+};
+
+// GetPoseDerivative with Jacobians (types.h:380-425); every lane computes k, lane 0 fills the blocks
+__device__ inline void pose_derivative_jac(const Pose<double>& y, Vec<double> g, const Meas<double>& z0, const Meas<double>& z1,
+                                           Vec<double> bg, Vec<double> ba, const double sf[6], double dt, double k[9],
+                                           Work* W, int lane) {
+  imu::pose_derivative<double>(y, g, z0, z1, bg, ba, sf, dt, k);
+  wzero(W->dk_db, 54, lane);
+  wzero(W->dk_dy, 90, lane);
+  if (lane == 0) {
+    const double alpha = (z1.time - (z0.time + dt)) / (z1.time - z0.time);
+    const Vec<double> zg = imu::scale(z0.w, alpha) + imu::scale(z1.w, 1.0 - alpha);
+    const Vec<double> za = imu::scale(z0.a, alpha) + imu::scale(z1.a, 1.0 - alpha);
+    double R[9];
+    qmat(Q4{y.q.x, y.q.y, y.q.z, y.q.w}, R);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        W->dk_db[(3 + i) * 6 + j] = R[i * 3 + j];      // dw/dbg
+        W->dk_db[(6 + i) * 6 + 3 + j] = R[i * 3 + j];  // da/dba
+      }
+    for (int i = 0; i < 3; ++i) W->dk_dy[i * 10 + 7 + i] = 1.0;  // dv/dv
+    // dw/dq and da/dq use the UNSCALED measurements (the reference ignores sf here, types.h:413-423)
+    dqx_dq(y.q, zg + bg, W->dk_dy + 3 * 10 + 3, 10);
+    dqx_dq(y.q, za + ba, W->dk_dy + 6 * 10 + 3, 10);
+  }
+  __syncwarp();
+}
+// IntegratePose with Jacobians (types.h:330-378)
+__device__ inline Pose<double> integrate_pose_jac(const Pose<double>& y0, const double k[9], double dt, Work* W, int lane) {
+  const Vec<double> wdt{k[3] * dt, k[4] * dt, k[5] * dt};
+  wzero(W->dy_dk, 90, lane);
+  wzero(W->dy_dy, 100, lane);
+  if (lane == 0) {
+    const Quat<double> r = imu::so3_exp<double>(wdt);
+    double a[16], e[12];
+    dq1q2_dq1(y0.q, a, 4);
+    dqExp_dw(wdt, e);
+    for (int i = 0; i < 3; ++i) { W->dy_dk[i * 9 + i] = dt; W->dy_dk[(7 + i) * 9 + 6 + i] = dt; }
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double s = 0;
+        for (int q = 0; q < 4; ++q) s += a[i * 4 + q] * e[q * 3 + j];
+        W->dy_dk[(3 + i) * 9 + 3 + j] = s * dt;
+      }
+    for (int i = 0; i < 3; ++i) { W->dy_dy[i * 10 + i] = 1.0; W->dy_dy[(7 + i) * 10 + 7 + i] = 1.0; }
+    dq1q2_dq2(r, W->dy_dy + 3 * 10 + 3, 10);
+  }
+  __syncwarp();
+  return imu::integrate_pose<double>(y0, k, dt);
+}
+
+// one RK4 stage's bookkeeping: T = total derivative of k_n; accumulate into tot with weight wgt;
+// then (dy_db, dy_dy0) <- Jacobians of IntegratePose(pose, k_n, h)
+__device__ inline void stage_total(Work* W, double wgt, int lane) {
+  // T_db = dk_db + dk_dy * dy_db ; T_dy = dk_dy * dy_dy0
+  wcopy(W->T_db, W->dk_db, 54, lane);
+  wmm(W->T_db, W->dk_dy, W->dy_db, 9, 10, 6, lane, false, true);
+  wmm(W->T_dy, W->dk_dy, W->dy_dy0, 9, 10, 10, lane);
+  waxpy(W->tot_db, W->T_db, wgt, 54, lane);
+  waxpy(W->tot_dy, W->T_dy, wgt, 90, lane);
+}
+__device__ inline void stage_push(Work* W, const double* k_db, const double* k_dy, int lane) {
+  // dy_db = dy_dk * k_db ; dy_dy0 = dy_dy + dy_dk * k_dy
+  wmm(W->dy_db, W->dy_dk, k_db, 10, 9, 6, lane);
+  wcopy(W->dy_dy0, W->dy_dy, 100, lane);
+  wmm(W->dy_dy0, W->dy_dk, k_dy, 10, 9, 10, lane, false, true);
+}
+
+// IntegrateImu, Jacobian + covariance branch (types.h:427-595): C <- A C A^T + G R G^T
+__device__ inline Pose<double> integrate_imu_cov(const Pose<double>& pose, const Meas<double>& z0, const Meas<double>& z1,
+                                                 Vec<double> bg, Vec<double> ba, const double sf[6], Vec<double> g,
+                                                 double sg2, double sa2, Work* W, int lane) {
+  const double dt = z1.time - z0.time;
+  if (dt == 0) return pose;  // degenerate step: identity map (the reference leaves its outputs untouched)
+  double k1[9], k2[9], k3[9], k4[9], k[9];
+  wzero(W->dy_db, 60, lane);
+  wzero(W->dy_dy0, 100, lane);
+  wzero(W->tot_db, 54, lane);
+  wzero(W->tot_dy, 90, lane);
+  if (lane < 10) W->dy_dy0[lane * 11] = 1.0;
+  __syncwarp();
+  pose_derivative_jac(pose, g, z0, z1, bg, ba, sf, 0.0, k1, W, lane);
+  stage_total(W, 1.0, lane);
+  const Pose<double> y1 = integrate_pose_jac(pose, k1, dt * 0.5, W, lane);
+  stage_push(W, W->T_db, W->T_dy, lane);
+  pose_derivative_jac(y1, g, z0, z1, bg, ba, sf, dt / 2, k2, W, lane);
+  stage_total(W, 2.0, lane);
+  const Pose<double> y2 = integrate_pose_jac(pose, k2, dt * 0.5, W, lane);
+  stage_push(W, W->T_db, W->T_dy, lane);
+  pose_derivative_jac(y2, g, z0, z1, bg, ba, sf, dt / 2, k3, W, lane);
+  stage_total(W, 2.0, lane);
+  const Pose<double> y3 = integrate_pose_jac(pose, k3, dt, W, lane);
+  stage_push(W, W->T_db, W->T_dy, lane);
+  pose_derivative_jac(y3, g, z0, z1, bg, ba, sf, dt, k4, W, lane);
+  stage_total(W, 1.0, lane);
+  for (int i = 0; i < 9; ++i) k[i] = k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i];
+  const Pose<double> res = integrate_pose_jac(pose, k, dt / 6.0, W, lane);
+  stage_push(W, W->tot_db, W->tot_dy, lane);
+  // C = dy_dy0 C dy_dy0^T + dy_db R dy_db^T, R = diag(sg2 x3, sa2 x3)
+  wmm(W->t1, W->dy_dy0, W->C, 10, 10, 10, lane);
+  wmm(W->t2, W->t1, W->dy_dy0, 10, 10, 10, lane, true);
+  for (int e = lane; e < 100; e += 32) {
+    const int r = e / 10, c = e - r * 10;
+    double s = 0.0;
+    for (int q = 0; q < 6; ++q) s += W->dy_db[r * 6 + q] * (q < 3 ? sg2 : sa2) * W->dy_db[c * 6 + q];
+    W->C[e] = W->t2[e] + s;
+  }
+  __syncwarp();
+  return res;
+}
+
+struct WeightArgs {
+  DevProblem dp;
+  imu::ImuBuf buf;
+  const double* state;
+  const double* ftime;
+  double* wsqrt;
+  int ni;
+  double sigma_g, sigma_a;
+};
+constexpr int kWtWarps = 2;
+
+__global__ void __launch_bounds__(32 * kWtWarps) imu_weights_kernel(WeightArgs a) {
+  __shared__ Work work[kWtWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int kk = blockIdx.x * kWtWarps + wid;
+  if (kk >= a.ni) return;
+  Work* W = &work[wid];
+  const double* X1 = a.state + 7 * static_cast<int64_t>(kk);
+  const double* X2 = a.state + 7 * static_cast<int64_t>(kk + 1);
+  const double* V1 = a.state + a.dp.off_v + 3 * static_cast<int64_t>(kk);
+  const double* P = a.state + a.dp.off_imu;
+  const double ts = P[14];
+  const double t_start = a.ftime[kk], t_end = a.ftime[kk + 1];
+  // measurements.size() == 0 -> continue (vicalibrator.h:731-733)
+  if (!(t_start >= a.buf.start_time + ts && t_start <= a.buf.end_time + ts) || a.buf.n == 0) return;
+  const Vec<double> g = imu::gravity_vector<double>(P[0], P[1]);
+  const Vec<double> bg{P[2], P[3], P[4]}, ba{P[5], P[6], P[7]};
+  double sf[6];
+  for (int i = 0; i < 6; ++i) sf[i] = P[8 + i];
+  Pose<double> y{{X1[4], X1[5], X1[6]}, {X1[0], X1[1], X1[2], X1[3]}, {V1[0], V1[1], V1[2]}};
+  wzero(W->C, 100, lane);
+  const double sg2 = a.sigma_g * a.sigma_g, sa2 = a.sigma_a * a.sigma_a;
+  int idx;
+  Meas<double> prev = imu::get_element<double>(a.buf, t_start, ts, &idx), cur;
+  bool more = true;
+  while (more) {
+    more = imu::get_next<double>(a.buf, t_end, ts, &idx, &cur);
+    y = integrate_imu_cov(y, prev, cur, bg, ba, sf, g, sg2, sa2, W, lane);
+    prev = cur;
+  }
+  // t12 = T_end * T_2w, T_2w = T_w2^-1
+  const Quat<double> q2i = imu::qconj(Quat<double>{X2[0], X2[1], X2[2], X2[3]});
+  const Vec<double> t2 = imu::qrot(q2i, Vec<double>{X2[4], X2[5], X2[6]});
+  const Vec<double> t2i{-t2.x, -t2.y, -t2.z};
+  const Quat<double> q12 = imu::qmul(y.q, q2i);
+  const Vec<double> t12 = y.p + imu::qrot(y.q, t2i);
+  // Jt (9x10) = [dLog_dSE3(t12) * dt1t2_dt1(T_end, T_2w), 0; 0, I3]   (vicalibrator.h:763-781)
+  double* Jt = W->t1;   // 90
+  double* tmp = W->t2;  // 100
+  if (lane == 0) {
+    double dlog[42], dmul[49];
+    dLog_dSE3(q12, t12, dlog);
+    for (int i = 0; i < 49; ++i) dmul[i] = 0.0;
+    for (int i = 0; i < 3; ++i) dmul[i * 7 + i] = 1.0;
+    dqx_dq(y.q, t2i, dmul + 3, 7);          // block(0,3) = dqx_dq(t1.q, t2.translation)
+    dq1q2_dq1(q2i, dmul + 3 * 7 + 3, 7);    // block(3,3) = dq1q2_dq1(t2.q)
+    for (int i = 0; i < 90; ++i) Jt[i] = 0.0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 7; ++j) {
+        double s = 0;
+        for (int q = 0; q < 7; ++q) s += dlog[i * 7 + q] * dmul[q * 7 + j];
+        Jt[i * 10 + j] = s;
+      }
+    for (int i = 0; i < 3; ++i) Jt[(6 + i) * 10 + 7 + i] = 1.0;
+  }
+  __syncwarp();
+  // P = Jt C Jt^T  (9x9) -> T_dy[0..80]
+  wmm(tmp, Jt, W->C, 9, 10, 10, lane);
+  double* Pm = W->T_dy;
+  wmm(Pm, tmp, Jt, 9, 10, 9, lane, true);
+  // inverse by Gauss-Jordan with partial pivoting (Eigen .inverse()), lane 0
+  double* inv = W->tot_dy;  // 81
+  __shared__ int singular[kWtWarps];
+  if (lane == 0) {
+    double M[9][18];
+    for (int i = 0; i < 9; ++i)
+      for (int j = 0; j < 9; ++j) { M[i][j] = Pm[i * 9 + j]; M[i][9 + j] = i == j ? 1.0 : 0.0; }
+    int bad = 0;
+    for (int c = 0; c < 9 && !bad; ++c) {
+      int p = c;
+      for (int r = c + 1; r < 9; ++r) if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
+      if (M[p][c] == 0.0) { bad = 1; break; }
+      if (p != c) for (int j = 0; j < 18; ++j) { const double t = M[p][j]; M[p][j] = M[c][j]; M[c][j] = t; }
+      const double iv = 1.0 / M[c][c];
+      for (int j = 0; j < 18; ++j) M[c][j] *= iv;
+      for (int r = 0; r < 9; ++r) {
+        if (r == c) continue;
+        const double f = M[r][c];
+        if (f == 0.0) continue;
+        for (int j = 0; j < 18; ++j) M[r][j] -= f * M[c][j];
+      }
+    }
+    for (int i = 0; i < 9; ++i)
+      for (int j = 0; j < 9; ++j) inv[i * 9 + j] = M[i][9 + j];
+    singular[wid] = bad;
+  }
+  __syncwarp();
+  if (singular[wid]) return;
+  // principal square root: cyclic Jacobi on the symmetrised matrix; A in t1, V in t2
+  double* A = W->t1;
+  double* V = W->t2;
+  for (int e = lane; e < 81; e += 32) {
+    const int r = e / 9, c = e - r * 9;
+    A[e] = 0.5 * (inv[r * 9 + c] + inv[c * 9 + r]);
+    V[e] = r == c ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < 9; ++i) {
+      dg += A[i * 9 + i] * A[i * 9 + i];
+      for (int j = i + 1; j < 9; ++j) off += A[i * 9 + j] * A[i * 9 + j];
+    }
+    if (off <= 1e-30 * dg) break;
+    for (int p = 0; p < 9; ++p)
+      for (int q = p + 1; q < 9; ++q) {
+        const double apq = A[p * 9 + q];
+        if (apq == 0.0) continue;  // uniform across the warp
+        const double tau = (A[q * 9 + q] - A[p * 9 + p]) / (2.0 * apq);
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+        __syncwarp();
+        if (lane < 9) {  // columns p,q of A and V
+          const double akp = A[lane * 9 + p], akq = A[lane * 9 + q];
+          A[lane * 9 + p] = c * akp - s * akq;
+          A[lane * 9 + q] = s * akp + c * akq;
+          const double vkp = V[lane * 9 + p], vkq = V[lane * 9 + q];
+          V[lane * 9 + p] = c * vkp - s * vkq;
+          V[lane * 9 + q] = s * vkp + c * vkq;
+        }
+        __syncwarp();
+        if (lane < 9) {  // rows p,q of A
+          const double apk = A[p * 9 + lane], aqk = A[q * 9 + lane];
+          A[p * 9 + lane] = c * apk - s * aqk;
+          A[q * 9 + lane] = s * apk + c * aqk;
+        }
+        __syncwarp();
+      }
+  }
+  double* out = a.wsqrt + static_cast<int64_t>(kk) * 81;
+  for (int e = lane; e < 81; e += 32) {
+    const int r = e / 9, c = e - r * 9;
+    double s = 0.0;
+    for (int k = 0; k < 9; ++k) {
+      const double l = A[k * 9 + k] > 0 ? sqrt(A[k * 9 + k]) : 0.0;
+      s += V[r * 9 + k] * l * V[c * 9 + k];
+    }
+    out[e] = s;
+  }
+}
+
+}  // namespace wts
+}  // namespace vc

@@ -16,6 +16,7 @@
 #include "vc_kernels.cuh"
 #include "vc_imu.cuh"
 #include "vc_chain.cuh"
+#include "vc_imu_weights.cuh"
 
 using namespace vc;
 
@@ -52,8 +53,6 @@ static void dev_free(T** p) {
   *p = nullptr;
 }
 
-#include "vc_imu_host.inl"
-
 // ------------------------------------------------------------------ stage timers
 struct StageScope {
   vcgpu_handle* h;
@@ -78,6 +77,8 @@ static void stage_collect(vcgpu_handle* h) {  // call after a stream synchronise
       h->st_used[s] = false;
     }
 }
+#include "vc_imu_host.inl"
+
 extern "C" int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2) {
   if (!h) return VCGPU_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
