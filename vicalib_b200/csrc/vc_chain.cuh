@@ -237,12 +237,22 @@ __global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs
 }
 
 // sum of the per-CTA Schur partials (coalesced across entries)
-__global__ void sum_partials_kernel(const double* part, int n_part, int NS, double* out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= NS) return;
+// launch with 256 threads: 32 entries per CTA, 8 partial-slices per entry, fixed summation order
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* part, int n_part, int NS, double* out) {
+  __shared__ double sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int b = 0; b < n_part; ++b) s += part[static_cast<int64_t>(b) * NS + e];
-  out[e] = s;
+  if (e < NS)
+    for (int b = ty; b < n_part; b += 8) s += part[static_cast<int64_t>(b) * NS + e];
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && e < NS) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][tx];
+    out[e] = t;
+  }
 }
 
 // dense solve of [globals | top-level chain nodes]

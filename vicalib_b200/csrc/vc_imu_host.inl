@@ -180,7 +180,7 @@ static int imu_chain_solve(vcgpu_handle* h, int buf, const double* D2) {
     ++h->launches;
     part += nsep;
   }
-  sum_partials_kernel<<<static_cast<int>((NS + 255) / 256), 256, 0, h->stream>>>(h->d_Spart, part, static_cast<int>(NS), d->Ssum);
+  sum_partials_kernel<<<static_cast<int>((NS + 31) / 32), 256, 0, h->stream>>>(h->d_Spart, part, static_cast<int>(NS), d->Ssum);
   ++h->launches;
   DenseArgs da;
   da.dp = dp; da.b = h->blk[buf]; da.scale = h->d_scale; da.D2 = D2; da.Ssum = d->Ssum; da.top = d->levels.back();

@@ -50,7 +50,7 @@ struct vcgpu_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long launches = 0;
   // measurement hooks
-  bool profiling = false, flush_l2 = false;
+  bool profiling = false, flush_l2 = false, materialize = false;
   cudaEvent_t st_ev[VCGPU_STAGE_COUNT][2] = {};
   bool st_used[VCGPU_STAGE_COUNT] = {};
   double st_ms[VCGPU_STAGE_COUNT] = {};
@@ -101,6 +101,7 @@ struct vcgpu_handle {
   double* d_scale = nullptr;      // Jacobi scaling [nf*fd+G]
   double* d_X = nullptr;          // [nf][fd][G+1]
   double* d_Spart = nullptr;      // [solve blocks][G*G+G]
+  double* d_Ssum = nullptr;       // [G*G+G] summed Schur partials
   int n_solve_blocks = 0;
   double* d_delta = nullptr;      // [nf*fd+G] scaled step
   double* d_red = nullptr;        // small reduction scratch

@@ -289,51 +289,58 @@ struct FinalizeArgs {
   Blocks out;
   double* scalars;
 };
-__global__ void __launch_bounds__(256) finalize_globals_kernel(FinalizeArgs a) {
-  __shared__ double sh[8];
-  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G;
-  for (int k = tid; k < NS; k += 256) {
+constexpr int kFinalizeThreads = 1024;
+__global__ void __launch_bounds__(kFinalizeThreads) finalize_globals_kernel(FinalizeArgs a) {
+  // 6 sums (cost, |g|^2, 4 step reductions) + 1 max (|g|_inf) reduced together; fixed order
+  __shared__ double sh[kFinalizeThreads / 32][8];
+  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G, lane = tid & 31, warp = tid >> 5;
+  double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // cost, g2, st0..3, gmax
+  for (int k = tid; k < NS; k += kFinalizeThreads) {
     double s = 0.0;
     for (int b = 0; b < kReduceBlocks; ++b) s += a.Cpart[static_cast<int64_t>(b) * NS + k];
-    if (k < G * G) a.out.C[k] = s;
-    else a.out.gc[k - G * G] = s;
+    if (k < G * G) {
+      a.out.C[k] = s;
+    } else {
+      a.out.gc[k - G * G] = s;
+      v[6] = fmax(v[6], fabs(s));
+      v[1] += s * s;
+    }
   }
-  double c = 0.0;
-  for (int k = tid; k < a.n_cost_part; k += 256) c += a.cost_part[k];
-  for (int k = tid; k < a.n_imu_cost_part; k += 256) c += a.imu_cost_part[k];
-  c = block_sum_256(c, sh);
-  __syncthreads();
-  // gradient norms over [gf | gc]
-  double gm = 0.0, g2 = 0.0;
+  for (int k = tid; k < a.n_cost_part; k += kFinalizeThreads) v[0] += a.cost_part[k];
+  for (int k = tid; k < a.n_imu_cost_part; k += kFinalizeThreads) v[0] += a.imu_cost_part[k];
   const int64_t nfp = static_cast<int64_t>(a.dp.n_frames) * a.dp.fd;
-  for (int64_t k = tid; k < nfp; k += 256) {
-    const double v = a.out.gf[k];
-    gm = fmax(gm, fabs(v));
-    g2 += v * v;
+  for (int64_t k = tid; k < nfp; k += kFinalizeThreads) {
+    const double g = a.out.gf[k];
+    v[6] = fmax(v[6], fabs(g));
+    v[1] += g * g;
   }
-  for (int k = tid; k < G; k += 256) {
-    const double v = a.out.gc[k];
-    gm = fmax(gm, fabs(v));
-    g2 += v * v;
+  if (a.step_part)
+    for (int k = tid; k < a.n_step_part; k += kFinalizeThreads)
+      for (int q = 0; q < 4; ++q) v[2 + q] += a.step_part[4 * k + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+    v[6] = fmax(v[6], __shfl_down_sync(0xffffffffu, v[6], o));
   }
-  gm = block_max_256(gm, sh);
-  g2 = block_sum_256(g2, sh);
-  double st[4] = {0.0, 0.0, 0.0, 0.0};
-  if (a.step_part) {
-    for (int k = tid; k < a.n_step_part; k += 256)
-      for (int q = 0; q < 4; ++q) st[q] += a.step_part[4 * k + q];
-    for (int q = 0; q < 4; ++q) st[q] = block_sum_256(st[q], sh);
-  }
+  if (lane == 0)
+    for (int q = 0; q < 7; ++q) sh[warp][q] = v[q];
+  __syncthreads();
   if (tid == 0) {
-    *a.out.cost = c;
-    a.scalars[kScCost] = c;
-    a.scalars[kScGmax] = gm;
-    a.scalars[kScGnorm2] = g2;
+    double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < kFinalizeThreads / 32; ++w) {
+      for (int q = 0; q < 6; ++q) t[q] += sh[w][q];
+      t[6] = fmax(t[6], sh[w][6]);
+    }
+    *a.out.cost = t[0];
+    a.scalars[kScCost] = t[0];
+    a.scalars[kScGmax] = t[6];
+    a.scalars[kScGnorm2] = t[1];
     if (a.step_part) {
-      a.scalars[kScDotG] = st[0];
-      a.scalars[kScDotD] = st[1];
-      a.scalars[kScStep2] = st[2];
-      a.scalars[kScXnorm2] = st[3];
+      a.scalars[kScDotG] = t[2];
+      a.scalars[kScDotD] = t[3];
+      a.scalars[kScStep2] = t[4];
+      a.scalars[kScXnorm2] = t[5];
     }
   }
 }
@@ -374,82 +381,101 @@ struct SolveArgs {
   double* scalars;
 };
 constexpr int kSolveThreads = 128;
+constexpr int kSolveWarps = kSolveThreads / 32;
 
+// One warp per frame: every lane factors the (damped, scaled) FD x FD block in registers and the
+// lanes split the right-hand-side columns [E | g]; the CTA then accumulates E^T X for its four
+// frames with a fixed thread->entry ownership (deterministic).
 template <int FD>
 __global__ void __launch_bounds__(kSolveThreads) frame_solve_kernel(SolveArgs a) {
   extern __shared__ double sm[];
-  const int G = a.dp.G, M = G + 1, tid = threadIdx.x, NS = G * G + G;
-  double* Sacc = sm;            // [G*G+G]
-  double* A = Sacc + NS;        // [FD*FD]
-  double* Es = A + FD * FD;     // [FD*G]
-  double* R = Es + FD * G;      // [FD*M]
+  const int G = a.dp.G, M = G + 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NS = G * G + G;
+  double* Sacc = sm;                                   // [G*G+G]
+  double* Esw = Sacc + NS + warp * (2 * FD * M);       // per warp: Es [FD][M] (col G = scaled g)
+  double* Xw = Esw + FD * M;                           // per warp: X  [FD][M]
   const double* sc = a.scale + static_cast<int64_t>(a.dp.n_frames) * FD;
   for (int k = tid; k < NS; k += kSolveThreads) Sacc[k] = 0.0;
-  for (int f = blockIdx.x; f < a.dp.n_frames; f += gridDim.x) {
-    const double* sf = a.scale + static_cast<int64_t>(f) * FD;
-    const double* Bf = a.b.B + static_cast<int64_t>(f) * FD * FD;
-    const double* Ef = a.b.E + static_cast<int64_t>(f) * FD * G;
-    __syncthreads();
-    for (int k = tid; k < FD * FD; k += kSolveThreads) {
-      const int r = k / FD, c = k - r * FD;
-      double v = Bf[k] * sf[r] * sf[c];
-      if (r == c) v += a.D2[static_cast<int64_t>(f) * FD + r];
-      A[k] = v;
-    }
-    for (int k = tid; k < FD * G; k += kSolveThreads) {
-      const int r = k / G, c = k - r * G;
-      const double v = Ef[k] * sf[r] * sc[c];
-      Es[k] = v;
-      R[r * M + c] = v;
-    }
-    for (int k = tid; k < FD; k += kSolveThreads) R[k * M + G] = a.b.gf[static_cast<int64_t>(f) * FD + k] * sf[k];
-    __syncthreads();
-    if (tid == 0) {
+  for (int base = blockIdx.x * kSolveWarps; base < a.dp.n_frames; base += gridDim.x * kSolveWarps) {
+    const int f = base + warp;
+    __syncthreads();  // Sacc zeroed / previous accumulation finished reading Esw, Xw
+    if (f < a.dp.n_frames) {
+      const double* sf = a.scale + static_cast<int64_t>(f) * FD;
+      const double* Bf = a.b.B + static_cast<int64_t>(f) * FD * FD;
+      const double* Ef = a.b.E + static_cast<int64_t>(f) * FD * G;
+      double s[FD], L[FD][FD];
+#pragma unroll
+      for (int i = 0; i < FD; ++i) s[i] = sf[i];
+#pragma unroll
+      for (int i = 0; i < FD; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          double v = Bf[i * FD + j] * s[i] * s[j];
+          if (i == j) v += a.D2[static_cast<int64_t>(f) * FD + i];
+          L[i][j] = v;
+        }
       bool ok = true;
+#pragma unroll
       for (int j = 0; j < FD; ++j) {
-        double d = A[j * FD + j];
-        for (int k = 0; k < j; ++k) d -= A[j * FD + k] * A[j * FD + k];
+        double d = L[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
         if (!(d > 0.0)) { ok = false; d = 1.0; }
         d = sqrt(d);
-        A[j * FD + j] = d;
+        L[j][j] = d;
+        const double inv = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < FD; ++i) {
-          double s = A[i * FD + j];
-          for (int k = 0; k < j; ++k) s -= A[i * FD + k] * A[j * FD + k];
-          A[i * FD + j] = s / d;
+          double t = L[i][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+          L[i][j] = t * inv;
         }
       }
-      if (!ok) a.scalars[kScNotPD] = 1.0;
+      if (!ok && lane == 0) a.scalars[kScNotPD] = 1.0;
+      double* Xf = a.X + static_cast<int64_t>(f) * FD * M;
+      for (int c = lane; c < M; c += 32) {
+        double x[FD];
+        const double scc = c < G ? sc[c] : 1.0;
+#pragma unroll
+        for (int i = 0; i < FD; ++i) {
+          const double r = (c < G ? Ef[i * G + c] : a.b.gf[static_cast<int64_t>(f) * FD + i]) * s[i] * scc;
+          Esw[i * M + c] = r;
+          x[i] = r;
+        }
+#pragma unroll
+        for (int i = 0; i < FD; ++i) {
+          double t = x[i];
+#pragma unroll
+          for (int k = 0; k < i; ++k) t -= L[i][k] * x[k];
+          x[i] = t / L[i][i];
+        }
+#pragma unroll
+        for (int i = FD - 1; i >= 0; --i) {
+          double t = x[i];
+#pragma unroll
+          for (int k = i + 1; k < FD; ++k) t -= L[k][i] * x[k];
+          x[i] = t / L[i][i];
+        }
+#pragma unroll
+        for (int i = 0; i < FD; ++i) {
+          Xw[i * M + c] = x[i];
+          Xf[i * M + c] = x[i];
+        }
+      }
     }
     __syncthreads();
-    for (int c = tid; c < M; c += kSolveThreads) {
-      double x[FD];
-#pragma unroll
-      for (int i = 0; i < FD; ++i) {
-        double s = R[i * M + c];
-#pragma unroll
-        for (int k = 0; k < i; ++k) s -= A[i * FD + k] * x[k];
-        x[i] = s / A[i * FD + i];
-      }
-#pragma unroll
-      for (int i = FD - 1; i >= 0; --i) {
-        double s = x[i];
-#pragma unroll
-        for (int k = i + 1; k < FD; ++k) s -= A[k * FD + i] * x[k];
-        x[i] = s / A[i * FD + i];
-      }
-#pragma unroll
-      for (int i = 0; i < FD; ++i) R[i * M + c] = x[i];
-    }
-    __syncthreads();
-    double* Xf = a.X + static_cast<int64_t>(f) * FD * M;
-    for (int k = tid; k < FD * M; k += kSolveThreads) Xf[k] = R[k];
+    const int nact = min(kSolveWarps, a.dp.n_frames - base);
     for (int e = tid; e < NS; e += kSolveThreads) {
       const int ra = e < G * G ? e / G : e - G * G;
       const int cb = e < G * G ? e - ra * G : G;
-      double s = 0.0;
+      double sum = 0.0;
+      for (int w = 0; w < nact; ++w) {
+        const double* Ew = sm + NS + w * (2 * FD * M);
+        const double* Xv = Ew + FD * M;
 #pragma unroll
-      for (int k = 0; k < FD; ++k) s += Es[k * G + ra] * R[k * M + cb];
-      Sacc[e] += s;
+        for (int k = 0; k < FD; ++k) sum += Ew[k * M + ra] * Xv[k * M + cb];
+      }
+      Sacc[e] += sum;
     }
   }
   __syncthreads();

@@ -16,6 +16,7 @@
 #include "vc_kernels.cuh"
 #include "vc_imu.cuh"
 #include "vc_chain.cuh"
+#include "vc_fused.cuh"
 #include "vc_imu_weights.cuh"
 
 using namespace vc;
@@ -89,7 +90,8 @@ extern "C" int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2) {
     CUDA_TRY(h, cudaEventCreate(&h->it_ev[1]));
   }
   if (flush_l2 && !h->d_flush) CUDA_TRY(h, cudaMalloc(&h->d_flush, 256u << 20));
-  h->profiling = profile != 0;
+  h->profiling = (profile & 1) != 0;
+  h->materialize = (profile & 2) != 0;  // bit 1: use the two-pass path that materialises J in HBM
   h->flush_l2 = flush_l2 != 0;
   for (int s = 0; s < VCGPU_STAGE_COUNT; ++s) { h->st_ms[s] = 0; h->st_n[s] = 0; h->st_used[s] = false; }
   return VCGPU_OK;
@@ -151,7 +153,7 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_Cg); dev_free(&h->d_Cpart);
   dev_free(&h->d_blk_mem[0]); dev_free(&h->d_blk_mem[1]);
   dev_free(&h->d_scale); dev_free(&h->d_X); dev_free(&h->d_Spart); dev_free(&h->d_delta);
-  dev_free(&h->d_red); dev_free(&h->d_scalars);
+  dev_free(&h->d_red); dev_free(&h->d_scalars); dev_free(&h->d_Ssum);
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -429,7 +431,7 @@ static int prepare(vcgpu_handle* h) {
     VC_TRY(dev_alloc(h, &h->d_J, joff));
     h->n_cost_part = 0;
     for (int c = 0; c < nc; ++c) h->n_cost_part += (dp.cams[c].n_obs + 255) / 256;
-    VC_TRY(dev_alloc(h, &h->d_cost_part, h->n_cost_part));
+    VC_TRY(dev_alloc(h, &h->d_cost_part, std::max(h->n_cost_part, nf)));
     VC_TRY(dev_alloc(h, &h->d_Cg, static_cast<size_t>(h->n_groups) * kCgStride));
     CUDA_TRY(h, cudaMemset(h->d_Cg, 0, std::max<size_t>(1, static_cast<size_t>(h->n_groups) * kCgStride) * sizeof(double)));
     const size_t NS = static_cast<size_t>(G) * G + G;
@@ -451,8 +453,9 @@ static int prepare(vcgpu_handle* h) {
     const size_t np = static_cast<size_t>(nf) * fd + G;
     VC_TRY(dev_alloc(h, &h->d_scale, 2 * np));  // [scale | D2]
     VC_TRY(dev_alloc(h, &h->d_X, static_cast<size_t>(nf) * fd * (G + 1)));
-    h->n_solve_blocks = std::min(nf, 296);
+    h->n_solve_blocks = std::min((nf + kSolveWarps - 1) / kSolveWarps, 444);
     VC_TRY(dev_alloc(h, &h->d_Spart, static_cast<size_t>(h->n_solve_blocks) * NS));
+    VC_TRY(dev_alloc(h, &h->d_Ssum, NS));
     VC_TRY(dev_alloc(h, &h->d_delta, np));
     VC_TRY(dev_alloc(h, &h->d_red, 4 * (static_cast<size_t>((nf + kUpdateWarps - 1) / kUpdateWarps) + 1)));
     VC_TRY(dev_alloc(h, &h->d_scalars, kScCount));
@@ -527,7 +530,8 @@ static int eval_reproj(vcgpu_handle* h, int buf, bool jac, bool apply_loss, cons
 static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
   const DevProblem& dp = h->dp;
   const bool visual = h->flags.visual && h->n_obs > 0;
-  if (visual) {
+  const bool fused = !h->materialize;
+  if (visual && !fused) {
     StageScope st(h, VCGPU_STAGE_EVAL_REPROJ);
     VC_TRY(eval_reproj(h, buf, true, true, h->d_mask));
   }
@@ -541,8 +545,29 @@ static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
   if (!visual) ba.dp.n_cams = 0;
   ba.grp_start = h->d_grp_start; ba.grp_count = h->d_grp_count; ba.group_of = h->d_group_of;
   ba.r = h->d_r; ba.J = h->d_J; ba.n_obs = h->n_obs; ba.out = h->blk[buf]; ba.Cg = h->d_Cg;
-  const size_t bsm = (2 * kBuildChunk * kMaxW + 9 * 9 + 9) * sizeof(double);
-  {
+  int n_vis_cost = visual ? h->n_cost_part : 0;
+  if (fused) {
+    // evaluate + J^T J in one pass: the Jacobian tile lives in shared memory only
+    StageScope st(h, VCGPU_STAGE_BUILD);
+    FusedArgs fa;
+    fa.dp = ba.dp; fa.state = h->d_state[buf];
+    fa.grp_start = h->d_grp_start; fa.grp_count = h->d_grp_count; fa.group_of = h->d_group_of;
+    fa.obs = h->d_obs; fa.n_obs = h->n_obs; fa.mask = h->d_mask; fa.out = h->blk[buf]; fa.Cg = h->d_Cg;
+    fa.cost_part = h->d_cost_part;
+    const size_t fsm = (static_cast<size_t>(kFusedCols) * kFusedLd + kFusedWarps * 384 + 9 * 9 + 9 + kFusedWarps) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
+      CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
+      attr_done = true;
+    }
+    if (dp.fd == 6) fused_build_kernel<6><<<dp.n_frames, kFusedThreads, fsm, h->stream>>>(fa);
+    else fused_build_kernel<9><<<dp.n_frames, kFusedThreads, fsm, h->stream>>>(fa);
+    ++h->launches;
+    n_vis_cost = dp.n_frames;
+    if (dp.inertial) VC_TRY(imu_accumulate(h, buf));
+  } else {
+    const size_t bsm = (2 * kBuildChunk * kMaxW + 9 * 9 + 9) * sizeof(double);
     StageScope st(h, VCGPU_STAGE_BUILD);
     if (dp.fd == 6) build_frames_kernel<6><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
     else build_frames_kernel<9><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
@@ -560,14 +585,14 @@ static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
   }
   FinalizeArgs fa;
   fa.dp = dp; fa.Cpart = h->d_Cpart;
-  fa.cost_part = h->d_cost_part; fa.n_cost_part = visual ? h->n_cost_part : 0;
+  fa.cost_part = h->d_cost_part; fa.n_cost_part = n_vis_cost;
   fa.imu_cost_part = imu_cost_part(h); fa.n_imu_cost_part = n_imu_cost;
   fa.step_part = with_step ? h->d_red : nullptr;
   fa.n_step_part = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps + 1;
   fa.out = h->blk[buf]; fa.scalars = h->d_scalars;
   {
     StageScope st(h, VCGPU_STAGE_FINALIZE);
-    finalize_globals_kernel<<<1, 256, 0, h->stream>>>(fa);
+    finalize_globals_kernel<<<1, kFinalizeThreads, 0, h->stream>>>(fa);
     ++h->launches;
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -606,13 +631,20 @@ static int solve_and_update(vcgpu_handle* h, int buf) {
     SolveArgs sa;
     sa.dp = dp; sa.b = h->blk[buf]; sa.scale = h->d_scale; sa.D2 = D2; sa.X = h->d_X; sa.Spart = h->d_Spart;
     sa.scalars = h->d_scalars;
-    const size_t ssm = (NS + 6 * 6 + 6 * dp.G + 6 * (dp.G + 1)) * sizeof(double);
+    const size_t ssm = (NS + static_cast<size_t>(kSolveWarps) * 2 * 6 * (dp.G + 1)) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(h, cudaFuncSetAttribute(frame_solve_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_done = true;
+    }
     frame_solve_kernel<6><<<h->n_solve_blocks, kSolveThreads, ssm, h->stream>>>(sa);
+    ++h->launches;
+    sum_partials_kernel<<<static_cast<int>((NS + 31) / 32), 256, 0, h->stream>>>(h->d_Spart, h->n_solve_blocks, static_cast<int>(NS), h->d_Ssum);
     ++h->launches;
   }
   GlobalSolveArgs ga;
-  ga.dp = dp; ga.b = h->blk[buf]; ga.scale = h->d_scale; ga.D2 = D2; ga.Spart = h->d_Spart;
-  ga.n_spart = h->n_solve_blocks; ga.delta = h->d_delta; ga.scalars = h->d_scalars;
+  ga.dp = dp; ga.b = h->blk[buf]; ga.scale = h->d_scale; ga.D2 = D2; ga.Spart = h->d_Ssum;
+  ga.n_spart = 1; ga.delta = h->d_delta; ga.scalars = h->d_scalars;
   if (!dp.inertial) {  // the chain path ends in its own dense solve (globals + top-level nodes)
     StageScope st(h, VCGPU_STAGE_GLOBAL_SOLVE);
     global_solve_kernel<<<1, 256, NS * sizeof(double), h->stream>>>(ga);
