@@ -26,14 +26,19 @@ constexpr int kChainThreads = 128;
 
 // level 0 from the block normal equations: scaled + damped
 template <int FD>
-__global__ void chain_init_kernel(DevProblem dp, Blocks b, const double* scale, const double* D2, ChainLevel L) {
+__global__ void chain_init_kernel(DevProblem dp, Blocks b0, Blocks b1, const Ctl* ctl, const double* scale,
+                                  const double* D2x, ChainLevel L) {
+  if (ctl->done) return;
+  const Blocks& b = ctl->cur ? b1 : b0;
+  const double rinv = 1.0 / ctl->radius;
   const int G = dp.G, f = blockIdx.x, tid = threadIdx.x;
   const double* sf = scale + static_cast<int64_t>(f) * FD;
   const double* sc = scale + static_cast<int64_t>(dp.n_frames) * FD;
   for (int e = tid; e < FD * FD; e += blockDim.x) {
     const int r = e / FD, c = e - r * FD;
-    double v = b.B[static_cast<int64_t>(f) * FD * FD + e] * sf[r] * sf[c];
-    if (r == c) v += D2[static_cast<int64_t>(f) * FD + r];
+    const double bij = b.B[static_cast<int64_t>(f) * FD * FD + e];
+    double v = bij * sf[r] * sf[c];
+    if (r == c) v += D2x ? D2x[static_cast<int64_t>(f) * FD + r] : lm_damp(bij, sf[r], rinv);
     L.A[static_cast<int64_t>(f) * FD * FD + e] = v;
     double u = 0.0;
     if (f > 0) u = b.U[static_cast<int64_t>(f) * FD * FD + e] * scale[static_cast<int64_t>(f - 1) * FD + r] * sf[c];
@@ -49,6 +54,7 @@ __global__ void chain_init_kernel(DevProblem dp, Blocks b, const double* scale, 
 
 struct ElimArgs {
   int G, c;
+  const Ctl* ctl;
   ChainLevel cur, next;
   double* Spart;  // [gridDim][G*G+G]
   double* scalars;
@@ -68,6 +74,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs
   double* Uc = Ap + FD * FD;               // [FD*FD] U[p]
   double* V = Uc + FD * FD;                // [(c-1)][FD][VW]
   __shared__ int bad;
+  if (a.ctl->done) return;
   const ChainLevel& L = a.cur;
   const int j = blockIdx.x, s = j * c, n = L.n;
   const bool hasR = s + c < n;
@@ -238,13 +245,25 @@ __global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs
 
 // sum of the per-CTA Schur partials (coalesced across entries)
 // launch with 256 threads: 32 entries per CTA, 8 partial-slices per entry, fixed summation order
-__global__ void __launch_bounds__(256) sum_partials_kernel(const double* part, int n_part, int NS, double* out) {
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* part, int n_part, int NS, double* out,
+                                                           const Ctl* ctl) {
   __shared__ double sh[8][33];
+  if (ctl->done) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + tx;
   double s = 0.0;
-  if (e < NS)
-    for (int b = ty; b < n_part; b += 8) s += part[static_cast<int64_t>(b) * NS + e];
+  if (e < NS) {
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = ty;
+    for (; b + 24 < n_part; b += 32) {
+      s += part[static_cast<int64_t>(b) * NS + e];
+      s1 += part[static_cast<int64_t>(b + 8) * NS + e];
+      s2 += part[static_cast<int64_t>(b + 16) * NS + e];
+      s3 += part[static_cast<int64_t>(b + 24) * NS + e];
+    }
+    for (; b < n_part; b += 8) s += part[static_cast<int64_t>(b) * NS + e];
+    s = (s + s1) + (s2 + s3);
+  }
   sh[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && e < NS) {
@@ -258,9 +277,10 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const double* part, i
 // dense solve of [globals | top-level chain nodes]
 struct DenseArgs {
   DevProblem dp;
-  Blocks b;
+  Blocks bs[2];
+  const Ctl* ctl;
   const double* scale;
-  const double* D2;
+  const double* D2x;
   const double* Ssum;  // [G*G+G] summed Schur partials
   ChainLevel top;      // n may be 0
   double* delta;
@@ -273,6 +293,9 @@ __global__ void __launch_bounds__(256) dense_solve_kernel(DenseArgs a) {
   double* S = sm;          // [N*N]
   double* rhs = sm + N * N;
   __shared__ int bad;
+  if (a.ctl->done) return;
+  const Blocks& b = a.bs[a.ctl->cur];
+  const double rinv = 1.0 / a.ctl->radius;
   if (tid == 0) bad = 0;
   const int64_t nfp = static_cast<int64_t>(a.dp.n_frames) * a.dp.fd;
   const double* sc = a.scale + nfp;
@@ -281,12 +304,12 @@ __global__ void __launch_bounds__(256) dense_solve_kernel(DenseArgs a) {
   for (int e = tid; e < G * G + G; e += 256) {
     if (e < G * G) {
       const int r = e / G, c = e - r * G;
-      double v = a.b.C[e] * sc[r] * sc[c] - a.Ssum[e];
-      if (r == c) v += a.D2[nfp + r];
+      double v = b.C[e] * sc[r] * sc[c] - a.Ssum[e];
+      if (r == c) v += a.D2x ? a.D2x[nfp + r] : lm_damp(b.C[e], sc[r], rinv);
       S[r * N + c] = v;
     } else {
       const int r = e - G * G;
-      rhs[r] = -a.b.gc[r] * sc[r] + a.Ssum[e];
+      rhs[r] = -b.gc[r] * sc[r] + a.Ssum[e];
     }
   }
   const bool add = a.top.addA != nullptr;
@@ -351,6 +374,7 @@ __global__ void __launch_bounds__(256) dense_solve_kernel(DenseArgs a) {
 
 // back-substitution of one level: x_p = -Z_g - Z_L x_left - Z_R x_right - Z_E dc
 struct BacksubArgs {
+  const Ctl* ctl;
   int G, c, nfp_off;  // nfp_off unused
   ChainLevel cur;
   double* delta;
@@ -361,7 +385,7 @@ __global__ void __launch_bounds__(128) chain_backsub_kernel(BacksubArgs a) {
   const int G = a.G, c = a.c, w = 2 * FD + G + 1;
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * 4 + (threadIdx.x >> 5);  // node index at this level
-  if (p >= a.cur.n || p % c == 0) return;              // separators are solved at the next level
+  if (a.ctl->done || p >= a.cur.n || p % c == 0) return;              // separators are solved at the next level
   const int s = (p / c) * c, r = s + c;
   const double* xl = a.delta + static_cast<int64_t>(a.cur.orig[s]) * FD;
   const double* xr = r < a.cur.n ? a.delta + static_cast<int64_t>(a.cur.orig[r]) * FD : nullptr;

@@ -1,0 +1,373 @@
+// The iteration engine (included by vcgpu.cu): kernel launch helpers, the evaluation pass, the
+// damped arrow solve and the trust-region loop.  All trust-region state lives in a device-resident
+// Ctl block, so an iteration is a fixed sequence of launches the host enqueues without waiting:
+//
+//   frame_solve -> sum_partials -> global_solve -> backsub_update        (vision)
+//   chain_init -> chain_eliminate x levels -> sum_partials -> dense_solve -> chain_backsub x levels
+//              -> backsub_update                                         (inertial)
+//   fused_build [-> imu_eval -> imu_accumulate] -> reduce_globals -> finalize -> decide [-> imu_weights]
+//
+// Multi-GPU: all_reduce_dense() after the partial sums and all_reduce_eval() before decide are the
+// only cross-rank points (frames are sharded; every rank then solves the same small dense system).
+
+// Measured on B200 (config 2): folding the back-substitution into the fused kernel serialises ~2 us
+// of single-thread SE3 work in front of every CTA wave (+25 us/iteration), and summing the Schur
+// partials inside the single-CTA dense solve is latency-bound (+18 us); both stay as separate,
+// fully parallel launches.
+constexpr bool kFuseUpdate = false;
+constexpr bool kSumInSolve = false;
+
+// ------------------------------------------------------------------ control block
+static int ctl_upload(vcgpu_handle* h) {
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+  return VCGPU_OK;
+}
+static int ctl_download(vcgpu_handle* h) {
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  stage_collect(h);
+  h->cur = h->h_ctl->cur;
+  return VCGPU_OK;
+}
+// fresh control block for an inspection hook or a new solve
+static int ctl_reset(vcgpu_handle* h, int fixed, int max_iters) {
+  Ctl* c = h->h_ctl;
+  std::memset(c, 0, sizeof *c);
+  c->cur = h->cur;
+  c->fixed = fixed;
+  c->max_iters = max_iters;
+  c->radius = h->opts.init_radius;
+  c->decrease_factor = 2.0;
+  c->function_tol = h->opts.function_tol;
+  c->gradient_tol = h->opts.gradient_tol;
+  c->param_tol = h->opts.param_tol;
+  return ctl_upload(h);
+}
+
+// ------------------------------------------------------------------ reprojection pass (two-pass path + hooks)
+template <bool JAC>
+static void launch_eval_cam(vcgpu_handle* h, const EvalArgs& a, int model, int nblk) {
+  switch (model) {
+    case kLinear: eval_reproj_kernel<kLinear, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+    case kFov: eval_reproj_kernel<kFov, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+    case kPoly2: eval_reproj_kernel<kPoly2, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+    case kPoly3: eval_reproj_kernel<kPoly3, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+    default: eval_reproj_kernel<kKb4, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
+  }
+  ++h->launches;
+}
+
+static int eval_reproj(vcgpu_handle* h, int which, bool jac, bool apply_loss, const double* mask_dev) {
+  const DevProblem& dp = h->dp;
+  const int64_t n = h->n_obs;
+  int part = 0;
+  for (int c = 0; c < dp.n_cams; ++c) {
+    const CamInfo& ci = dp.cams[c];
+    if (ci.n_obs == 0) continue;
+    EvalArgs a;
+    a.state[0] = h->d_state[0]; a.state[1] = h->d_state[1]; a.ctl = h->d_ctl; a.which = which;
+    a.cam_off = dp.off_cam + kCamStateStride * c;
+    a.frame = h->d_obs_frame + ci.obs_start;
+    a.pwx = h->d_obs + ci.obs_start;
+    a.pwy = h->d_obs + n + ci.obs_start;
+    a.pwz = h->d_obs + 2 * n + ci.obs_start;
+    a.pcu = h->d_obs + 3 * n + ci.obs_start;
+    a.pcv = h->d_obs + 4 * n + ci.obs_start;
+    a.mask = mask_dev + ci.goff;
+    a.r0 = h->d_r + ci.obs_start;
+    a.r1 = h->d_r + n + ci.obs_start;
+    a.J = h->d_J + ci.joff;
+    a.cost_part = h->d_cost_part + part;
+    a.n = ci.n_obs;
+    a.apply_loss = apply_loss ? 1 : 0;
+    a.mult = dp.visual_mult;
+    const int nblk = (ci.n_obs + 255) / 256;
+    part += nblk;
+    if (jac) launch_eval_cam<true>(h, a, ci.model, nblk);
+    else launch_eval_cam<false>(h, a, ci.model, nblk);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+// ------------------------------------------------------------------ evaluation pass
+// which = 0: the accepted point (buffers[cur]); which = 1: the trial point (buffers[1-cur]).
+// Residuals, Jacobians and block normal equations land in blk[buffer]; cost / gradient norms (and
+// the step reductions when with_step) land in d_scalars for decide_kernel.
+static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_mode, const double* D2x = nullptr) {
+  const DevProblem& dp = h->dp;
+  const bool visual = h->flags.visual && h->n_obs > 0;
+  const bool fused = !h->materialize;
+  if (visual && !fused) {
+    StageScope st(h, VCGPU_STAGE_EVAL_REPROJ);
+    VC_TRY(eval_reproj(h, which, true, true, h->d_mask));
+  }
+  int n_imu_cost = 0;
+  DevProblem vdp = dp;
+  if (!visual) vdp.n_cams = 0;
+  int n_vis_cost = visual ? h->n_cost_part : 0;
+  if (fused) {
+    StageScope st(h, VCGPU_STAGE_BUILD);
+    FusedArgs fa;
+    fa.dp = vdp; fa.ctl = h->d_ctl; fa.which = which;
+    fa.state[0] = h->d_state[0]; fa.state[1] = h->d_state[1];
+    fa.grp_start = h->d_grp_start; fa.grp_count = h->d_grp_count; fa.group_of = h->d_group_of;
+    fa.obs = h->d_obs; fa.n_obs = h->n_obs; fa.mask = h->d_mask;
+    fa.out[0] = h->blk[0]; fa.out[1] = h->blk[1]; fa.Cg = h->d_Cg; fa.cost_part = h->d_cost_part;
+    // the trial-point launch also performs the back-substitution / x (+) delta for its frame
+    fa.apply_update = (with_step && kFuseUpdate) ? 1 : 0;
+    fa.scale = h->d_scale; fa.D2x = D2x; fa.X = dp.inertial ? nullptr : h->d_X; fa.delta = h->d_delta;
+    fa.states_rw[0] = h->d_state[0]; fa.states_rw[1] = h->d_state[1]; fa.step_part = h->d_red;
+    const size_t fsm = (static_cast<size_t>(kFusedCols) * kFusedLd + kFusedWarps * 384 + 9 * 9 + 9 + kFusedWarps + 8 +
+                        kMaxCams * kCamStateStride) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
+      CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
+      attr_done = true;
+    }
+    if (dp.fd == 6) fused_build_kernel<6><<<dp.n_frames, kFusedThreads, fsm, h->stream>>>(fa);
+    else fused_build_kernel<9><<<dp.n_frames, kFusedThreads, fsm, h->stream>>>(fa);
+    ++h->launches;
+    n_vis_cost = dp.n_frames;
+  } else {
+    StageScope st(h, VCGPU_STAGE_BUILD);
+    BuildArgs ba;
+    ba.dp = vdp; ba.ctl = h->d_ctl; ba.which = which;
+    ba.grp_start = h->d_grp_start; ba.grp_count = h->d_grp_count; ba.group_of = h->d_group_of;
+    ba.r = h->d_r; ba.J = h->d_J; ba.n_obs = h->n_obs; ba.out[0] = h->blk[0]; ba.out[1] = h->blk[1]; ba.Cg = h->d_Cg;
+    const size_t bsm = (2 * kBuildChunk * kMaxW + 9 * 9 + 9) * sizeof(double);
+    if (dp.fd == 6) build_frames_kernel<6><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
+    else build_frames_kernel<9><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
+    ++h->launches;
+  }
+  if (dp.inertial) {  // after the fused launch: it is the one that writes the trial state
+    StageScope st(h, VCGPU_STAGE_IMU_EVAL);
+    VC_TRY(imu_evaluate(h, which, true, &n_imu_cost));
+    VC_TRY(imu_accumulate(h, which));
+  }
+  const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
+  {
+    StageScope st(h, VCGPU_STAGE_REDUCE);
+    RedFinArgs ra;
+    ra.dp = vdp; ra.ctl = h->d_ctl; ra.which = which; ra.decide_mode = decide_mode;
+    ra.Cg = h->d_Cg; ra.imuCg = dp.inertial ? imu_cg(h) : nullptr; ra.ni = dp.n_frames - 1; ra.imu_goff = dp.imu_goff;
+    ra.imu_stride = kImuCgStride;
+    ra.Cpart = h->d_Cpart; ra.red_part = h->d_red_part;
+    ra.cost_part = h->d_cost_part; ra.n_cost_part = n_vis_cost;
+    ra.imu_cost_part = imu_cost_part(h); ra.n_imu_cost_part = n_imu_cost;
+    ra.step_part = with_step ? h->d_red : nullptr;
+    ra.n_step_part = (fused && kFuseUpdate) ? dp.n_frames + 1 : (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps + 1;
+    ra.n_frames_fd = dp.n_frames * dp.fd;
+    ra.out[0] = h->blk[0]; ra.out[1] = h->blk[1]; ra.scalars = h->d_scalars; ra.counter = h->d_counter;
+    reduce_finalize_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
+    ++h->launches;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+static int read_scalars(vcgpu_handle* h) {
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, kScCount * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  stage_collect(h);
+  return VCGPU_OK;
+}
+
+// ------------------------------------------------------------------ damped arrow solve + state update
+// Solves (H + D) step = -g on the blocks of the accepted buffer and writes the trial state into the
+// other buffer.  D2x: explicit damping vector (inspection hook) or null for the LM rule.
+static int solve_and_update(vcgpu_handle* h, const double* D2x, bool with_update_in_eval) {
+  const DevProblem& dp = h->dp;
+  const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
+  if (dp.inertial) {
+    {
+      StageScope st(h, VCGPU_STAGE_FRAME_SOLVE);
+      VC_TRY(imu_chain_eliminate(h, D2x));
+    }
+    {
+      StageScope st(h, VCGPU_STAGE_GLOBAL_SOLVE);
+      VC_TRY(imu_chain_dense(h, D2x));
+    }
+    StageScope st(h, VCGPU_STAGE_BACKSUB);
+    VC_TRY(imu_chain_backsub(h, D2x, h->materialize || !with_update_in_eval));
+  } else {
+    {
+      StageScope st(h, VCGPU_STAGE_FRAME_SOLVE);
+      SolveArgs sa;
+      sa.dp = dp; sa.b[0] = h->blk[0]; sa.b[1] = h->blk[1]; sa.ctl = h->d_ctl; sa.scale = h->d_scale; sa.D2x = D2x;
+      sa.X = h->d_X; sa.Spart = h->d_Spart; sa.scalars = h->d_scalars;
+      const size_t ssm = (NS + static_cast<size_t>(kSolveWarps) * 2 * 6 * (dp.G + 1)) * sizeof(double);
+      static bool attr_done = false;
+      if (!attr_done) {
+        CUDA_TRY(h, cudaFuncSetAttribute(frame_solve_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done = true;
+      }
+      frame_solve_kernel<6><<<h->n_solve_blocks, kSolveThreads, ssm, h->stream>>>(sa);
+      ++h->launches;
+    }
+    const bool sum_in_solve = kSumInSolve && NS <= 1024;
+    if (!sum_in_solve) {
+      sum_partials_kernel<<<static_cast<int>((NS + 31) / 32), 256, 0, h->stream>>>(h->d_Spart, h->n_solve_blocks,
+                                                                                   static_cast<int>(NS), h->d_Ssum, h->d_ctl);
+      ++h->launches;
+    }
+    {
+      StageScope st(h, VCGPU_STAGE_GLOBAL_SOLVE);
+      GlobalSolveArgs ga;
+      ga.dp = dp; ga.b[0] = h->blk[0]; ga.b[1] = h->blk[1]; ga.ctl = h->d_ctl; ga.scale = h->d_scale; ga.D2x = D2x;
+      ga.Ssum = h->d_Ssum; ga.Spart = h->d_Spart; ga.n_part = sum_in_solve ? h->n_solve_blocks : 0;
+      ga.delta = h->d_delta; ga.scalars = h->d_scalars;
+      global_solve_kernel<<<1, 256, NS * sizeof(double), h->stream>>>(ga);
+      ++h->launches;
+    }
+    if (h->materialize || !with_update_in_eval) {  // two-pass path / hook: explicit back-substitution kernel
+      StageScope st(h, VCGPU_STAGE_BACKSUB);
+      UpdateArgs ua;
+      ua.dp = dp; ua.b[0] = h->blk[0]; ua.b[1] = h->blk[1]; ua.ctl = h->d_ctl; ua.scale = h->d_scale; ua.D2x = D2x;
+      ua.X = h->d_X; ua.delta = h->d_delta; ua.state[0] = h->d_state[0]; ua.state[1] = h->d_state[1];
+      ua.step_part = h->d_red;
+      const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
+      backsub_update_kernel<6><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
+      ++h->launches;
+    }
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+static double host_state_norm(const vcgpu_handle* h) {
+  double s = 0;
+  for (double v : h->h_T) s += v * v;
+  if (h->flags.inertial) for (double v : h->h_v) s += v * v;
+  for (int c = 0; c < h->n_cams; ++c) {
+    for (int i = 0; i < 4; ++i) s += h->h_qck[4 * c + i] * h->h_qck[4 * c + i];
+    for (int i = 0; i < 3; ++i) s += h->h_pck[3 * c + i] * h->h_pck[3 * c + i];
+    for (int i = 0; i < num_intr(h->h_model[c]); ++i) s += h->h_intr[10 * c + i] * h->h_intr[10 * c + i];
+  }
+  if (h->flags.inertial) {
+    s += h->h_g[0] * h->h_g[0] + h->h_g[1] * h->h_g[1] + h->h_ts * h->h_ts;
+    for (int i = 0; i < 6; ++i) s += h->h_b[i] * h->h_b[i] + h->h_sf[i] * h->h_sf[i];
+  }
+  return std::sqrt(s);
+}
+
+static int num_residuals(const vcgpu_handle* h) {
+  int64_t n = 0;
+  if (h->flags.visual) {
+    int64_t act = 0;
+    for (uint8_t a : h->h_active) act += a;
+    n += static_cast<int64_t>(2 * act * h->flags.visual_mult);
+  }
+  if (h->flags.inertial && h->n_frames > 1) n += static_cast<int64_t>(9 * (h->n_frames - 1) * h->flags.imu_mult);
+  return static_cast<int>(n);
+}
+
+// one trust-region iteration, enqueued (no host wait)
+static int enqueue_iteration(vcgpu_handle* h, bool weights) {
+  VC_TRY(solve_and_update(h, nullptr, kFuseUpdate));
+  VC_TRY(evaluate_into(h, 1, true, 1));
+  if (weights) VC_TRY(imu_update_weights(h));  // the reference's iteration callback (vicalibrator.h:691)
+  return VCGPU_OK;
+}
+
+// ------------------------------------------------------------------ the trust-region loop
+static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out, int fixed_iters) {
+  VC_TRY(prepare(h));
+  if (h->opts.strategy != 0) return fail(h, VCGPU_ERR_INVALID, "DOGLEG strategy is not implemented on the device yet; use strategy 0 (LM)");
+  const DevProblem& dp = h->dp;
+  const vcgpu_options& o = h->opts;
+  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
+  const long launches0 = h->launches;
+  const int max_it = fixed_iters > 0 ? fixed_iters : o.max_iters;
+  const bool weights = o.update_imu_weights && dp.inertial;
+  VC_TRY(ctl_reset(h, fixed_iters > 0 ? 1 : 0, max_it));
+  h->h_ctl->x_norm = host_state_norm(h);
+  VC_TRY(ctl_upload(h));
+  if (weights) VC_TRY(imu_update_weights(h));  // vicalibrator.h:955
+  VC_TRY(evaluate_into(h, 0, false, 0));
+  if (o.jacobi_scaling) {
+    jacobi_scale_kernel<<<static_cast<int>((np + 255) / 256), 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale);
+    ++h->launches;
+  } else {
+    std::vector<double> ones(np, 1.0);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_scale, ones.data(), np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  if (weights) VC_TRY(imu_update_weights(h));  // callback after iteration 0 (vicalibrator.h:691)
+  const bool per_iteration = cb != nullptr || o.update_state_every_iteration || h->flush_l2 || h->profiling;
+  auto report = [&](void) -> int {  // invoke the user's callback with the last iteration's summary
+    const Ctl& c = *h->h_ctl;
+    vcgpu_iteration it;
+    it.iteration = c.iter; it.step_is_successful = c.last_accepted; it.cost = c.cost; it.cost_change = c.last_cost_change;
+    it.gradient_max_norm = c.gmax; it.gradient_norm = c.last_accepted ? c.gnorm : 0.0; it.step_norm = c.last_step_norm;
+    it.relative_decrease = c.last_rho; it.trust_region_radius = c.radius;
+    if (o.update_state_every_iteration) { VC_TRY(download_state(h)); write_mirrors(h); }
+    if (cb && cb(&it, user)) {
+      if (!c.done) {
+        h->h_ctl->done = 1 + VCGPU_TERM_CALLBACK;
+        CUDA_TRY(h, cudaMemcpyAsync(&h->d_ctl->done, &h->h_ctl->done, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      }
+    }
+    return VCGPU_OK;
+  };
+  if (per_iteration && fixed_iters <= 0) {
+    VC_TRY(ctl_download(h));
+    VC_TRY(report());
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  double flushed_ms = 0.0;
+  if (per_iteration) {
+    for (int k = 0; k < max_it && !h->h_ctl->done; ++k) {
+      if (h->flush_l2) {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_flush, k & 0xff, 256u << 20, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->it_ev[0], h->stream));
+      }
+      VC_TRY(enqueue_iteration(h, weights));
+      if (h->flush_l2) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->it_ev[1], h->stream));
+      }
+      VC_TRY(ctl_download(h));
+      if (h->flush_l2) {
+        float ims = 0;
+        CUDA_TRY(h, cudaEventElapsedTime(&ims, h->it_ev[0], h->it_ev[1]));
+        flushed_ms += ims;
+      }
+      if (fixed_iters <= 0) VC_TRY(report());
+    }
+  } else {
+    // free-running: enqueue batches; the device decides, the host only looks at `done` between batches
+    const int batch = fixed_iters > 0 ? 32 : 4;
+    int queued = 0;
+    while (queued < max_it) {
+      const int n = std::min(batch, max_it - queued);
+      for (int k = 0; k < n; ++k) VC_TRY(enqueue_iteration(h, weights));
+      queued += n;
+      if (fixed_iters > 0 && queued < max_it) continue;  // benchmark mode: no intermediate sync at all
+      VC_TRY(ctl_download(h));
+      if (h->h_ctl->done) break;
+    }
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  VC_TRY(ctl_download(h));
+  CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  const Ctl& c = *h->h_ctl;
+  vcgpu_summary sum;
+  std::memset(&sum, 0, sizeof sum);
+  sum.num_residuals = num_residuals(h);
+  sum.iterations = c.iter;
+  sum.successful_steps = c.successful;
+  sum.termination = c.done ? c.done - 1 : VCGPU_TERM_NO_CONVERGENCE;
+  sum.initial_cost = c.initial_cost;
+  sum.final_cost = c.cost;
+  sum.device_seconds = (h->flush_l2 ? flushed_ms : ms) * 1e-3;
+  sum.kernel_launches = static_cast<int>(h->launches - launches0);
+  h->blocks_valid = true;
+  VC_TRY(download_state(h));
+  write_mirrors(h);
+  if (out) *out = sum;
+  return VCGPU_OK;
+}

@@ -23,14 +23,25 @@ static_assert(kFusedLd % 16 == 4, "fragment loads need ld == 4 (mod 16)");
 
 struct FusedArgs {
   DevProblem dp;
-  const double* state;
+  const Ctl* ctl;
+  int which;
+  const double* state[2];
   const int32_t *grp_start, *grp_count, *group_of;
   const double* obs;   // SoA [5][n_obs]
   int64_t n_obs;
   const double* mask;  // [G]
-  Blocks out;
+  Blocks out[2];
   double* Cg;          // [n_groups][kCgStride]
   double* cost_part;   // [n_frames]
+  // apply_update: this launch first forms the trial state x_new = x_cur (+) step for its frame (and
+  // block 0 for the globals) — the back-substitution of the arrow solve — then evaluates there.
+  int apply_update;
+  const double* scale;
+  const double* D2x;   // explicit damping or null (LM rule)
+  const double* X;     // [nf][FD][G+1] per-frame solutions, or null when the chain solver wrote delta
+  double* delta;       // scaled step [nf*FD + G]
+  double* states_rw[2];
+  double* step_part;   // [n_frames + 1][4]
 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -91,17 +102,134 @@ __device__ __forceinline__ double eval_obs_to_tile(const double* T, const double
 template <int FD>
 __global__ void __launch_bounds__(kFusedThreads) fused_build_kernel(FusedArgs a) {
   extern __shared__ double smem[];
+  if (a.ctl->done) return;
+  const int buf = a.which ? 1 - a.ctl->cur : a.ctl->cur;
+  const double* state = a.state[buf];
+  const Blocks& out = a.out[buf];
   double* tile = smem;                                   // [24][kFusedLd]
   double* red = tile + kFusedCols * kFusedLd;            // [warps][6][64]
   double* smB = red + kFusedWarps * 6 * 64;              // [FD*FD]
   double* smg = smB + FD * FD;                           // [FD]
   double* wcost = smg + FD;                              // [warps]
+  double* smT = wcost + kFusedWarps;                     // [7] trial frame pose
+  double* smCam = smT + 8;                               // [kMaxCams][kCamStateStride] trial camera states
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = a.dp.G, nf = a.dp.n_frames;
   for (int k = tid; k < FD * FD + FD; k += kFusedThreads) smB[k] = 0.0;
-  double* Ef = a.out.E + static_cast<int64_t>(f) * FD * G;
+  double* Ef = out.E + static_cast<int64_t>(f) * FD * G;
   for (int k = tid; k < FD * G; k += kFusedThreads) Ef[k] = 0.0;
-  const double* T = a.state + 7 * static_cast<int64_t>(f);
+  const double* T = state + 7 * static_cast<int64_t>(f);
+  const double* camBase = state + a.dp.off_cam;
+  if (a.apply_update) {
+    const int cur = a.ctl->cur;
+    const Blocks& bc = a.out[cur];
+    const double* x_cur = a.states_rw[cur];
+    double* x_new = a.states_rw[1 - cur];
+    const double rinv = 1.0 / a.ctl->radius;
+    const int M = G + 1;
+    const int64_t nfp = static_cast<int64_t>(nf) * FD;
+    const double* dc = a.delta + nfp;
+    const double* scg = a.scale + nfp;
+    if (warp == 0) {  // this frame's step and pose
+      double d[FD];
+      if (a.X) {
+        const double* Xf = a.X + static_cast<int64_t>(f) * FD * M;
+#pragma unroll
+        for (int r = 0; r < FD; ++r) {
+          double s = 0.0;
+          for (int c = lane; c < G; c += 32) s += Xf[r * M + c] * dc[c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          d[r] = -Xf[r * M + G] - s;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < FD; ++r) d[r] = a.delta[static_cast<int64_t>(f) * FD + r];
+      }
+      if (lane == 0) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0}, du[FD];
+#pragma unroll
+        for (int r = 0; r < FD; ++r) {
+          const int64_t k = static_cast<int64_t>(f) * FD + r;
+          const double sc = a.scale[k];
+          const double d2 = a.D2x ? a.D2x[k] : lm_damp(bc.B[k * FD + r], sc, rinv);
+          a.delta[k] = d[r];
+          acc[0] += d[r] * bc.gf[k] * sc;
+          acc[1] += d[r] * d[r] * d2;
+          du[r] = d[r] * sc;
+        }
+        const double* x = x_cur + 7 * static_cast<int64_t>(f);
+        double xo[7];
+        se3_plus(x, du, xo);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          x_new[7 * static_cast<int64_t>(f) + k] = xo[k];
+          smT[k] = xo[k];
+          acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+          acc[3] += xo[k] * xo[k];
+        }
+        const double* v = x_cur + a.dp.off_v + 3 * static_cast<int64_t>(f);
+        double* vo = x_new + a.dp.off_v + 3 * static_cast<int64_t>(f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double nv = (FD == 9) ? v[k] + du[(FD == 9) ? 6 + k : 0] : v[k];
+          vo[k] = nv;
+          if (FD == 9) {
+            acc[2] += (nv - v[k]) * (nv - v[k]);
+            acc[3] += nv * nv;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a.step_part[4 * static_cast<int64_t>(f) + q] = acc[q];
+      }
+    } else if (warp == 1 && lane < a.dp.n_cams) {  // trial camera states (every CTA needs them)
+      const int c = lane;
+      const CamInfo& ci = a.dp.cams[c];
+      const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
+      double* xo = smCam + kCamStateStride * c;
+      double du[3], qo[4];
+      for (int k = 0; k < 3; ++k) du[k] = dc[ci.goff + k] * scg[ci.goff + k];
+      so3_plus(x, du, qo);
+      for (int k = 0; k < 4; ++k) xo[k] = qo[k];
+      for (int k = 0; k < 3; ++k) xo[4 + k] = x[4 + k] + dc[ci.goff + 3 + k] * scg[ci.goff + 3 + k];
+      for (int k = 0; k < 10; ++k) xo[7 + k] = x[7 + k] + (k < ci.K ? dc[ci.goff + 6 + k] * scg[ci.goff + 6 + k] : 0.0);
+      if (f == 0) {
+        double* xg = x_new + a.dp.off_cam + kCamStateStride * c;
+        for (int k = 0; k < kCamStateStride; ++k) xg[k] = xo[k];
+      }
+    } else if (warp == 2 && lane == 0 && f == 0) {  // IMU globals + the globals' share of the step reductions
+      double g4[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int c = 0; c < a.dp.n_cams; ++c) {
+        const CamInfo& ci = a.dp.cams[c];
+        const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
+        double du[3], qo[4];
+        for (int k = 0; k < 3; ++k) du[k] = dc[ci.goff + k] * scg[ci.goff + k];
+        so3_plus(x, du, qo);
+        for (int k = 0; k < 4; ++k) { g4[2] += (qo[k] - x[k]) * (qo[k] - x[k]); g4[3] += qo[k] * qo[k]; }
+        for (int k = 0; k < 3 + ci.K; ++k) {
+          const double dd = dc[ci.goff + 3 + k] * scg[ci.goff + 3 + k], nv = x[4 + k] + dd;
+          g4[2] += dd * dd;
+          g4[3] += nv * nv;
+        }
+      }
+      const double* x = x_cur + a.dp.off_imu;
+      double* xo = x_new + a.dp.off_imu;
+      for (int k = 0; k < kImuStateSize; ++k) {
+        const double dd = a.dp.inertial ? dc[a.dp.imu_goff + k] * scg[a.dp.imu_goff + k] : 0.0;
+        xo[k] = x[k] + dd;
+        if (a.dp.inertial) { g4[2] += dd * dd; g4[3] += xo[k] * xo[k]; }
+      }
+      for (int k = 0; k < G; ++k) {
+        const double d2 = a.D2x ? a.D2x[nfp + k] : lm_damp(bc.C[k * G + k], scg[k], rinv);
+        g4[0] += dc[k] * bc.gc[k] * scg[k];
+        g4[1] += dc[k] * dc[k] * d2;
+      }
+      for (int q = 0; q < 4; ++q) a.step_part[4 * static_cast<int64_t>(nf) + q] = g4[q];
+    }
+    __syncthreads();
+    T = smT;
+    camBase = smCam;
+  }
   double cost = 0.0;
   for (int c = 0; c < a.dp.n_cams; ++c) {
     const int g = a.group_of[c * nf + f];
@@ -109,7 +237,7 @@ __global__ void __launch_bounds__(kFusedThreads) fused_build_kernel(FusedArgs a)
     const CamInfo& ci = a.dp.cams[c];
     const int W = 13 + ci.K;
     const int start = a.grp_start[g], cnt = a.grp_count[g];
-    const double* cam = a.state + a.dp.off_cam + kCamStateStride * c;
+    const double* cam = camBase + kCamStateStride * c;
     const double* mask = a.mask + ci.goff;
     double acc[6][2];
 #pragma unroll
@@ -186,9 +314,9 @@ __global__ void __launch_bounds__(kFusedThreads) fused_build_kernel(FusedArgs a)
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_down_sync(0xffffffffu, cost, o);
   if (lane == 0) wcost[warp] = cost;
   __syncthreads();
-  double* Bf = a.out.B + static_cast<int64_t>(f) * FD * FD;
+  double* Bf = out.B + static_cast<int64_t>(f) * FD * FD;
   for (int k = tid; k < FD * FD; k += kFusedThreads) Bf[k] = smB[k];
-  for (int k = tid; k < FD; k += kFusedThreads) a.out.gf[static_cast<int64_t>(f) * FD + k] = smg[k];
+  for (int k = tid; k < FD; k += kFusedThreads) out.gf[static_cast<int64_t>(f) * FD + k] = smg[k];
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < kFusedWarps; ++w) s += wcost[w];

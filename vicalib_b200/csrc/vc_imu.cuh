@@ -22,7 +22,9 @@ constexpr int kImuCgStride = 136;  // 15*16/2 = 120 packed sym + 15 gradient (+1
 struct ImuEvalArgs {
   DevProblem dp;
   imu::ImuBuf buf;
-  const double* state;
+  const Ctl* ctl;
+  int which;
+  const double* states[2];
   const double* ftime;
   const double* wsqrt;  // [ni][81]
   const double* mask;   // 15 IMU global columns
@@ -52,14 +54,15 @@ __global__ void __launch_bounds__(32 * kImuWarps) imu_eval_kernel(ImuEvalArgs a)
   using imu::D1;
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * kImuWarps + (threadIdx.x >> 5);
-  if (k >= a.ni) return;
+  if (k >= a.ni || a.ctl->done) return;
+  const double* state = a.states[a.which ? 1 - a.ctl->cur : a.ctl->cur];
   // lane -> Jacobian column: pose2 0-5 | pose1 6-11 | (v2 12-14 analytic) | v1 15-17 | g 18-19 | b 20-25 | sf 26-31 | ts 32
   const int col = lane < 12 ? lane : lane + 3;
-  const double* X2 = a.state + 7 * static_cast<int64_t>(k + 1);
-  const double* X1 = a.state + 7 * static_cast<int64_t>(k);
-  const double* V2 = a.state + a.dp.off_v + 3 * static_cast<int64_t>(k + 1);
-  const double* V1 = a.state + a.dp.off_v + 3 * static_cast<int64_t>(k);
-  const double* P = a.state + a.dp.off_imu;  // g2 b6 sf6 ts
+  const double* X2 = state + 7 * static_cast<int64_t>(k + 1);
+  const double* X1 = state + 7 * static_cast<int64_t>(k);
+  const double* V2 = state + a.dp.off_v + 3 * static_cast<int64_t>(k + 1);
+  const double* V1 = state + a.dp.off_v + 3 * static_cast<int64_t>(k);
+  const double* P = state + a.dp.off_imu;  // g2 b6 sf6 ts
   double s2[7], s1[7];
   se3_local_column(X2, col < 6 ? col : 0, s2);
   se3_local_column(X1, (col >= 6 && col < 12) ? col - 6 : 0, s1);
@@ -143,8 +146,10 @@ __global__ void __launch_bounds__(32 * kImuWarps) imu_eval_kernel(ImuEvalArgs a)
 // ---------------------------------------------------------------- IMU -> frame blocks
 struct ImuAccArgs {
   DevProblem dp;
+  const Ctl* ctl;
+  int which;
   const double *r, *J;  // [ni][9], [ni][9*33] (loss-corrected, masked)
-  Blocks out;
+  Blocks outs[2];
   double* Cg;  // [ni][kImuCgStride]
   int ni;
 };
@@ -155,6 +160,8 @@ __device__ __forceinline__ int imu_local_col(int c) {
 __global__ void __launch_bounds__(128) imu_accumulate_kernel(ImuAccArgs a) {
   // one CTA per frame f: interval f-1 (f is its second frame) and interval f (f is its first frame)
   __shared__ double Jl[2][9][34];  // [which][row][local col 0..32, 33 = residual]
+  if (a.ctl->done) return;
+  const Blocks& out = a.outs[a.which ? 1 - a.ctl->cur : a.ctl->cur];
   const int f = blockIdx.x, tid = threadIdx.x, G = a.dp.G, nf = a.dp.n_frames, io = a.dp.imu_goff;
   const bool hasP = f > 0, hasN = f < nf - 1;
   for (int e = tid; e < 2 * 9 * 34; e += 128) {
@@ -166,10 +173,10 @@ __global__ void __launch_bounds__(128) imu_accumulate_kernel(ImuAccArgs a) {
   }
   __syncthreads();
   const double m = a.dp.imu_mult;
-  double* Bf = a.out.B + static_cast<int64_t>(f) * 81;
-  double* Uf = a.out.U + static_cast<int64_t>(f) * 81;
-  double* Ef = a.out.E + static_cast<int64_t>(f) * 9 * G;
-  double* gf = a.out.gf + static_cast<int64_t>(f) * 9;
+  double* Bf = out.B + static_cast<int64_t>(f) * 81;
+  double* Uf = out.U + static_cast<int64_t>(f) * 81;
+  double* Ef = out.E + static_cast<int64_t>(f) * 9 * G;
+  double* gf = out.gf + static_cast<int64_t>(f) * 9;
   // B (81) | U (81) | E imu columns (9*15) | g (9) | Cg of interval f (120 + 15)
   for (int e = tid; e < 81 + 81 + 135 + 9 + 135; e += 128) {
     if (e < 81) {

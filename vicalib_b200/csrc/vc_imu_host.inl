@@ -117,12 +117,14 @@ static int imu_prepare(vcgpu_handle* h) {
   return VCGPU_OK;
 }
 
-static int imu_evaluate(vcgpu_handle* h, int buf, bool apply_loss, int* n_cost, const double* mask_dev = nullptr) {
+static int imu_evaluate(vcgpu_handle* h, int which, bool apply_loss, int* n_cost, const double* mask_dev = nullptr) {
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
   const int ni = dp.n_frames - 1;
   ImuEvalArgs a;
-  a.dp = dp; a.buf = d->buf; a.state = h->d_state[buf]; a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
+  a.dp = dp; a.buf = d->buf; a.ctl = h->d_ctl; a.which = which;
+  a.states[0] = h->d_state[0]; a.states[1] = h->d_state[1];
+  a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
   a.mask = (mask_dev ? mask_dev : h->d_mask) + dp.imu_goff;
   a.r = h->d_imu_r; a.J = h->d_imu_J; a.cost = d->cost; a.ni = ni; a.apply_loss = apply_loss ? 1 : 0;
   a.mult = dp.imu_mult;
@@ -133,11 +135,13 @@ static int imu_evaluate(vcgpu_handle* h, int buf, bool apply_loss, int* n_cost, 
   return VCGPU_OK;
 }
 static const double* imu_cost_part(vcgpu_handle* h) { return imu_dev(h) ? imu_dev(h)->cost : nullptr; }
+static const double* imu_cg(vcgpu_handle* h) { return imu_dev(h) ? imu_dev(h)->Cg : nullptr; }
 
-static int imu_accumulate(vcgpu_handle* h, int buf) {
+static int imu_accumulate(vcgpu_handle* h, int which) {
   vc::ImuDev* d = imu_dev(h);
   ImuAccArgs a;
-  a.dp = h->dp; a.r = h->d_imu_r; a.J = h->d_imu_J; a.out = h->blk[buf]; a.Cg = d->Cg; a.ni = h->dp.n_frames - 1;
+  a.dp = h->dp; a.ctl = h->d_ctl; a.which = which; a.r = h->d_imu_r; a.J = h->d_imu_J;
+  a.outs[0] = h->blk[0]; a.outs[1] = h->blk[1]; a.Cg = d->Cg; a.ni = h->dp.n_frames - 1;
   imu_accumulate_kernel<<<h->dp.n_frames, 128, 0, h->stream>>>(a);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
@@ -153,14 +157,14 @@ static int imu_reduce_globals(vcgpu_handle* h) {
   return VCGPU_OK;
 }
 
-// forward elimination of the frame chain + dense solve; the step lands in d_delta
-static int imu_chain_solve(vcgpu_handle* h, int buf, const double* D2) {
+// forward elimination of the frame chain; the summed Schur partials land in Ssum
+static int imu_chain_eliminate(vcgpu_handle* h, const double* D2x) {
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
   constexpr int FD = 9;
   const int G = dp.G;
   const size_t NS = static_cast<size_t>(G) * G + G;
-  chain_init_kernel<FD><<<dp.n_frames, 128, 0, h->stream>>>(dp, h->blk[buf], h->d_scale, D2, d->levels[0]);
+  chain_init_kernel<FD><<<dp.n_frames, 128, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, D2x, d->levels[0]);
   ++h->launches;
   const size_t w_cols = 2 * FD + G + 1;
   const size_t esm = (NS + 3 * FD * FD + FD * G + FD + static_cast<size_t>(kChainC - 1) * FD * (FD + w_cols)) * sizeof(double);
@@ -173,19 +177,28 @@ static int imu_chain_solve(vcgpu_handle* h, int buf, const double* D2) {
   int part = 0;
   for (size_t l = 0; l + 1 < d->levels.size(); ++l) {
     ElimArgs ea;
-    ea.G = G; ea.c = kChainC; ea.cur = d->levels[l]; ea.next = d->levels[l + 1];
+    ea.G = G; ea.c = kChainC; ea.ctl = h->d_ctl; ea.cur = d->levels[l]; ea.next = d->levels[l + 1];
     ea.Spart = h->d_Spart + static_cast<size_t>(part) * NS; ea.scalars = h->d_scalars;
     const int nsep = d->levels[l + 1].n;
     chain_eliminate_kernel<FD><<<nsep, kChainThreads, esm, h->stream>>>(ea);
     ++h->launches;
     part += nsep;
   }
-  sum_partials_kernel<<<static_cast<int>((NS + 31) / 32), 256, 0, h->stream>>>(h->d_Spart, part, static_cast<int>(NS), d->Ssum);
+  sum_partials_kernel<<<static_cast<int>((NS + 31) / 32), 256, 0, h->stream>>>(h->d_Spart, part, static_cast<int>(NS), d->Ssum, h->d_ctl);
   ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
+// dense solve of [globals | top-level nodes]; globals and top-node steps land in d_delta
+static int imu_chain_dense(vcgpu_handle* h, const double* D2x) {
+  vc::ImuDev* d = imu_dev(h);
+  const DevProblem& dp = h->dp;
+  constexpr int FD = 9;
   DenseArgs da;
-  da.dp = dp; da.b = h->blk[buf]; da.scale = h->d_scale; da.D2 = D2; da.Ssum = d->Ssum; da.top = d->levels.back();
-  da.delta = h->d_delta; da.scalars = h->d_scalars;
-  const size_t N = G + static_cast<size_t>(d->levels.back().n) * FD;
+  da.dp = dp; da.bs[0] = h->blk[0]; da.bs[1] = h->blk[1]; da.ctl = h->d_ctl; da.scale = h->d_scale; da.D2x = D2x;
+  da.Ssum = d->Ssum; da.top = d->levels.back(); da.delta = h->d_delta; da.scalars = h->d_scalars;
+  const size_t N = dp.G + static_cast<size_t>(d->levels.back().n) * FD;
   dense_solve_kernel<FD><<<1, 256, (N * N + N) * sizeof(double), h->stream>>>(da);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
@@ -193,41 +206,47 @@ static int imu_chain_solve(vcgpu_handle* h, int buf, const double* D2) {
 }
 
 // back-substitution through the levels (top-down), then x (+) delta
-static int imu_chain_backsub(vcgpu_handle* h, int buf, const double* D2) {
+static int imu_chain_backsub(vcgpu_handle* h, const double* D2x, bool explicit_update) {
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
   constexpr int FD = 9;
   for (int l = static_cast<int>(d->levels.size()) - 2; l >= 0; --l) {
     BacksubArgs ba;
-    ba.G = dp.G; ba.c = kChainC; ba.nfp_off = 0; ba.cur = d->levels[l]; ba.delta = h->d_delta;
+    ba.ctl = h->d_ctl; ba.G = dp.G; ba.c = kChainC; ba.nfp_off = 0; ba.cur = d->levels[l]; ba.delta = h->d_delta;
     ba.nfp = static_cast<int64_t>(dp.n_frames) * FD;
     chain_backsub_kernel<FD><<<(d->levels[l].n + 3) / 4, 128, 0, h->stream>>>(ba);
     ++h->launches;
   }
-  UpdateArgs ua;
-  ua.dp = dp; ua.b = h->blk[buf]; ua.scale = h->d_scale; ua.D2 = D2; ua.X = nullptr; ua.delta = h->d_delta;
-  ua.x_cur = h->d_state[buf]; ua.x_new = h->d_state[1 - buf]; ua.step_part = h->d_red;
-  const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
-  backsub_update_kernel<9><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
-  ++h->launches;
+  if (explicit_update) {  // otherwise the fused evaluate kernel applies x (+) delta itself
+    UpdateArgs ua;
+    ua.dp = dp; ua.b[0] = h->blk[0]; ua.b[1] = h->blk[1]; ua.ctl = h->d_ctl; ua.scale = h->d_scale; ua.D2x = D2x;
+    ua.X = nullptr; ua.delta = h->d_delta; ua.state[0] = h->d_state[0]; ua.state[1] = h->d_state[1];
+    ua.step_part = h->d_red;
+    const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
+    backsub_update_kernel<9><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
+    ++h->launches;
+  }
   CUDA_TRY(h, cudaGetLastError());
   return VCGPU_OK;
 }
 
 // UpdateImuWeights (vicalibrator.h:723-799): active only when inertial && !rotation_only (:725)
-static int imu_update_weights(vcgpu_handle* h, int buf) {
+static int imu_update_weights(vcgpu_handle* h) {
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
   if (!dp.inertial || dp.rotation_only) return VCGPU_OK;
   StageScope st(h, VCGPU_STAGE_IMU_WEIGHTS);
   vc::wts::WeightArgs a;
-  a.dp = dp; a.buf = d->buf; a.state = h->d_state[buf]; a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
+  a.dp = dp; a.buf = d->buf; a.ctl = h->d_ctl; a.states[0] = h->d_state[0]; a.states[1] = h->d_state[1];
+  a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
   a.ni = dp.n_frames - 1; a.sigma_g = h->sigma_g; a.sigma_a = h->sigma_a;
   vc::wts::imu_weights_kernel<<<(a.ni + vc::wts::kWtWarps - 1) / vc::wts::kWtWarps, 32 * vc::wts::kWtWarps, 0, h->stream>>>(a);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
   return VCGPU_OK;
 }
+
+static int ctl_reset(vcgpu_handle* h, int fixed, int max_iters);
 
 static int imu_eval_hook(vcgpu_handle* h, double* r, double* J) {
   const DevProblem& dp = h->dp;
@@ -237,8 +256,9 @@ static int imu_eval_hook(vcgpu_handle* h, double* r, double* J) {
   VC_TRY(dev_alloc(h, &ones, dp.G));
   std::vector<double> hones(dp.G, 1.0);
   CUDA_TRY(h, cudaMemcpy(ones, hones.data(), dp.G * sizeof(double), cudaMemcpyHostToDevice));
+  VC_TRY(ctl_reset(h, 0, 0));
   int nc = 0;
-  VC_TRY(imu_evaluate(h, h->cur, false, &nc, ones));
+  VC_TRY(imu_evaluate(h, 0, false, &nc, ones));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   cudaFree(ones);
   h->blocks_valid = false;

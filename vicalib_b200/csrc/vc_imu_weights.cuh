@@ -289,7 +289,8 @@ __device__ inline Pose<double> integrate_imu_cov(const Pose<double>& pose, const
 struct WeightArgs {
   DevProblem dp;
   imu::ImuBuf buf;
-  const double* state;
+  const Ctl* ctl;
+  const double* states[2];
   const double* ftime;
   double* wsqrt;
   int ni;
@@ -301,12 +302,13 @@ __global__ void __launch_bounds__(32 * kWtWarps) imu_weights_kernel(WeightArgs a
   __shared__ Work work[kWtWarps];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int kk = blockIdx.x * kWtWarps + wid;
-  if (kk >= a.ni) return;
+  if (kk >= a.ni || a.ctl->done) return;
   Work* W = &work[wid];
-  const double* X1 = a.state + 7 * static_cast<int64_t>(kk);
-  const double* X2 = a.state + 7 * static_cast<int64_t>(kk + 1);
-  const double* V1 = a.state + a.dp.off_v + 3 * static_cast<int64_t>(kk);
-  const double* P = a.state + a.dp.off_imu;
+  const double* state = a.states[a.ctl->cur];
+  const double* X1 = state + 7 * static_cast<int64_t>(kk);
+  const double* X2 = state + 7 * static_cast<int64_t>(kk + 1);
+  const double* V1 = state + a.dp.off_v + 3 * static_cast<int64_t>(kk);
+  const double* P = state + a.dp.off_imu;
   const double ts = P[14];
   const double t_start = a.ftime[kk], t_end = a.ftime[kk + 1];
   // measurements.size() == 0 -> continue (vicalibrator.h:731-733)

@@ -41,6 +41,32 @@ struct Blocks {  // block normal equations (device pointers)
   double *B, *U, *E, *gf, *C, *gc, *cost;
 };
 
+// Trust-region state kept ON THE DEVICE so iterations can be enqueued back to back with no host
+// round trip: the accept/reject decision (Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy,
+// SURVEY App. A.3) is taken by decide_kernel and every kernel selects its buffers through `cur`.
+struct Ctl {
+  int cur;           // which double buffer holds the accepted point
+  int done;          // 0 = running, else 1 + VCGPU_TERM_*
+  int iter;          // iterations executed so far
+  int successful;    // accepted steps
+  int fixed;         // benchmark mode: never terminate on tolerances
+  int max_iters;
+  int last_accepted; // summary of the most recent iteration
+  int pad_;
+  double radius, decrease_factor;
+  double cost, x_norm, gmax, gnorm;
+  double function_tol, gradient_tol, param_tol;
+  double last_cost_change, last_rho, last_step_norm, last_cand_cost;
+  double initial_cost;
+};
+
+// damping of LevenbergMarquardtStrategy::ComputeStep: D^2 = clamp(diag(J'J), 1e-6, 1e32) / radius,
+// on the Jacobi-scaled system
+__host__ __device__ inline double lm_damp(double diag, double scale, double radius_inv) {
+  const double d = diag * scale * scale;
+  return (d < 1e-6 ? 1e-6 : (d > 1e32 ? 1e32 : d)) * radius_inv;
+}
+
 }  // namespace vc
 
 struct vcgpu_handle {
@@ -104,9 +130,13 @@ struct vcgpu_handle {
   double* d_Ssum = nullptr;       // [G*G+G] summed Schur partials
   int n_solve_blocks = 0;
   double* d_delta = nullptr;      // [nf*fd+G] scaled step
-  double* d_red = nullptr;        // small reduction scratch
+  double* d_red = nullptr;        // step reductions [n_frames+1][4]
+  double* d_red_part = nullptr;   // [kReduceBlocks][8] level-1 scalar partials
+  unsigned* d_counter = nullptr;  // last-CTA tickets
   double* d_scalars = nullptr;    // device scalars (see vcgpu.cu)
   double* h_scalars = nullptr;    // pinned mirror
+  vc::Ctl* d_ctl = nullptr;       // device-resident trust-region state
+  vc::Ctl* h_ctl = nullptr;       // pinned mirror
   // IMU
   double* d_imu = nullptr;        // [7][n_imu]: t w3 a3
   int n_imu = 0;

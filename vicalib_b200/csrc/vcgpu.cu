@@ -134,7 +134,9 @@ extern "C" int vcgpu_create(const vcgpu_config* cfg, vcgpu_handle** out) {
   h->device = dev;
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
-      cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), kScCount * sizeof(double)) != cudaSuccess) {
+      cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), kScCount * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&h->h_ctl), sizeof(Ctl)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&h->d_ctl), sizeof(Ctl)) != cudaSuccess) {
     delete h;
     return VCGPU_ERR_CUDA;
   }
@@ -153,10 +155,12 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_Cg); dev_free(&h->d_Cpart);
   dev_free(&h->d_blk_mem[0]); dev_free(&h->d_blk_mem[1]);
   dev_free(&h->d_scale); dev_free(&h->d_X); dev_free(&h->d_Spart); dev_free(&h->d_delta);
-  dev_free(&h->d_red); dev_free(&h->d_scalars); dev_free(&h->d_Ssum);
+  dev_free(&h->d_red); dev_free(&h->d_scalars); dev_free(&h->d_Ssum); dev_free(&h->d_red_part); dev_free(&h->d_counter);
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->d_ctl) cudaFree(h->d_ctl);
   if (h->d_flush) cudaFree(h->d_flush);
   if (h->it_ev[0]) {
     for (int s = 0; s < VCGPU_STAGE_COUNT; ++s)
@@ -453,11 +457,14 @@ static int prepare(vcgpu_handle* h) {
     const size_t np = static_cast<size_t>(nf) * fd + G;
     VC_TRY(dev_alloc(h, &h->d_scale, 2 * np));  // [scale | D2]
     VC_TRY(dev_alloc(h, &h->d_X, static_cast<size_t>(nf) * fd * (G + 1)));
-    h->n_solve_blocks = std::min((nf + kSolveWarps - 1) / kSolveWarps, 444);
+    h->n_solve_blocks = std::min((nf + kSolveWarps - 1) / kSolveWarps, 148);
     VC_TRY(dev_alloc(h, &h->d_Spart, static_cast<size_t>(h->n_solve_blocks) * NS));
     VC_TRY(dev_alloc(h, &h->d_Ssum, NS));
     VC_TRY(dev_alloc(h, &h->d_delta, np));
-    VC_TRY(dev_alloc(h, &h->d_red, 4 * (static_cast<size_t>((nf + kUpdateWarps - 1) / kUpdateWarps) + 1)));
+    VC_TRY(dev_alloc(h, &h->d_red, 4 * (static_cast<size_t>(nf) + 2)));
+    VC_TRY(dev_alloc(h, &h->d_red_part, 8 * kReduceBlocks));
+    VC_TRY(dev_alloc(h, &h->d_counter, 4));
+    CUDA_TRY(h, cudaMemset(h->d_counter, 0, 4 * sizeof(unsigned)));
     VC_TRY(dev_alloc(h, &h->d_scalars, kScCount));
     CUDA_TRY(h, cudaMemset(h->d_scalars, 0, kScCount * sizeof(double)));
     VC_TRY(imu_prepare(h));
@@ -478,353 +485,7 @@ static int prepare(vcgpu_handle* h) {
   return VCGPU_OK;
 }
 
-// ------------------------------------------------------------------ kernel launch helpers
-template <bool JAC>
-static void launch_eval_cam(vcgpu_handle* h, const EvalArgs& a, int model, int nblk) {
-  switch (model) {
-    case kLinear: eval_reproj_kernel<kLinear, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
-    case kFov: eval_reproj_kernel<kFov, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
-    case kPoly2: eval_reproj_kernel<kPoly2, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
-    case kPoly3: eval_reproj_kernel<kPoly3, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
-    default: eval_reproj_kernel<kKb4, JAC><<<nblk, 256, 0, h->stream>>>(a); break;
-  }
-  ++h->launches;
-}
-
-// residual (+ Jacobian) pass over every camera's observations at state buffer `buf`
-static int eval_reproj(vcgpu_handle* h, int buf, bool jac, bool apply_loss, const double* mask_dev) {
-  const DevProblem& dp = h->dp;
-  const int64_t n = h->n_obs;
-  int part = 0;
-  for (int c = 0; c < dp.n_cams; ++c) {
-    const CamInfo& ci = dp.cams[c];
-    if (ci.n_obs == 0) continue;
-    EvalArgs a;
-    a.state = h->d_state[buf];
-    a.cam = h->d_state[buf] + dp.off_cam + kCamStateStride * c;
-    a.frame = h->d_obs_frame + ci.obs_start;
-    a.pwx = h->d_obs + ci.obs_start;
-    a.pwy = h->d_obs + n + ci.obs_start;
-    a.pwz = h->d_obs + 2 * n + ci.obs_start;
-    a.pcu = h->d_obs + 3 * n + ci.obs_start;
-    a.pcv = h->d_obs + 4 * n + ci.obs_start;
-    a.mask = mask_dev + ci.goff;
-    a.r0 = h->d_r + ci.obs_start;
-    a.r1 = h->d_r + n + ci.obs_start;
-    a.J = h->d_J + ci.joff;
-    a.cost_part = h->d_cost_part + part;
-    a.n = ci.n_obs;
-    a.apply_loss = apply_loss ? 1 : 0;
-    a.mult = dp.visual_mult;
-    const int nblk = (ci.n_obs + 255) / 256;
-    part += nblk;
-    if (jac) launch_eval_cam<true>(h, a, ci.model, nblk);
-    else launch_eval_cam<false>(h, a, ci.model, nblk);
-  }
-  CUDA_TRY(h, cudaGetLastError());
-  return VCGPU_OK;
-}
-
-// full evaluation at state buffer `buf`: residuals, Jacobians, block normal equations into blk[buf];
-// scalars cost / gradient norms (and the step reductions when `with_step`) land in d_scalars.
-static int evaluate_into(vcgpu_handle* h, int buf, bool with_step) {
-  const DevProblem& dp = h->dp;
-  const bool visual = h->flags.visual && h->n_obs > 0;
-  const bool fused = !h->materialize;
-  if (visual && !fused) {
-    StageScope st(h, VCGPU_STAGE_EVAL_REPROJ);
-    VC_TRY(eval_reproj(h, buf, true, true, h->d_mask));
-  }
-  int n_imu_cost = 0;
-  if (dp.inertial) {
-    StageScope st(h, VCGPU_STAGE_IMU_EVAL);
-    VC_TRY(imu_evaluate(h, buf, true, &n_imu_cost));
-  }
-  BuildArgs ba;
-  ba.dp = dp;
-  if (!visual) ba.dp.n_cams = 0;
-  ba.grp_start = h->d_grp_start; ba.grp_count = h->d_grp_count; ba.group_of = h->d_group_of;
-  ba.r = h->d_r; ba.J = h->d_J; ba.n_obs = h->n_obs; ba.out = h->blk[buf]; ba.Cg = h->d_Cg;
-  int n_vis_cost = visual ? h->n_cost_part : 0;
-  if (fused) {
-    // evaluate + J^T J in one pass: the Jacobian tile lives in shared memory only
-    StageScope st(h, VCGPU_STAGE_BUILD);
-    FusedArgs fa;
-    fa.dp = ba.dp; fa.state = h->d_state[buf];
-    fa.grp_start = h->d_grp_start; fa.grp_count = h->d_grp_count; fa.group_of = h->d_group_of;
-    fa.obs = h->d_obs; fa.n_obs = h->n_obs; fa.mask = h->d_mask; fa.out = h->blk[buf]; fa.Cg = h->d_Cg;
-    fa.cost_part = h->d_cost_part;
-    const size_t fsm = (static_cast<size_t>(kFusedCols) * kFusedLd + kFusedWarps * 384 + 9 * 9 + 9 + kFusedWarps) * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-      CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
-      CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
-      attr_done = true;
-    }
-    if (dp.fd == 6) fused_build_kernel<6><<<dp.n_frames, kFusedThreads, fsm, h->stream>>>(fa);
-    else fused_build_kernel<9><<<dp.n_frames, kFusedThreads, fsm, h->stream>>>(fa);
-    ++h->launches;
-    n_vis_cost = dp.n_frames;
-    if (dp.inertial) VC_TRY(imu_accumulate(h, buf));
-  } else {
-    const size_t bsm = (2 * kBuildChunk * kMaxW + 9 * 9 + 9) * sizeof(double);
-    StageScope st(h, VCGPU_STAGE_BUILD);
-    if (dp.fd == 6) build_frames_kernel<6><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
-    else build_frames_kernel<9><<<dp.n_frames, kBuildThreads, bsm, h->stream>>>(ba);
-    ++h->launches;
-    if (dp.inertial) VC_TRY(imu_accumulate(h, buf));
-  }
-  const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
-  ReduceArgs ra;
-  ra.dp = ba.dp; ra.Cg = h->d_Cg; ra.Cpart = h->d_Cpart;
-  {
-    StageScope st(h, VCGPU_STAGE_REDUCE);
-    reduce_globals_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
-    ++h->launches;
-    if (dp.inertial) VC_TRY(imu_reduce_globals(h));
-  }
-  FinalizeArgs fa;
-  fa.dp = dp; fa.Cpart = h->d_Cpart;
-  fa.cost_part = h->d_cost_part; fa.n_cost_part = n_vis_cost;
-  fa.imu_cost_part = imu_cost_part(h); fa.n_imu_cost_part = n_imu_cost;
-  fa.step_part = with_step ? h->d_red : nullptr;
-  fa.n_step_part = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps + 1;
-  fa.out = h->blk[buf]; fa.scalars = h->d_scalars;
-  {
-    StageScope st(h, VCGPU_STAGE_FINALIZE);
-    finalize_globals_kernel<<<1, kFinalizeThreads, 0, h->stream>>>(fa);
-    ++h->launches;
-  }
-  CUDA_TRY(h, cudaGetLastError());
-  return VCGPU_OK;
-}
-
-static int read_scalars(vcgpu_handle* h) {
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, kScCount * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  stage_collect(h);
-  return VCGPU_OK;
-}
-
-static int compute_diag(vcgpu_handle* h, int buf, int mode, double factor, double* out) {
-  const DevProblem& dp = h->dp;
-  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
-  StageScope st(h, VCGPU_STAGE_DIAG);
-  diag_kernel<<<static_cast<int>((np + 255) / 256), 256, 0, h->stream>>>(dp, h->blk[buf], h->d_scale, out, mode, factor);
-  ++h->launches;
-  CUDA_TRY(h, cudaGetLastError());
-  return VCGPU_OK;
-}
-
-// damped arrow solve with blocks of `buf` and D2 = d_scale + np; step -> d_delta; trial state -> d_state[1-buf]
-static int solve_and_update(vcgpu_handle* h, int buf) {
-  const DevProblem& dp = h->dp;
-  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
-  const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
-  const double* D2 = h->d_scale + np;
-  CUDA_TRY(h, cudaMemsetAsync(h->d_scalars + kScNotPD, 0, sizeof(double), h->stream));
-  if (dp.inertial) {
-    StageScope st(h, VCGPU_STAGE_FRAME_SOLVE);
-    VC_TRY(imu_chain_solve(h, buf, D2));
-  } else {
-    StageScope st(h, VCGPU_STAGE_FRAME_SOLVE);
-    SolveArgs sa;
-    sa.dp = dp; sa.b = h->blk[buf]; sa.scale = h->d_scale; sa.D2 = D2; sa.X = h->d_X; sa.Spart = h->d_Spart;
-    sa.scalars = h->d_scalars;
-    const size_t ssm = (NS + static_cast<size_t>(kSolveWarps) * 2 * 6 * (dp.G + 1)) * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-      CUDA_TRY(h, cudaFuncSetAttribute(frame_solve_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_done = true;
-    }
-    frame_solve_kernel<6><<<h->n_solve_blocks, kSolveThreads, ssm, h->stream>>>(sa);
-    ++h->launches;
-    sum_partials_kernel<<<static_cast<int>((NS + 31) / 32), 256, 0, h->stream>>>(h->d_Spart, h->n_solve_blocks, static_cast<int>(NS), h->d_Ssum);
-    ++h->launches;
-  }
-  GlobalSolveArgs ga;
-  ga.dp = dp; ga.b = h->blk[buf]; ga.scale = h->d_scale; ga.D2 = D2; ga.Spart = h->d_Ssum;
-  ga.n_spart = 1; ga.delta = h->d_delta; ga.scalars = h->d_scalars;
-  if (!dp.inertial) {  // the chain path ends in its own dense solve (globals + top-level nodes)
-    StageScope st(h, VCGPU_STAGE_GLOBAL_SOLVE);
-    global_solve_kernel<<<1, 256, NS * sizeof(double), h->stream>>>(ga);
-    ++h->launches;
-  }
-  if (dp.inertial) {
-    StageScope st(h, VCGPU_STAGE_BACKSUB);
-    VC_TRY(imu_chain_backsub(h, buf, D2));
-  } else {
-    StageScope st(h, VCGPU_STAGE_BACKSUB);
-    UpdateArgs ua;
-    ua.dp = dp; ua.b = h->blk[buf]; ua.scale = h->d_scale; ua.D2 = D2; ua.X = h->d_X; ua.delta = h->d_delta;
-    ua.x_cur = h->d_state[buf]; ua.x_new = h->d_state[1 - buf]; ua.step_part = h->d_red;
-    const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
-    backsub_update_kernel<6><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
-    ++h->launches;
-  }
-  CUDA_TRY(h, cudaGetLastError());
-  return VCGPU_OK;
-}
-
-static double host_state_norm(const vcgpu_handle* h) {
-  double s = 0;
-  for (double v : h->h_T) s += v * v;
-  if (h->flags.inertial) for (double v : h->h_v) s += v * v;
-  for (int c = 0; c < h->n_cams; ++c) {
-    for (int i = 0; i < 4; ++i) s += h->h_qck[4 * c + i] * h->h_qck[4 * c + i];
-    for (int i = 0; i < 3; ++i) s += h->h_pck[3 * c + i] * h->h_pck[3 * c + i];
-    for (int i = 0; i < num_intr(h->h_model[c]); ++i) s += h->h_intr[10 * c + i] * h->h_intr[10 * c + i];
-  }
-  if (h->flags.inertial) {
-    s += h->h_g[0] * h->h_g[0] + h->h_g[1] * h->h_g[1] + h->h_ts * h->h_ts;
-    for (int i = 0; i < 6; ++i) s += h->h_b[i] * h->h_b[i] + h->h_sf[i] * h->h_sf[i];
-  }
-  return std::sqrt(s);
-}
-
-static int num_residuals(const vcgpu_handle* h) {
-  int64_t n = 0;
-  if (h->flags.visual) {
-    int64_t act = 0;
-    for (uint8_t a : h->h_active) act += a;
-    n += static_cast<int64_t>(2 * act * h->flags.visual_mult);
-  }
-  if (h->flags.inertial && h->n_frames > 1) n += static_cast<int64_t>(9 * (h->n_frames - 1) * h->flags.imu_mult);
-  return static_cast<int>(n);
-}
-
-// ------------------------------------------------------------------ the trust-region loop
-static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out, int fixed_iters) {
-  VC_TRY(prepare(h));
-  if (h->opts.strategy != 0) return fail(h, VCGPU_ERR_INVALID, "DOGLEG strategy is not implemented on the device yet; use strategy 0 (LM)");
-  const DevProblem& dp = h->dp;
-  const vcgpu_options& o = h->opts;
-  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
-  const long launches0 = h->launches;
-  vcgpu_summary sum;
-  std::memset(&sum, 0, sizeof sum);
-  sum.num_residuals = num_residuals(h);
-  const bool weights = o.update_imu_weights && dp.inertial;
-  if (weights) VC_TRY(imu_update_weights(h, h->cur));  // vicalibrator.h:955
-  VC_TRY(evaluate_into(h, h->cur, false));
-  if (o.jacobi_scaling) {
-    VC_TRY(compute_diag(h, h->cur, 0, 0.0, h->d_scale));
-  } else {
-    std::vector<double> ones(np, 1.0);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_scale, ones.data(), np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  }
-  VC_TRY(read_scalars(h));
-  h->blocks_valid = true;
-  double cost = h->h_scalars[kScCost], gmax = h->h_scalars[kScGmax], gnorm = std::sqrt(h->h_scalars[kScGnorm2]);
-  sum.initial_cost = cost;
-  double x_norm = host_state_norm(h);
-  double radius = o.init_radius, decrease_factor = 2.0;
-  int term = VCGPU_TERM_NO_CONVERGENCE;
-  bool done = false;
-  auto callback = [&](const vcgpu_iteration& it) -> int {
-    if (weights) { int rc = imu_update_weights(h, h->cur); if (rc) return rc; }  // vicalibrator.h:691
-    if (fixed_iters > 0) return 0;
-    if (cb && (o.update_state_every_iteration || h->mirror[3])) {
-      if (o.update_state_every_iteration) { int rc = download_state(h); if (rc) return rc; write_mirrors(h); }
-    }
-    int stop = 0;
-    if (cb) stop = cb(&it, user);
-    if (it.gradient_norm > 0 && it.gradient_norm < 1e-9) stop = 1;  // vicalibrator.h:713-717
-    return stop ? 1 : 0;
-  };
-  vcgpu_iteration it;
-  std::memset(&it, 0, sizeof it);
-  it.iteration = 0; it.step_is_successful = 1; it.cost = cost; it.gradient_max_norm = gmax; it.gradient_norm = gnorm;
-  it.trust_region_radius = radius;
-  if (fixed_iters <= 0 && gmax <= o.gradient_tol) { term = VCGPU_TERM_GRADIENT_TOL; done = true; }
-  if (!done) {
-    const int rc = callback(it);
-    if (rc < 0) return rc;
-    if (rc > 0) { term = VCGPU_TERM_CALLBACK; done = true; }
-  }
-  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-  double flushed_ms = 0.0;
-  const int max_it = fixed_iters > 0 ? fixed_iters : o.max_iters;
-  for (int iter = 1; !done; ++iter) {
-    if (iter > max_it) { term = VCGPU_TERM_NO_CONVERGENCE; break; }
-    if (radius < 1e-32) {
-      if (fixed_iters > 0) { radius = o.init_radius; decrease_factor = 2.0; }  // benchmark mode never stops early
-      else { term = VCGPU_TERM_RADIUS; break; }
-    }
-    sum.iterations = iter;
-    if (h->flush_l2) {
-      CUDA_TRY(h, cudaMemsetAsync(h->d_flush, iter & 0xff, 256u << 20, h->stream));
-      CUDA_TRY(h, cudaEventRecord(h->it_ev[0], h->stream));
-    }
-    // LevenbergMarquardtStrategy::ComputeStep: D = sqrt(clamp(diag(J'J)) / radius)
-    VC_TRY(compute_diag(h, h->cur, 1, 1.0 / radius, h->d_scale + np));
-    VC_TRY(solve_and_update(h, h->cur));
-    VC_TRY(evaluate_into(h, 1 - h->cur, true));
-    if (h->flush_l2) {
-      CUDA_TRY(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, kScCount * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      CUDA_TRY(h, cudaEventRecord(h->it_ev[1], h->stream));
-    }
-    VC_TRY(read_scalars(h));
-    if (h->flush_l2) {
-      float ims = 0;
-      CUDA_TRY(h, cudaEventElapsedTime(&ims, h->it_ev[0], h->it_ev[1]));
-      flushed_ms += ims;
-    }
-    const double* sc = h->h_scalars;
-    std::memset(&it, 0, sizeof it);
-    it.iteration = iter; it.cost = cost; it.gradient_max_norm = gmax; it.trust_region_radius = radius;
-    // model_cost_change = -step.g - step.H.step/2, with (H + D2) step = -g
-    const double model_change = -0.5 * sc[kScDotG] + 0.5 * sc[kScDotD];
-    if (sc[kScNotPD] > 0.0 || !(model_change > 0.0) || !std::isfinite(sc[kScCost])) {
-      radius /= decrease_factor; decrease_factor *= 2.0;  // StepIsInvalid / StepRejected
-      it.trust_region_radius = radius;
-      const int rc = callback(it);
-      if (rc < 0) return rc;
-      if (rc > 0) { term = VCGPU_TERM_CALLBACK; break; }
-      continue;
-    }
-    const double cand = sc[kScCost];
-    const double step_norm = std::sqrt(sc[kScStep2]);
-    const double cost_change = cost - cand;
-    it.step_norm = step_norm; it.cost_change = cost_change;
-    if (fixed_iters <= 0) {
-      if (step_norm <= o.param_tol * (x_norm + o.param_tol)) { term = VCGPU_TERM_PARAM_TOL; break; }
-      if (std::fabs(cost_change) <= o.function_tol * cost) { term = VCGPU_TERM_FUNCTION_TOL; break; }
-    }
-    const double rho = cost_change / model_change;
-    it.relative_decrease = rho;
-    if (rho > 1e-3) {
-      h->cur = 1 - h->cur;  // the candidate's blocks were built speculatively: accept = flip
-      cost = cand;
-      gmax = sc[kScGmax]; gnorm = std::sqrt(sc[kScGnorm2]);
-      x_norm = std::sqrt(sc[kScXnorm2]);
-      ++sum.successful_steps;
-      radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
-      decrease_factor = 2.0;
-      it.step_is_successful = 1; it.cost = cost; it.gradient_max_norm = gmax; it.gradient_norm = gnorm;
-      it.trust_region_radius = radius;
-      if (fixed_iters <= 0 && gmax <= o.gradient_tol) { term = VCGPU_TERM_GRADIENT_TOL; callback(it); break; }
-    } else {
-      radius /= decrease_factor; decrease_factor *= 2.0;
-      it.trust_region_radius = radius;
-    }
-    const int rc = callback(it);
-    if (rc < 0) return rc;
-    if (rc > 0) { term = VCGPU_TERM_CALLBACK; break; }
-  }
-  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
-  CUDA_TRY(h, cudaEventSynchronize(h->ev1));
-  float ms = 0;
-  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  sum.device_seconds = (h->flush_l2 ? flushed_ms : ms) * 1e-3;
-  sum.termination = term;
-  sum.final_cost = cost;
-  sum.kernel_launches = static_cast<int>(h->launches - launches0);
-  VC_TRY(download_state(h));
-  write_mirrors(h);
-  if (out) *out = sum;
-  return VCGPU_OK;
-}
+#include "vc_engine.inl"
 
 extern "C" int vcgpu_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out) {
   if (!h) return VCGPU_ERR_INVALID;
@@ -839,7 +500,8 @@ extern "C" int vcgpu_iterate(vcgpu_handle* h, int n, vcgpu_summary* out) {
 extern "C" int vcgpu_cost(vcgpu_handle* h, double* cost) {
   if (!h || !cost) return VCGPU_ERR_INVALID;
   VC_TRY(prepare(h));
-  VC_TRY(evaluate_into(h, h->cur, false));
+  VC_TRY(ctl_reset(h, 0, 0));
+  VC_TRY(evaluate_into(h, 0, false, -1));
   VC_TRY(read_scalars(h));
   *cost = h->h_scalars[kScCost];
   return VCGPU_OK;
@@ -850,7 +512,8 @@ extern "C" int vcgpu_evaluate(vcgpu_handle* h, int cam, double* cost, double* re
   VC_TRY(prepare(h));
   const DevProblem& dp = h->dp;
   if (cam >= dp.n_cams) return fail(h, VCGPU_ERR_INVALID, "evaluate: camera index out of range");
-  VC_TRY(eval_reproj(h, h->cur, false, false, h->d_mask));
+  VC_TRY(ctl_reset(h, 0, 0));
+  VC_TRY(eval_reproj(h, 0, false, false, h->d_mask));
   const int64_t n = h->n_obs;
   std::vector<double> r(2 * std::max<int64_t>(n, 1));
   CUDA_TRY(h, cudaMemcpyAsync(r.data(), h->d_r, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -879,7 +542,8 @@ extern "C" int vcgpu_remove_outliers(vcgpu_handle* h, const double* rmse, double
   if (!h || !rmse) return VCGPU_ERR_INVALID;
   VC_TRY(prepare(h));
   const DevProblem& dp = h->dp;
-  VC_TRY(eval_reproj(h, h->cur, false, false, h->d_mask));
+  VC_TRY(ctl_reset(h, 0, 0));
+  VC_TRY(eval_reproj(h, 0, false, false, h->d_mask));
   const int64_t n = h->n_obs;
   std::vector<double> r(2 * std::max<int64_t>(n, 1));
   CUDA_TRY(h, cudaMemcpyAsync(r.data(), h->d_r, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -944,9 +608,8 @@ extern "C" int vcgpu_eval_reproj(vcgpu_handle* h, double* r_out, double* J_out) 
   VC_TRY(dev_alloc(h, &ones, dp.G));
   std::vector<double> hones(dp.G, 1.0);
   CUDA_TRY(h, cudaMemcpy(ones, hones.data(), dp.G * sizeof(double), cudaMemcpyHostToDevice));
-  const double vm = h->dp.visual_mult;
-  VC_TRY(eval_reproj(h, h->cur, J_out != nullptr, false, ones));
-  (void)vm;
+  VC_TRY(ctl_reset(h, 0, 0));
+  VC_TRY(eval_reproj(h, 0, J_out != nullptr, false, ones));
   std::vector<double> r(2 * std::max<int64_t>(n, 1));
   CUDA_TRY(h, cudaMemcpyAsync(r.data(), h->d_r, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -977,7 +640,8 @@ extern "C" int vcgpu_normal_equations(vcgpu_handle* h, double* B, double* U, dou
                                       double* gc, double* cost) {
   if (!h) return VCGPU_ERR_INVALID;
   VC_TRY(prepare(h));
-  VC_TRY(evaluate_into(h, h->cur, false));
+  VC_TRY(ctl_reset(h, 0, 0));
+  VC_TRY(evaluate_into(h, 0, false, -1));
   VC_TRY(read_scalars(h));
   const DevProblem& dp = h->dp;
   const size_t nf = dp.n_frames, fd = dp.fd, G = dp.G;
@@ -995,12 +659,14 @@ extern "C" int vcgpu_normal_equations(vcgpu_handle* h, double* B, double* U, dou
 extern "C" int vcgpu_solve_arrow(vcgpu_handle* h, const double* scale, const double* D2, double* x) {
   if (!h || !scale || !D2 || !x) return VCGPU_ERR_INVALID;
   VC_TRY(prepare(h));
-  VC_TRY(evaluate_into(h, h->cur, false));
+  VC_TRY(ctl_reset(h, 0, 0));
+  VC_TRY(evaluate_into(h, 0, false, -1));
   const DevProblem& dp = h->dp;
   const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
   CUDA_TRY(h, cudaMemcpyAsync(h->d_scale, scale, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_scale + np, D2, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  VC_TRY(solve_and_update(h, h->cur));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_scalars + kScNotPD, 0, sizeof(double), h->stream));
+  VC_TRY(solve_and_update(h, h->d_scale + np, false));
   VC_TRY(read_scalars(h));
   if (h->h_scalars[kScNotPD] > 0) return fail(h, VCGPU_ERR_NUMERIC, "arrow system is not positive definite");
   CUDA_TRY(h, cudaMemcpy(x, h->d_delta, np * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1016,7 +682,8 @@ extern "C" int vcgpu_update_imu_weights(vcgpu_handle* h) {
   if (!h) return VCGPU_ERR_INVALID;
   VC_TRY(prepare(h));
   if (!h->dp.inertial) return VCGPU_OK;
-  VC_TRY(imu_update_weights(h, h->cur));
+  VC_TRY(ctl_reset(h, 0, 0));
+  VC_TRY(imu_update_weights(h));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return VCGPU_OK;
 }
