@@ -1,0 +1,60 @@
+"""Worker for the multi-GPU parity test: run under torchrun with N ranks (one GPU each).
+
+Every rank solves its frame shard of the same seeded problem jointly (NCCL all-reduce inside
+libvcgpu); rank 0 additionally solves the whole problem on its own GPU and compares.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch.distributed as dist  # noqa: E402
+
+from vicalib_b200 import synth  # noqa: E402
+from vicalib_b200.capi import Calibrator  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dist.init_process_group("gloo")
+    p = synth.make_problem(models=("poly3", "fov"), n_frames=64, seed=33)
+    uid = [Calibrator.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g = Calibrator(device=local)
+    g.comm_init(uid[0], rank, world)
+    ps = synth.shard(p, rank, world)
+    g.load(ps)
+    g.set_options(function_tol=1e-14, max_iters=30)
+    s = g.solve()
+    st = g.state()
+    out = [None] * world
+    dist.all_gather_object(out, dict(cost=s["final_cost"], iters=s["iterations"], intr=st["intr"], p_ck=st["p_ck"],
+                                     q_ck=st["q_ck"], T=st["T_wp"]))
+    ok = True
+    if rank == 0:
+        ref = Calibrator(device=local)
+        ref.load(p)
+        ref.set_options(function_tol=1e-14, max_iters=30)
+        sr = ref.solve()
+        sref = ref.state()
+        T = np.concatenate([o["T"] for o in out])
+        checks = {
+            "cost": abs(out[0]["cost"] - sr["final_cost"]) <= 1e-9 * sr["final_cost"],
+            "iters": all(o["iters"] == sr["iterations"] for o in out),
+            "ranks_agree": all(np.array_equal(o["intr"], out[0]["intr"]) and o["cost"] == out[0]["cost"] for o in out),
+            "intr": np.abs(out[0]["intr"] - sref["intr"]).max() <= 1e-6 * np.abs(sref["intr"]).max(),
+            "p_ck": np.abs(out[0]["p_ck"] - sref["p_ck"]).max() <= 1e-8,
+            "poses": np.abs(T - sref["T_wp"]).max() <= 1e-8,
+        }
+        ok = all(checks.values())
+        print("MG_CHECK", "PASS" if ok else "FAIL", checks, "cost", out[0]["cost"], sr["final_cost"], flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

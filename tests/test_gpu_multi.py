@@ -1,0 +1,30 @@
+"""Multi-GPU parity: N frame shards solved jointly == the whole problem on one GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    import ctypes
+
+    try:
+        cuda = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        return n.value if cuda.cuInit(0) == 0 and cuda.cuDeviceGetCount(ctypes.byref(n)) == 0 else 0
+    except OSError:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_solve_matches_single_gpu(world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mg_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MG_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

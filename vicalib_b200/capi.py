@@ -159,6 +159,18 @@ class Calibrator:
             setattr(self.opts, k, v)
         self._chk(self.L.vcgpu_set_options(self.h, C.byref(self.opts)))
 
+    # ---- multi-GPU (one process per GPU; frames sharded; NCCL all-reduce of the reduced system)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        if lib().vcgpu_comm_unique_id(buf) != 0:
+            raise VcgpuError("ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._chk(self.L.vcgpu_comm_init(self.h, buf, C.c_int(rank), C.c_int(nranks)))
+
     # ---- hot path
     def solve(self, callback=None):
         s = Summary()

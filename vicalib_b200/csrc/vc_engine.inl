@@ -17,6 +17,15 @@
 constexpr bool kFuseUpdate = false;
 constexpr bool kSumInSolve = false;
 
+// ------------------------------------------------------------------ multi-GPU all-reduce
+static int all_reduce(vcgpu_handle* h, double* buf, size_t n) {
+  if (h->nranks <= 1) return VCGPU_OK;
+  const ncclResult_t rc = ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, static_cast<ncclComm_t>(h->comm), h->stream);
+  if (rc != ncclSuccess) return fail(h, VCGPU_ERR_COMM, std::string("ncclAllReduce: ") + ncclGetErrorString(rc));
+  ++h->collectives;
+  return VCGPU_OK;
+}
+
 // ------------------------------------------------------------------ control block
 static int ctl_upload(vcgpu_handle* h) {
   CUDA_TRY(h, cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
@@ -150,18 +159,28 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
   {
     StageScope st(h, VCGPU_STAGE_REDUCE);
     RedFinArgs ra;
-    ra.dp = vdp; ra.ctl = h->d_ctl; ra.which = which; ra.decide_mode = decide_mode;
+    const bool multi = h->nranks > 1;
+    ra.dp = vdp; ra.ctl = h->d_ctl; ra.which = which; ra.decide_mode = multi ? -1 : decide_mode; ra.multi = multi ? 1 : 0;
     ra.Cg = h->d_Cg; ra.imuCg = dp.inertial ? imu_cg(h) : nullptr; ra.ni = dp.n_frames - 1; ra.imu_goff = dp.imu_goff;
     ra.imu_stride = kImuCgStride;
     ra.Cpart = h->d_Cpart; ra.red_part = h->d_red_part;
     ra.cost_part = h->d_cost_part; ra.n_cost_part = n_vis_cost;
     ra.imu_cost_part = imu_cost_part(h); ra.n_imu_cost_part = n_imu_cost;
     ra.step_part = with_step ? h->d_red : nullptr;
-    ra.n_step_part = (fused && kFuseUpdate) ? dp.n_frames + 1 : (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps + 1;
+    // the last step_part slot is the globals' share: counted once (rank 0) in a sharded run
+    ra.n_step_part = ((fused && kFuseUpdate) ? dp.n_frames : (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps) +
+                     (h->rank == 0 ? 1 : 0);
     ra.n_frames_fd = dp.n_frames * dp.fd;
     ra.out[0] = h->blk[0]; ra.out[1] = h->blk[1]; ra.scalars = h->d_scalars; ra.counter = h->d_counter;
     reduce_finalize_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
     ++h->launches;
+    if (multi) {  // sum the global blocks, cost and step scalars over the frame shards, then decide everywhere
+      mg_pack_kernel<<<8, 256, 0, h->stream>>>(dp.G, h->d_ctl, which, h->blk[0], h->blk[1], h->d_scalars, h->rank, h->nranks, h->d_mg);
+      ++h->launches;
+      VC_TRY(all_reduce(h, h->d_mg, NS + 6 + h->nranks));
+      mg_unpack_decide_kernel<<<1, 256, 0, h->stream>>>(dp.G, h->d_ctl, which, h->blk[0], h->blk[1], h->d_scalars, h->nranks, h->d_mg, decide_mode);
+      ++h->launches;
+    }
   }
   CUDA_TRY(h, cudaGetLastError());
   return VCGPU_OK;
@@ -206,11 +225,12 @@ static int solve_and_update(vcgpu_handle* h, const double* D2x, bool with_update
       frame_solve_kernel<6><<<h->n_solve_blocks, kSolveThreads, ssm, h->stream>>>(sa);
       ++h->launches;
     }
-    const bool sum_in_solve = kSumInSolve && NS <= 1024;
+    const bool sum_in_solve = kSumInSolve && NS <= 1024 && h->nranks == 1;
     if (!sum_in_solve) {
       sum_partials_kernel<<<static_cast<int>((NS + 31) / 32), 256, 0, h->stream>>>(h->d_Spart, h->n_solve_blocks,
                                                                                    static_cast<int>(NS), h->d_Ssum, h->d_ctl);
       ++h->launches;
+      VC_TRY(all_reduce(h, h->d_Ssum, NS));  // every rank then solves the same reduced system
     }
     {
       StageScope st(h, VCGPU_STAGE_GLOBAL_SOLVE);
@@ -274,6 +294,8 @@ static int enqueue_iteration(vcgpu_handle* h, bool weights) {
 // ------------------------------------------------------------------ the trust-region loop
 static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out, int fixed_iters) {
   VC_TRY(prepare(h));
+  if (h->nranks > 1 && h->dp.inertial)
+    return fail(h, VCGPU_ERR_INVALID, "frame-sharded multi-GPU runs support the visual terms only in this build");
   if (h->opts.strategy != 0) return fail(h, VCGPU_ERR_INVALID, "DOGLEG strategy is not implemented on the device yet; use strategy 0 (LM)");
   const DevProblem& dp = h->dp;
   const vcgpu_options& o = h->opts;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/vcgpu.h"
@@ -74,7 +75,8 @@ struct vcgpu_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  long launches = 0;
+  long launches = 0, collectives = 0;
+  std::unordered_map<void*, size_t> capacity;  // bytes held by each dev_alloc()ed pointer slot
   // measurement hooks
   bool profiling = false, flush_l2 = false, materialize = false;
   cudaEvent_t st_ev[VCGPU_STAGE_COUNT][2] = {};
@@ -144,4 +146,8 @@ struct vcgpu_handle {
   double* d_imu_r = nullptr;      // [(nf-1)][9]
   double* d_imu_J = nullptr;      // [(nf-1)][9*33]
   void* imu = nullptr;            // ImuDevHost (vc_imu_host.inl)
+  // multi-GPU (one process per GPU; frames sharded; see vc_engine.inl)
+  void* comm = nullptr;           // ncclComm_t
+  int rank = 0, nranks = 1;
+  double* d_mg = nullptr;         // all-reduce buffer [G*G+G+6+nranks]
 };

@@ -425,6 +425,7 @@ struct RedFinArgs {
   Ctl* ctl;
   int which;
   int decide_mode;      // -1: none (multi-GPU: decide after the all-reduce), 0: initial point, 1: iteration
+  int multi;            // 1: frame-sharded run: scalars cover this rank's frames only (gc joins after the all-reduce)
   const double* Cg;
   const double* imuCg;  // [ni][kImuCgStride] or null
   int ni, imu_goff, imu_stride;
@@ -584,8 +585,10 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
   double w[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (tid < nb)
     for (int q = 0; q < 7; ++q) w[q] = __ldcg(a.red_part + 8 * tid + q);
-  w[1] += g2;
-  w[6] = fmax(w[6], gm);
+  if (!a.multi) {
+    w[1] += g2;
+    w[6] = fmax(w[6], gm);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -612,6 +615,60 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
       a.scalars[kScXnorm2] = t[5];
     }
     if (a.decide_mode >= 0) decide_step(a.ctl, a.scalars, a.decide_mode);
+  }
+}
+
+// ---------------------------------------------------------------- multi-GPU: pack / unpack around the all-reduce
+// buffer: [C G*G | gc G | cost, |gf|^2, dotG, dotD, step2, xnorm2 | per-rank |gf|_inf slots]
+__global__ void mg_pack_kernel(int G, const Ctl* ctl, int which, Blocks b0, Blocks b1, const double* scalars, int rank,
+                               int nranks, double* buf) {
+  if (ctl->done) return;
+  const Blocks& b = pick(ctl, which) ? b1 : b0;
+  const int NS = G * G + G, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = tid; k < NS; k += gridDim.x * blockDim.x) buf[k] = k < G * G ? b.C[k] : b.gc[k - G * G];
+  if (tid == 0) {
+    buf[NS + 0] = scalars[kScCost];
+    buf[NS + 1] = scalars[kScGnorm2];
+    buf[NS + 2] = scalars[kScDotG];
+    buf[NS + 3] = scalars[kScDotD];
+    buf[NS + 4] = scalars[kScStep2];
+    buf[NS + 5] = scalars[kScXnorm2];
+    for (int r = 0; r < nranks; ++r) buf[NS + 6 + r] = r == rank ? scalars[kScGmax] : 0.0;
+  }
+}
+__global__ void mg_unpack_decide_kernel(int G, Ctl* ctl, int which, Blocks b0, Blocks b1, double* scalars, int nranks,
+                                        const double* buf, int decide_mode) {
+  if (ctl->done) return;
+  const Blocks& b = pick(ctl, which) ? b1 : b0;
+  const int NS = G * G + G, tid = threadIdx.x;
+  __shared__ double shm[256], shs[256];
+  double gm = 0.0, g2 = 0.0;
+  for (int k = tid; k < NS; k += 256) {
+    const double v = buf[k];
+    if (k < G * G) {
+      b.C[k] = v;
+    } else {
+      b.gc[k - G * G] = v;
+      gm = fmax(gm, fabs(v));
+      g2 += v * v;
+    }
+  }
+  shm[tid] = gm;
+  shs[tid] = g2;
+  __syncthreads();
+  if (tid == 0) {
+    gm = 0.0; g2 = 0.0;
+    for (int k = 0; k < 256; ++k) { gm = fmax(gm, shm[k]); g2 += shs[k]; }
+    for (int r = 0; r < nranks; ++r) gm = fmax(gm, buf[NS + 6 + r]);
+    *b.cost = buf[NS];
+    scalars[kScCost] = buf[NS];
+    scalars[kScGmax] = gm;
+    scalars[kScGnorm2] = buf[NS + 1] + g2;
+    scalars[kScDotG] = buf[NS + 2];
+    scalars[kScDotD] = buf[NS + 3];
+    scalars[kScStep2] = buf[NS + 4];
+    scalars[kScXnorm2] = buf[NS + 5];
+    if (decide_mode >= 0) decide_step(ctl, scalars, decide_mode);
   }
 }
 

@@ -12,6 +12,8 @@
 #include <cstring>
 #include <numeric>
 
+#include <nccl.h>
+
 #include "vc_internal.h"
 #include "vc_kernels.cuh"
 #include "vc_imu.cuh"
@@ -40,12 +42,19 @@ static int fail(vcgpu_handle* h, int code, const std::string& msg) {
   return code;
 }
 
+// device buffers are reused across prepare() calls when they are already large enough (a re-upload of
+// a same-sized problem then costs no cudaMalloc / cudaFree)
 template <class T>
 static int dev_alloc(vcgpu_handle* h, T** p, size_t n) {
+  if (n == 0) n = 1;
+  const size_t bytes = n * sizeof(T);
+  void* key = static_cast<void*>(p);
+  auto it = h->capacity.find(key);
+  if (*p && it != h->capacity.end() && it->second >= bytes) return VCGPU_OK;
   if (*p) cudaFree(*p);
   *p = nullptr;
-  if (n == 0) n = 1;
-  CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(p), bytes));
+  h->capacity[key] = bytes;
   return VCGPU_OK;
 }
 template <class T>
@@ -158,6 +167,8 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_red); dev_free(&h->d_scalars); dev_free(&h->d_Ssum); dev_free(&h->d_red_part); dev_free(&h->d_counter);
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
+  dev_free(&h->d_mg);
+  if (h->comm) ncclCommDestroy(static_cast<ncclComm_t>(h->comm));
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->d_ctl) cudaFree(h->d_ctl);
@@ -463,6 +474,7 @@ static int prepare(vcgpu_handle* h) {
     VC_TRY(dev_alloc(h, &h->d_delta, np));
     VC_TRY(dev_alloc(h, &h->d_red, 4 * (static_cast<size_t>(nf) + 2)));
     VC_TRY(dev_alloc(h, &h->d_red_part, 8 * kReduceBlocks));
+    VC_TRY(dev_alloc(h, &h->d_mg, NS + 6 + h->nranks));
     VC_TRY(dev_alloc(h, &h->d_counter, 4));
     CUDA_TRY(h, cudaMemset(h->d_counter, 0, 4 * sizeof(unsigned)));
     VC_TRY(dev_alloc(h, &h->d_scalars, kScCount));
@@ -703,10 +715,27 @@ extern "C" int vcgpu_set_imu_weights(vcgpu_handle* h, const double* w) {
 }
 
 extern "C" int vcgpu_comm_unique_id(uint8_t id[VCGPU_UNIQUE_ID_BYTES]) {
-  (void)id;
-  return VCGPU_ERR_COMM;  // multi-GPU sharding lands with the IMU chain solver
+  static_assert(sizeof(ncclUniqueId) <= VCGPU_UNIQUE_ID_BYTES, "unique id does not fit");
+  if (!id) return VCGPU_ERR_INVALID;
+  ncclUniqueId u;
+  if (ncclGetUniqueId(&u) != ncclSuccess) return VCGPU_ERR_COMM;
+  std::memset(id, 0, VCGPU_UNIQUE_ID_BYTES);
+  std::memcpy(id, &u, sizeof u);
+  return VCGPU_OK;
 }
 extern "C" int vcgpu_comm_init(vcgpu_handle* h, const uint8_t id[VCGPU_UNIQUE_ID_BYTES], int rank, int nranks) {
-  (void)id; (void)rank; (void)nranks;
-  return h ? fail(h, VCGPU_ERR_COMM, "multi-GPU communicator not implemented yet") : VCGPU_ERR_COMM;
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return h ? fail(h, VCGPU_ERR_INVALID, "comm_init: bad arguments") : VCGPU_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->comm) { ncclCommDestroy(static_cast<ncclComm_t>(h->comm)); h->comm = nullptr; }
+  h->rank = rank;
+  h->nranks = nranks;
+  if (nranks == 1) return VCGPU_OK;
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof u);
+  ncclComm_t c;
+  const ncclResult_t rc = ncclCommInitRank(&c, nranks, u, rank);
+  if (rc != ncclSuccess) return fail(h, VCGPU_ERR_COMM, std::string("ncclCommInitRank: ") + ncclGetErrorString(rc));
+  h->comm = c;
+  h->dirty = true;
+  return VCGPU_OK;
 }

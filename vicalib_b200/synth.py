@@ -398,3 +398,27 @@ def make_config(name: str, **overrides) -> Problem:
     kw.setdefault("seed", 20260924 + idx + 1)
     kw.update(overrides)
     return make_problem(**kw)
+
+
+def shard_frames(n_frames: int, rank: int, world: int):
+    """Contiguous frame range [f0, f1) owned by `rank` (frames shard naturally)."""
+    base, rem = divmod(n_frames, world)
+    f0 = rank * base + min(rank, rem)
+    return f0, f0 + base + (1 if rank < rem else 0)
+
+
+def shard(p: Problem, rank: int, world: int) -> Problem:
+    """Rank-local slice of a vision-only problem: the rank's frames (re-indexed from 0) and the
+    observations of those frames; cameras / globals are replicated.  Inertial problems also need the
+    next rank's first frame as a ghost (cross-shard IMU factor) and are not sharded by this helper."""
+    if p.inertial:
+        raise NotImplementedError("sharding of inertial problems needs ghost frames")
+    f0, f1 = shard_frames(p.n_frames, rank, world)
+    sel = (p.obs_frame >= f0) & (p.obs_frame < f1)
+    truth = dict(p.truth)
+    truth["T_wp"] = p.truth["T_wp"][f0:f1]
+    truth["v_w"] = p.truth["v_w"][f0:f1]
+    return dataclasses.replace(
+        p, T_wp=p.T_wp[f0:f1].copy(), v_w=p.v_w[f0:f1].copy(), ftime=p.ftime[f0:f1].copy(),
+        obs_frame=(p.obs_frame[sel] - f0).astype(np.int32), obs_cam=p.obs_cam[sel].copy(), p_w=p.p_w[sel].copy(),
+        p_c=p.p_c[sel].copy(), grid_idx=p.grid_idx[sel].copy(), truth=truth)
