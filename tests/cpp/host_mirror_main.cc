@@ -1,0 +1,84 @@
+// Drives the C++ ViCalibrator mirror (vicalib_b200/host/vicalibrator.h) the way VicalibTask does
+// (vicalib-task.cc:128-147, 227-245, 339-363, 689): AddCamera / AddFrame / AddObservation /
+// AddImuMeasurements, SetOptimizationFlags, Start, poll IsRunning, WriteCameraModels.
+// Input: a flat binary problem written by tests/test_gpu_host_mirror.py.  Output: result text file.
+#include <unistd.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "../../vicalib_b200/host/vicalibrator.h"
+
+using namespace visual_inertial_calibration;
+
+template <class T>
+static std::vector<T> rd(FILE* f, size_t n) {
+  std::vector<T> v(n);
+  if (n && fread(v.data(), sizeof(T), n, f) != n) { std::fprintf(stderr, "short read\n"); std::exit(2); }
+  return v;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) { std::fprintf(stderr, "usage: %s problem.bin result.txt cameras.xml\n", argv[0]); return 2; }
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) return 2;
+  // header: n_cams n_frames n_obs n_imu inertial has_initial_guess max_iters dup
+  std::vector<int64_t> hd = rd<int64_t>(f, 8);
+  const int nc = static_cast<int>(hd[0]), nf = static_cast<int>(hd[1]);
+  const int64_t nobs = hd[2], nimu = hd[3];
+  const bool inertial = hd[4] != 0, has_guess = hd[5] != 0;
+  std::vector<int32_t> model = rd<int32_t>(f, nc);
+  std::vector<double> intr = rd<double>(f, 10 * nc), q = rd<double>(f, 4 * nc), p = rd<double>(f, 3 * nc);
+  std::vector<double> T = rd<double>(f, 7 * nf), tm = rd<double>(f, nf);
+  std::vector<int32_t> of = rd<int32_t>(f, nobs), oc = rd<int32_t>(f, nobs);
+  std::vector<double> pw = rd<double>(f, 3 * nobs), pc = rd<double>(f, 2 * nobs);
+  std::vector<double> it = rd<double>(f, nimu), iw = rd<double>(f, 3 * nimu), ia = rd<double>(f, 3 * nimu);
+  std::vector<double> g = rd<double>(f, 2);
+  fclose(f);
+
+  static const char* kTypes[5] = {"calibu_fu_fv_u0_v0", "calibu_fu_fv_u0_v0_w", "calibu_fu_fv_u0_v0_k1_k2",
+                                  "calibu_fu_fv_u0_v0_k1_k2_k3", "calibu_fu_fv_u0_v0_kb4"};
+  static const int kK[5] = {4, 5, 6, 7, 8};
+  CalibratorFlags flags;
+  flags.calibrate_imu = inertial;
+  flags.max_iters = static_cast<int>(hd[6]);
+  flags.remove_outliers = false;
+  ViCalibrator cal(flags);
+  cal.SetEmulateBlockDuplication(hd[7] != 0);
+  for (int c = 0; c < nc; ++c) {
+    std::vector<double> params(intr.begin() + 10 * c, intr.begin() + 10 * c + kK[model[c]]);
+    std::shared_ptr<CameraInterface> cam(new CameraInterface(kTypes[model[c]], 640, 480, params));
+    cal.AddCamera(cam, SE3d(&q[4 * c], &p[3 * c]));
+  }
+  for (int fr = 0; fr < nf; ++fr) cal.AddFrame(SE3d(&T[7 * fr], &T[7 * fr + 4]), tm[fr]);
+  for (int64_t i = 0; i < nobs; ++i)
+    cal.AddObservation(of[i], oc[i], Vector3d{{pw[3 * i], pw[3 * i + 1], pw[3 * i + 2]}}, Vector2d{{pc[2 * i], pc[2 * i + 1]}}, tm[of[i]]);
+  for (int64_t i = 0; i < nimu; ++i)
+    cal.AddImuMeasurements(Vector3d{{iw[3 * i], iw[3 * i + 1], iw[3 * i + 2]}}, Vector3d{{ia[3 * i], ia[3 * i + 1], ia[3 * i + 2]}}, it[i]);
+  cal.SetFunctionTolerance(1e-10);
+  if (has_guess) cal.SetOptimizationFlags(true, inertial, false, true);  // vicalib-task.cc:227-235
+  cal.Start();
+  while (cal.IsRunning()) usleep(2000);  // the reference polls every 30 ms (vicalib-engine.cc:388-400)
+  cal.Stop();
+  cal.WriteCameraModels(argv[3]);
+
+  FILE* o = fopen(argv[2], "w");
+  std::fprintf(o, "solves %d iterations %u mse %.17g ts %.17g\n", cal.num_solves(), cal.GetNumIterations(), cal.MeanSquaredError(),
+               cal.time_offset());
+  for (int c = 0; c < nc; ++c) {
+    std::fprintf(o, "cam %d rmse %.17g params", c, cal.GetCameraProjRMSE()[c]);
+    for (double v : cal.GetCamera(c).camera->GetParams()) std::fprintf(o, " %.17g", v);
+    std::fprintf(o, " T_ck");
+    for (int k = 0; k < 7; ++k) std::fprintf(o, " %.17g", cal.GetCamera(c).T_ck.d[k]);
+    std::fprintf(o, "\n");
+  }
+  Vector6d b = cal.GetBiases(), sf = cal.GetScaleFactor();
+  std::fprintf(o, "biases");
+  for (double v : b) std::fprintf(o, " %.17g", v);
+  std::fprintf(o, "\nscale");
+  for (double v : sf) std::fprintf(o, " %.17g", v);
+  std::fprintf(o, "\n");
+  fclose(o);
+  return 0;
+}
