@@ -122,39 +122,52 @@ __global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs
       }
       __syncthreads();
     }
-    if (tid == 0) {
+    if (tid < VW) {
+      // every column-solving thread factors the FD x FD pivot in registers (no serial section, no barrier)
+      double Lr[FD][FD], iL[FD];
+#pragma unroll
+      for (int ii = 0; ii < FD; ++ii)
+#pragma unroll
+        for (int k = 0; k <= ii; ++k) Lr[ii][k] = Ap[ii * FD + k];
+      bool ok = true;
+#pragma unroll
       for (int jj = 0; jj < FD; ++jj) {
-        double d = Ap[jj * FD + jj];
-        for (int k = 0; k < jj; ++k) d -= Ap[jj * FD + k] * Ap[jj * FD + k];
-        if (!(d > 0.0)) { bad = 1; d = 1.0; }
+        double d = Lr[jj][jj];
+#pragma unroll
+        for (int k = 0; k < jj; ++k) d -= Lr[jj][k] * Lr[jj][k];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
         d = sqrt(d);
-        Ap[jj * FD + jj] = d;
+        Lr[jj][jj] = d;
+        const double inv = 1.0 / d;
+        iL[jj] = inv;
+#pragma unroll
         for (int ii = jj + 1; ii < FD; ++ii) {
-          double t = Ap[ii * FD + jj];
-          for (int k = 0; k < jj; ++k) t -= Ap[ii * FD + k] * Ap[jj * FD + k];
-          Ap[ii * FD + jj] = t / d;
+          double t = Lr[ii][jj];
+#pragma unroll
+          for (int k = 0; k < jj; ++k) t -= Lr[ii][k] * Lr[jj][k];
+          Lr[ii][jj] = t * inv;
         }
       }
-    }
-    __syncthreads();
-    for (int q = tid; q < VW; q += kChainThreads) {
-      double x[FD];
+      if (!ok && tid == 0) bad = 1;
+      for (int q = tid; q < VW; q += kChainThreads) {
+        double x[FD];
 #pragma unroll
-      for (int ii = 0; ii < FD; ++ii) {
-        double t = Vi[ii * VW + q];
+        for (int ii = 0; ii < FD; ++ii) {
+          double t = Vi[ii * VW + q];
 #pragma unroll
-        for (int k = 0; k < ii; ++k) t -= Ap[ii * FD + k] * x[k];
-        x[ii] = t / Ap[ii * FD + ii];
+          for (int k = 0; k < ii; ++k) t -= Lr[ii][k] * x[k];
+          x[ii] = t * iL[ii];
+        }
+#pragma unroll
+        for (int ii = FD - 1; ii >= 0; --ii) {
+          double t = x[ii];
+#pragma unroll
+          for (int k = ii + 1; k < FD; ++k) t -= Lr[k][ii] * x[k];
+          x[ii] = t * iL[ii];
+        }
+#pragma unroll
+        for (int ii = 0; ii < FD; ++ii) Vi[ii * VW + q] = x[ii];
       }
-#pragma unroll
-      for (int ii = FD - 1; ii >= 0; --ii) {
-        double t = x[ii];
-#pragma unroll
-        for (int k = ii + 1; k < FD; ++k) t -= Ap[k * FD + ii] * x[k];
-        x[ii] = t / Ap[ii * FD + ii];
-      }
-#pragma unroll
-      for (int ii = 0; ii < FD; ++ii) Vi[ii * VW + q] = x[ii];
     }
     __syncthreads();
   }
@@ -274,6 +287,37 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const double* part, i
   }
 }
 
+// same sum, output selected on the device: [C | gc] of the buffer being evaluated (contiguous in Blocks)
+__global__ void __launch_bounds__(256) sum_partials_sel_kernel(const double* part, int n_part, int NS, double* out0,
+                                                               double* out1, const Ctl* ctl, int which) {
+  __shared__ double sh[8][33];
+  if (ctl->done) return;
+  double* out = (which ? 1 - ctl->cur : ctl->cur) ? out1 : out0;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (e < NS) {
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = ty;
+    for (; b + 24 < n_part; b += 32) {
+      s += part[static_cast<int64_t>(b) * NS + e];
+      s1 += part[static_cast<int64_t>(b + 8) * NS + e];
+      s2 += part[static_cast<int64_t>(b + 16) * NS + e];
+      s3 += part[static_cast<int64_t>(b + 24) * NS + e];
+    }
+    for (; b < n_part; b += 8) s += part[static_cast<int64_t>(b) * NS + e];
+    s = (s + s1) + (s2 + s3);
+  }
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && e < NS) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][tx];
+    out[e] = t;
+  }
+}
+
 // dense solve of [globals | top-level chain nodes]
 struct DenseArgs {
   DevProblem dp;
@@ -351,18 +395,23 @@ __global__ void __launch_bounds__(256) dense_solve_kernel(DenseArgs a) {
     }
     __syncthreads();
   }
-  if (tid == 0) {
+  if (tid < 32) {  // warp-cooperative triangular solves (column oriented), L L^T x = rhs
+    const int lane = tid;
     for (int i = 0; i < N; ++i) {
-      double s = rhs[i];
-      for (int k = 0; k < i; ++k) s -= S[i * N + k] * rhs[k];
-      rhs[i] = s / S[i * N + i];
+      const double xi = rhs[i] / S[i * N + i];
+      __syncwarp();
+      if (lane == 0) rhs[i] = xi;
+      for (int k = i + 1 + lane; k < N; k += 32) rhs[k] -= S[k * N + i] * xi;
+      __syncwarp();
     }
     for (int i = N - 1; i >= 0; --i) {
-      double s = rhs[i];
-      for (int k = i + 1; k < N; ++k) s -= S[k * N + i] * rhs[k];
-      rhs[i] = s / S[i * N + i];
+      const double xi = rhs[i] / S[i * N + i];
+      __syncwarp();
+      if (lane == 0) rhs[i] = xi;
+      for (int k = lane; k < i; k += 32) rhs[k] -= S[i * N + k] * xi;
+      __syncwarp();
     }
-    if (bad) a.scalars[7] = 1.0;
+    if (bad && lane == 0) a.scalars[7] = 1.0;
   }
   __syncthreads();
   for (int i = tid; i < G; i += 256) a.delta[nfp + i] = bad ? 0.0 : rhs[i];

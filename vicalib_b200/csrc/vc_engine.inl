@@ -160,7 +160,9 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     StageScope st(h, VCGPU_STAGE_REDUCE);
     RedFinArgs ra;
     const bool multi = h->nranks > 1;
+    const bool split = NS > 512;  // large global block: level 2 as its own parallel launches
     ra.dp = vdp; ra.ctl = h->d_ctl; ra.which = which; ra.decide_mode = multi ? -1 : decide_mode; ra.multi = multi ? 1 : 0;
+    ra.level1_only = split ? 1 : 0;
     ra.Cg = h->d_Cg; ra.imuCg = dp.inertial ? imu_cg(h) : nullptr; ra.ni = dp.n_frames - 1; ra.imu_goff = dp.imu_goff;
     ra.imu_stride = kImuCgStride;
     ra.Cpart = h->d_Cpart; ra.red_part = h->d_red_part;
@@ -174,6 +176,12 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     ra.out[0] = h->blk[0]; ra.out[1] = h->blk[1]; ra.scalars = h->d_scalars; ra.counter = h->d_counter;
     reduce_finalize_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
     ++h->launches;
+    if (split) {
+      sum_partials_sel_kernel<<<static_cast<int>((NS + 31) / 32), 256, 0, h->stream>>>(h->d_Cpart, kReduceBlocks, static_cast<int>(NS),
+                                                                                       h->blk[0].C, h->blk[1].C, h->d_ctl, which);
+      finalize_small_kernel<<<1, 256, 0, h->stream>>>(ra, kReduceBlocks);
+      h->launches += 2;
+    }
     if (multi) {  // sum the global blocks, cost and step scalars over the frame shards, then decide everywhere
       mg_pack_kernel<<<8, 256, 0, h->stream>>>(dp.G, h->d_ctl, which, h->blk[0], h->blk[1], h->d_scalars, h->rank, h->nranks, h->d_mg);
       ++h->launches;

@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(32 * kWtWarps) imu_weights_kernel(WeightArgs a
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int kk = blockIdx.x * kWtWarps + wid;
   if (kk >= a.ni || a.ctl->done) return;
+  // a rejected step leaves the accepted state — hence the weights — unchanged
+  if (a.ctl->iter > 0 && !a.ctl->last_accepted) return;
   Work* W = &work[wid];
   const double* state = a.states[a.ctl->cur];
   const double* X1 = state + 7 * static_cast<int64_t>(kk);

@@ -426,6 +426,7 @@ struct RedFinArgs {
   int which;
   int decide_mode;      // -1: none (multi-GPU: decide after the all-reduce), 0: initial point, 1: iteration
   int multi;            // 1: frame-sharded run: scalars cover this rank's frames only (gc joins after the all-reduce)
+  int level1_only;      // 1: stop after the per-CTA partials (large G: level 2 runs as its own parallel launches)
   const double* Cg;
   const double* imuCg;  // [ni][kImuCgStride] or null
   int ni, imu_goff, imu_stride;
@@ -546,9 +547,12 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
       t[6] = fmax(t[6], shr[w][6]);
     }
     for (int q = 0; q < 7; ++q) a.red_part[8 * bid + q] = t[q];
+    if (a.level1_only) { is_last = 0; }
     __threadfence();
-    const unsigned ticket = atomicInc(a.counter, static_cast<unsigned>(nb - 1));
-    is_last = ticket == static_cast<unsigned>(nb - 1);
+    if (!a.level1_only) {
+      const unsigned ticket = atomicInc(a.counter, static_cast<unsigned>(nb - 1));
+      is_last = ticket == static_cast<unsigned>(nb - 1);
+    }
   }
   __threadfence();
   __syncthreads();
@@ -589,6 +593,51 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
     w[1] += g2;
     w[6] = fmax(w[6], gm);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) w[q] += __shfl_down_sync(0xffffffffu, w[q], o);
+    w[6] = fmax(w[6], __shfl_down_sync(0xffffffffu, w[6], o));
+  }
+  if (lane == 0)
+    for (int q = 0; q < 7; ++q) shr[warp][q] = w[q];
+  __syncthreads();
+  if (tid == 0) {
+    double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int ww = 0; ww < 8; ++ww) {
+      for (int q = 0; q < 6; ++q) t[q] += shr[ww][q];
+      t[6] = fmax(t[6], shr[ww][6]);
+    }
+    *out.cost = t[0];
+    a.scalars[kScCost] = t[0];
+    a.scalars[kScGmax] = t[6];
+    a.scalars[kScGnorm2] = t[1];
+    if (a.step_part) {
+      a.scalars[kScDotG] = t[2];
+      a.scalars[kScDotD] = t[3];
+      a.scalars[kScStep2] = t[4];
+      a.scalars[kScXnorm2] = t[5];
+    }
+    if (a.decide_mode >= 0) decide_step(a.ctl, a.scalars, a.decide_mode);
+  }
+}
+
+// level 2 for large global blocks: C | gc were summed by sum_partials_sel_kernel; this one-CTA launch
+// finishes the scalars (fixed order) and decides
+__global__ void __launch_bounds__(256) finalize_small_kernel(RedFinArgs a, int nb) {
+  __shared__ double shr[8][8];
+  if (a.ctl->done) return;
+  const Blocks& out = a.out[pick(a.ctl, a.which)];
+  const int G = a.dp.G, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double w[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (tid < nb)
+    for (int q = 0; q < 7; ++q) w[q] = a.red_part[8 * tid + q];
+  if (!a.multi)
+    for (int k = tid; k < G; k += 256) {
+      const double v = out.gc[k];
+      w[1] += v * v;
+      w[6] = fmax(w[6], fabs(v));
+    }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -890,18 +939,23 @@ __global__ void __launch_bounds__(256) global_solve_kernel(GlobalSolveArgs a) {
     }
     __syncthreads();
   }
-  if (tid == 0) {
+  if (tid < 32) {  // warp-cooperative triangular solves (column oriented), L L^T x = rhs
+    const int lane = tid;
     for (int i = 0; i < G; ++i) {
-      double s = rhs[i];
-      for (int k = 0; k < i; ++k) s -= S[i * G + k] * rhs[k];
-      rhs[i] = s / S[i * G + i];
+      const double xi = rhs[i] / S[i * G + i];
+      __syncwarp();
+      if (lane == 0) rhs[i] = xi;
+      for (int k = i + 1 + lane; k < G; k += 32) rhs[k] -= S[k * G + i] * xi;
+      __syncwarp();
     }
     for (int i = G - 1; i >= 0; --i) {
-      double s = rhs[i];
-      for (int k = i + 1; k < G; ++k) s -= S[k * G + i] * rhs[k];
-      rhs[i] = s / S[i * G + i];
+      const double xi = rhs[i] / S[i * G + i];
+      __syncwarp();
+      if (lane == 0) rhs[i] = xi;
+      for (int k = lane; k < i; k += 32) rhs[k] -= S[i * G + k] * xi;
+      __syncwarp();
     }
-    if (bad) a.scalars[kScNotPD] = 1.0;
+    if (bad && lane == 0) a.scalars[7] = 1.0;
   }
   __syncthreads();
   for (int i = tid; i < G; i += 256) a.delta[nfp + i] = bad ? 0.0 : rhs[i];
