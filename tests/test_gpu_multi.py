@@ -27,4 +27,4 @@ def test_sharded_solve_matches_single_gpu(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mg_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "MG_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "MG_CHECK ALL PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -15,7 +15,8 @@
 namespace vc {
 
 struct ChainLevel {
-  int n;
+  int n;                        // nodes at this level (including the ghost, if any)
+  int ghost;                    // 1: the last node is the next rank's first frame: a forced separator, never eliminated
   double *A, *U, *E, *g;        // node blocks: A[n][FD*FD], U[i] = H[i-1,i], E[n][FD*G], g[n][FD]
   double *addA, *addE, *addg;   // Schur contributions from the chunk on the node's left (null on level 0)
   double* Z;                    // [n][FD][2FD+G+1]: eliminated nodes' solutions against [L | R | E | g]
@@ -27,18 +28,27 @@ constexpr int kChainThreads = 128;
 // level 0 from the block normal equations: scaled + damped
 template <int FD>
 __global__ void chain_init_kernel(DevProblem dp, Blocks b0, Blocks b1, const Ctl* ctl, const double* scale,
-                                  const double* D2x, ChainLevel L) {
+                                  const double* D2x, ChainLevel L, const double* sepdiag) {
   if (ctl->done) return;
   const Blocks& b = ctl->cur ? b1 : b0;
   const double rinv = 1.0 / ctl->radius;
   const int G = dp.G, f = blockIdx.x, tid = threadIdx.x;
+  // sharded chain: a rank's first frame (and its ghost copy on the previous rank) is damped once, by its
+  // owner, from the diagonal summed over both ranks; sepdiag[slot*FD + r]
+  const bool sep = sepdiag != nullptr && (f == 0 || (dp.ghost && f == dp.n_frames - 1));
+  const bool is_ghost = dp.ghost && f == dp.n_frames - 1;
+  const double* sd = sep ? sepdiag + (dp.rank + (is_ghost ? 1 : 0)) * FD : nullptr;
   const double* sf = scale + static_cast<int64_t>(f) * FD;
   const double* sc = scale + static_cast<int64_t>(dp.n_frames) * FD;
   for (int e = tid; e < FD * FD; e += blockDim.x) {
     const int r = e / FD, c = e - r * FD;
     const double bij = b.B[static_cast<int64_t>(f) * FD * FD + e];
     double v = bij * sf[r] * sf[c];
-    if (r == c) v += D2x ? D2x[static_cast<int64_t>(f) * FD + r] : lm_damp(bij, sf[r], rinv);
+    if (r == c) {
+      if (D2x) v += D2x[static_cast<int64_t>(f) * FD + r];
+      else if (!sep) v += lm_damp(bij, sf[r], rinv);
+      else if (!is_ghost) v += lm_damp(sd[r], sf[r], rinv);
+    }
     L.A[static_cast<int64_t>(f) * FD * FD + e] = v;
     double u = 0.0;
     if (f > 0) u = b.U[static_cast<int64_t>(f) * FD * FD + e] * scale[static_cast<int64_t>(f - 1) * FD + r] * sf[c];
@@ -76,9 +86,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs
   __shared__ int bad;
   if (a.ctl->done) return;
   const ChainLevel& L = a.cur;
-  const int j = blockIdx.x, s = j * c, n = L.n;
-  const bool hasR = s + c < n;
-  const int m = min(c - 1, n - 1 - s);
+  const int j = blockIdx.x, s = j * c, n = L.n, n_eff = L.n - L.ghost;
+  const int nsep = (n_eff + c - 1) / c;
+  const bool toGhost = L.ghost && !(s + c < n_eff);  // this chunk's right separator is the ghost node
+  const bool hasR = s + c < n_eff || toGhost;
+  const int m = min(c - 1, n_eff - 1 - s);            // interior nodes s+1 .. s+m
+  const int rIdx = s + m + 1;                         // right separator at this level (when hasR)
+  const int jr = toGhost ? nsep : j + 1;              // ... and its index at the next level
   const bool add = L.addA != nullptr;
   if (tid == 0) bad = 0;
   for (int e = tid; e < NS; e += kChainThreads) Sacc[e] = 0.0;
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs
     const double* X0 = V;                                          // node s+1
     const double* Xl = V + static_cast<int64_t>(m - 1) * FD * VW;  // last interior node
     const double* U0 = L.U + static_cast<int64_t>(s + 1) * FD * FD;  // H[s, s+1]
-    const double* Ur = hasR ? L.U + static_cast<int64_t>(s + c) * FD * FD : nullptr;  // H[s+c-1, s+c]
+    const double* Ur = hasR ? L.U + static_cast<int64_t>(rIdx) * FD * FD : nullptr;  // H[rIdx-1, rIdx]
     __syncthreads();
     for (int e = tid; e < FD * w; e += kChainThreads) {
       const int r = e / w, q = e - r * w;  // q indexes [L | R | E | g]
@@ -223,17 +237,34 @@ __global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs
         Al[r * FD + q] -= sl;                                        // A_s -= H[s,p0] Z_L
       } else if (q < 2 * FD) {
         if (hasR) {
-          a.next.U[static_cast<int64_t>(j + 1) * FD * FD + r * FD + (q - FD)] = -sl;     // fill H[s, s+c]
-          a.next.addA[static_cast<int64_t>(j + 1) * FD * FD + r * FD + (q - FD)] = -sr;  // A_{s+c} -= H[r,pl] Z_R
+          a.next.U[static_cast<int64_t>(jr) * FD * FD + r * FD + (q - FD)] = -sl;     // fill H[s, rIdx]
+          a.next.addA[static_cast<int64_t>(jr) * FD * FD + r * FD + (q - FD)] = -sr;  // A_r -= H[r,pl] Z_R
         }
       } else if (q < 2 * FD + G) {
         El[r * G + (q - 2 * FD)] -= sl;
-        if (hasR) a.next.addE[static_cast<int64_t>(j + 1) * FD * G + r * G + (q - 2 * FD)] = -sr;
+        if (hasR) a.next.addE[static_cast<int64_t>(jr) * FD * G + r * G + (q - 2 * FD)] = -sr;
       } else {
         gl[r] -= sl;
-        if (hasR) a.next.addg[static_cast<int64_t>(j + 1) * FD + r] = -sr;
+        if (hasR) a.next.addg[static_cast<int64_t>(jr) * FD + r] = -sr;
       }
     }
+  } else if (hasR) {
+    // no interior node between this separator and the ghost: the coupling passes through unchanged
+    for (int e = tid; e < FD * FD; e += kChainThreads) {
+      a.next.U[static_cast<int64_t>(jr) * FD * FD + e] = L.U[static_cast<int64_t>(rIdx) * FD * FD + e];
+      a.next.addA[static_cast<int64_t>(jr) * FD * FD + e] = 0.0;
+    }
+    for (int e = tid; e < FD * G; e += kChainThreads) a.next.addE[static_cast<int64_t>(jr) * FD * G + e] = 0.0;
+    for (int e = tid; e < FD; e += kChainThreads) a.next.addg[static_cast<int64_t>(jr) * FD + e] = 0.0;
+  }
+  if (toGhost) {  // carry the ghost node itself to the next level (its Schur updates went to next.add*)
+    for (int e = tid; e < FD * FD; e += kChainThreads)
+      a.next.A[static_cast<int64_t>(jr) * FD * FD + e] = L.A[static_cast<int64_t>(rIdx) * FD * FD + e] + (add ? L.addA[static_cast<int64_t>(rIdx) * FD * FD + e] : 0.0);
+    for (int e = tid; e < FD * G; e += kChainThreads)
+      a.next.E[static_cast<int64_t>(jr) * FD * G + e] = L.E[static_cast<int64_t>(rIdx) * FD * G + e] + (add ? L.addE[static_cast<int64_t>(rIdx) * FD * G + e] : 0.0);
+    for (int e = tid; e < FD; e += kChainThreads)
+      a.next.g[static_cast<int64_t>(jr) * FD + e] = L.g[static_cast<int64_t>(rIdx) * FD + e] + (add ? L.addg[static_cast<int64_t>(rIdx) * FD + e] : 0.0);
+    if (tid == 0) a.next.orig[jr] = L.orig[rIdx];
   }
   __syncthreads();
   for (int e = tid; e < FD * FD; e += kChainThreads) {
@@ -329,13 +360,18 @@ struct DenseArgs {
   ChainLevel top;      // n may be 0
   double* delta;
   double* scalars;
+  int n_slots;         // frame blocks in the dense system (single GPU: top.n; sharded: one per rank)
+  int slot_of[4];      // dense slot of each local top node
+  int add_globals;     // 1: this rank contributes C + D and -g_c (exactly one rank does)
+  int mode;            // 0: assemble + solve; 1: assemble the local partial into buf only; 2: solve the (summed) buf
+  double* buf;         // [N*N + N], N = G + n_slots*FD
 };
 template <int FD>
 __global__ void __launch_bounds__(256) dense_solve_kernel(DenseArgs a) {
   extern __shared__ double sm[];
-  const int G = a.dp.G, nt = a.top.n, N = G + nt * FD, tid = threadIdx.x;
-  double* S = sm;          // [N*N]
-  double* rhs = sm + N * N;
+  const int G = a.dp.G, nt = a.top.n, N = G + a.n_slots * FD, tid = threadIdx.x;
+  double* S = a.mode == 1 ? a.buf : sm;              // [N*N]
+  double* rhs = S + N * N;
   __shared__ int bad;
   if (a.ctl->done) return;
   const Blocks& b = a.bs[a.ctl->cur];
@@ -343,40 +379,49 @@ __global__ void __launch_bounds__(256) dense_solve_kernel(DenseArgs a) {
   if (tid == 0) bad = 0;
   const int64_t nfp = static_cast<int64_t>(a.dp.n_frames) * a.dp.fd;
   const double* sc = a.scale + nfp;
-  for (int e = tid; e < N * N; e += 256) S[e] = 0.0;
-  __syncthreads();
-  for (int e = tid; e < G * G + G; e += 256) {
-    if (e < G * G) {
-      const int r = e / G, c = e - r * G;
-      double v = b.C[e] * sc[r] * sc[c] - a.Ssum[e];
-      if (r == c) v += a.D2x ? a.D2x[nfp + r] : lm_damp(b.C[e], sc[r], rinv);
-      S[r * N + c] = v;
-    } else {
-      const int r = e - G * G;
-      rhs[r] = -b.gc[r] * sc[r] + a.Ssum[e];
-    }
-  }
-  const bool add = a.top.addA != nullptr;
-  for (int t = 0; t < nt; ++t) {
-    const int o = G + t * FD;
-    for (int e = tid; e < FD * FD; e += 256) {
-      const int r = e / FD, c = e - r * FD;
-      S[(o + r) * N + o + c] = a.top.A[static_cast<int64_t>(t) * FD * FD + e] + (add ? a.top.addA[static_cast<int64_t>(t) * FD * FD + e] : 0.0);
-      if (t > 0) {
-        const double u = a.top.U[static_cast<int64_t>(t) * FD * FD + e];  // H[t-1, t]
-        S[(o - FD + r) * N + o + c] = u;
-        S[(o + c) * N + o - FD + r] = u;
+  if (a.mode == 2) {
+    for (int e = tid; e < N * N + N; e += 256) S[e] = a.buf[e];
+  } else {
+    for (int e = tid; e < N * N + N; e += 256) S[e] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < G * G + G; e += 256) {
+      if (e < G * G) {
+        const int r = e / G, c = e - r * G;
+        double v = -a.Ssum[e];
+        if (a.add_globals) {
+          v += b.C[e] * sc[r] * sc[c];
+          if (r == c) v += a.D2x ? a.D2x[nfp + r] : lm_damp(b.C[e], sc[r], rinv);
+        }
+        S[r * N + c] = v;
+      } else {
+        const int r = e - G * G;
+        rhs[r] = (a.add_globals ? -b.gc[r] * sc[r] : 0.0) + a.Ssum[e];
       }
     }
-    for (int e = tid; e < FD * G; e += 256) {
-      const int r = e / G, c = e - r * G;
-      const double v = a.top.E[static_cast<int64_t>(t) * FD * G + e] + (add ? a.top.addE[static_cast<int64_t>(t) * FD * G + e] : 0.0);
-      S[(o + r) * N + c] = v;
-      S[c * N + o + r] = v;
+    const bool add = a.top.addA != nullptr;
+    for (int t = 0; t < nt; ++t) {
+      const int o = G + a.slot_of[t] * FD;
+      for (int e = tid; e < FD * FD; e += 256) {
+        const int r = e / FD, c = e - r * FD;
+        S[(o + r) * N + o + c] = a.top.A[static_cast<int64_t>(t) * FD * FD + e] + (add ? a.top.addA[static_cast<int64_t>(t) * FD * FD + e] : 0.0);
+        if (t > 0) {
+          const int op = G + a.slot_of[t - 1] * FD;
+          const double u = a.top.U[static_cast<int64_t>(t) * FD * FD + e];  // H[t-1, t]
+          S[(op + r) * N + o + c] = u;
+          S[(o + c) * N + op + r] = u;
+        }
+      }
+      for (int e = tid; e < FD * G; e += 256) {
+        const int r = e / G, c = e - r * G;
+        const double v = a.top.E[static_cast<int64_t>(t) * FD * G + e] + (add ? a.top.addE[static_cast<int64_t>(t) * FD * G + e] : 0.0);
+        S[(o + r) * N + c] = v;
+        S[c * N + o + r] = v;
+      }
+      for (int e = tid; e < FD; e += 256)
+        rhs[o + e] = -(a.top.g[static_cast<int64_t>(t) * FD + e] + (add ? a.top.addg[static_cast<int64_t>(t) * FD + e] : 0.0));
     }
-    for (int e = tid; e < FD; e += 256)
-      rhs[o + e] = -(a.top.g[static_cast<int64_t>(t) * FD + e] + (add ? a.top.addg[static_cast<int64_t>(t) * FD + e] : 0.0));
   }
+  if (a.mode == 1) return;
   __syncthreads();
   for (int j = 0; j < N; ++j) {
     if (tid == 0) {
@@ -417,7 +462,7 @@ __global__ void __launch_bounds__(256) dense_solve_kernel(DenseArgs a) {
   for (int i = tid; i < G; i += 256) a.delta[nfp + i] = bad ? 0.0 : rhs[i];
   for (int e = tid; e < nt * FD; e += 256) {
     const int t = e / FD, r = e - t * FD;
-    a.delta[static_cast<int64_t>(a.top.orig[t]) * FD + r] = bad ? 0.0 : rhs[G + e];
+    a.delta[static_cast<int64_t>(a.top.orig[t]) * FD + r] = bad ? 0.0 : rhs[G + a.slot_of[t] * FD + r];
   }
 }
 
@@ -434,8 +479,10 @@ __global__ void __launch_bounds__(128) chain_backsub_kernel(BacksubArgs a) {
   const int G = a.G, c = a.c, w = 2 * FD + G + 1;
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * 4 + (threadIdx.x >> 5);  // node index at this level
-  if (a.ctl->done || p >= a.cur.n || p % c == 0) return;              // separators are solved at the next level
-  const int s = (p / c) * c, r = s + c;
+  const int n_eff = a.cur.n - a.cur.ghost;
+  if (a.ctl->done || p >= n_eff || p % c == 0) return;              // separators (and the ghost) are solved at the next level
+  const int s = (p / c) * c;
+  const int r = s + c < n_eff ? s + c : (a.cur.ghost ? a.cur.n - 1 : a.cur.n);
   const double* xl = a.delta + static_cast<int64_t>(a.cur.orig[s]) * FD;
   const double* xr = r < a.cur.n ? a.delta + static_cast<int64_t>(a.cur.orig[r]) * FD : nullptr;
   const double* dc = a.delta + a.nfp;

@@ -163,6 +163,9 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     const bool split = NS > 512;  // large global block: level 2 as its own parallel launches
     ra.dp = vdp; ra.ctl = h->d_ctl; ra.which = which; ra.decide_mode = multi ? -1 : decide_mode; ra.multi = multi ? 1 : 0;
     ra.level1_only = split ? 1 : 0;
+    const bool sep = multi && dp.inertial;  // separator frames' gradients are normed after the all-reduce
+    ra.gf_skip_below = sep ? dp.fd : 0;
+    ra.gf_skip_from = sep ? static_cast<int64_t>(dp.n_own) * dp.fd : static_cast<int64_t>(dp.n_frames) * dp.fd;
     ra.Cg = h->d_Cg; ra.imuCg = dp.inertial ? imu_cg(h) : nullptr; ra.ni = dp.n_frames - 1; ra.imu_goff = dp.imu_goff;
     ra.imu_stride = kImuCgStride;
     ra.Cpart = h->d_Cpart; ra.red_part = h->d_red_part;
@@ -183,10 +186,13 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
       h->launches += 2;
     }
     if (multi) {  // sum the global blocks, cost and step scalars over the frame shards, then decide everywhere
-      mg_pack_kernel<<<8, 256, 0, h->stream>>>(dp.G, h->d_ctl, which, h->blk[0], h->blk[1], h->d_scalars, h->rank, h->nranks, h->d_mg);
+      const int sep_fd = sep ? dp.fd : 0;
+      mg_pack_kernel<<<8, 256, 0, h->stream>>>(dp.G, h->d_ctl, which, h->blk[0], h->blk[1], h->d_scalars, h->rank, h->nranks, h->d_mg,
+                                               sep_fd, dp.n_frames, dp.ghost);
       ++h->launches;
-      VC_TRY(all_reduce(h, h->d_mg, NS + 6 + h->nranks));
-      mg_unpack_decide_kernel<<<1, 256, 0, h->stream>>>(dp.G, h->d_ctl, which, h->blk[0], h->blk[1], h->d_scalars, h->nranks, h->d_mg, decide_mode);
+      VC_TRY(all_reduce(h, h->d_mg, NS + 6 + h->nranks + 2 * static_cast<size_t>(sep_fd) * h->nranks));
+      mg_unpack_decide_kernel<<<1, 256, 0, h->stream>>>(dp.G, h->d_ctl, which, h->blk[0], h->blk[1], h->d_scalars, h->nranks, h->d_mg,
+                                                        decide_mode, sep_fd, h->d_sep);
       ++h->launches;
     }
   }
@@ -254,7 +260,7 @@ static int solve_and_update(vcgpu_handle* h, const double* D2x, bool with_update
       UpdateArgs ua;
       ua.dp = dp; ua.b[0] = h->blk[0]; ua.b[1] = h->blk[1]; ua.ctl = h->d_ctl; ua.scale = h->d_scale; ua.D2x = D2x;
       ua.X = h->d_X; ua.delta = h->d_delta; ua.state[0] = h->d_state[0]; ua.state[1] = h->d_state[1];
-      ua.step_part = h->d_red;
+      ua.step_part = h->d_red; ua.sepdiag = nullptr;
       const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
       backsub_update_kernel<6><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
       ++h->launches;
@@ -302,8 +308,6 @@ static int enqueue_iteration(vcgpu_handle* h, bool weights) {
 // ------------------------------------------------------------------ the trust-region loop
 static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out, int fixed_iters) {
   VC_TRY(prepare(h));
-  if (h->nranks > 1 && h->dp.inertial)
-    return fail(h, VCGPU_ERR_INVALID, "frame-sharded multi-GPU runs support the visual terms only in this build");
   if (h->opts.strategy != 0) return fail(h, VCGPU_ERR_INVALID, "DOGLEG strategy is not implemented on the device yet; use strategy 0 (LM)");
   const DevProblem& dp = h->dp;
   const vcgpu_options& o = h->opts;
@@ -317,7 +321,8 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
   if (weights) VC_TRY(imu_update_weights(h));  // vicalibrator.h:955
   VC_TRY(evaluate_into(h, 0, false, 0));
   if (o.jacobi_scaling) {
-    jacobi_scale_kernel<<<static_cast<int>((np + 255) / 256), 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale);
+    jacobi_scale_kernel<<<static_cast<int>((np + 255) / 256), 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale,
+                                                                                   (h->nranks > 1 && dp.inertial) ? h->d_sep : nullptr);
     ++h->launches;
   } else {
     std::vector<double> ones(np, 1.0);

@@ -71,10 +71,13 @@ static int imu_prepare(vcgpu_handle* h) {
   CUDA_TRY(h, cudaMemset(d->Cg, 0, static_cast<size_t>(nf) * kImuCgStride * sizeof(double)));
   // chain levels
   const size_t w_cols = 2 * FD + G + 1;
+  // level sizes; a sharded rank reduces its chain to its first frame (+ the ghost) — the separators
+  // of all ranks then meet in the all-reduced dense system
   std::vector<int> sizes;
-  for (int m = nf;; m = (m + kChainC - 1) / kChainC) {
-    sizes.push_back(m);
-    if (m <= kChainTop) break;
+  const int top = h->nranks > 1 ? 1 : kChainTop;
+  for (int m = dp.n_own;; m = (m + kChainC - 1) / kChainC) {
+    sizes.push_back(m + dp.ghost);
+    if (m <= top) break;
   }
   size_t total = 0, itotal = 0;
   int n_part = 0;
@@ -82,7 +85,7 @@ static int imu_prepare(vcgpu_handle* h) {
     const size_t m = sizes[l];
     total += m * (2 * FD * FD + FD * G + FD);
     if (l > 0) total += m * (FD * FD + FD * G + FD);
-    if (l + 1 < sizes.size()) { total += m * FD * w_cols; n_part += (static_cast<int>(m) + kChainC - 1) / kChainC; }
+    if (l + 1 < sizes.size()) { total += m * FD * w_cols; n_part += (static_cast<int>(m) - dp.ghost + kChainC - 1) / kChainC; }
     itotal += m;
   }
   VC_TRY(dev_alloc(h, &d->pool, total));
@@ -94,6 +97,7 @@ static int imu_prepare(vcgpu_handle* h) {
     const size_t m = sizes[l];
     vc::ChainLevel& L = d->levels[l];
     L.n = static_cast<int>(m);
+    L.ghost = dp.ghost;
     L.A = p; p += m * FD * FD;
     L.U = p; p += m * FD * FD;
     L.E = p; p += m * FD * G;
@@ -164,7 +168,8 @@ static int imu_chain_eliminate(vcgpu_handle* h, const double* D2x) {
   constexpr int FD = 9;
   const int G = dp.G;
   const size_t NS = static_cast<size_t>(G) * G + G;
-  chain_init_kernel<FD><<<dp.n_frames, 128, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, D2x, d->levels[0]);
+  chain_init_kernel<FD><<<dp.n_frames, 128, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, D2x, d->levels[0],
+                                                           h->nranks > 1 ? h->d_sep : nullptr);
   ++h->launches;
   const size_t w_cols = 2 * FD + G + 1;
   const size_t esm = (NS + 3 * FD * FD + FD * G + FD + static_cast<size_t>(kChainC - 1) * FD * (FD + w_cols)) * sizeof(double);
@@ -179,7 +184,7 @@ static int imu_chain_eliminate(vcgpu_handle* h, const double* D2x) {
     ElimArgs ea;
     ea.G = G; ea.c = kChainC; ea.ctl = h->d_ctl; ea.cur = d->levels[l]; ea.next = d->levels[l + 1];
     ea.Spart = h->d_Spart + static_cast<size_t>(part) * NS; ea.scalars = h->d_scalars;
-    const int nsep = d->levels[l + 1].n;
+    const int nsep = d->levels[l + 1].n - dp.ghost;  // one CTA per separator-led chunk
     chain_eliminate_kernel<FD><<<nsep, kChainThreads, esm, h->stream>>>(ea);
     ++h->launches;
     part += nsep;
@@ -190,7 +195,10 @@ static int imu_chain_eliminate(vcgpu_handle* h, const double* D2x) {
   return VCGPU_OK;
 }
 
-// dense solve of [globals | top-level nodes]; globals and top-node steps land in d_delta
+// dense solve of [globals | top-level nodes]; globals and top-node steps land in d_delta.
+// Sharded: every rank assembles its partial of the [globals | one separator per rank] system, one
+// all-reduce sums them, every rank factors the same matrix.
+static int all_reduce(vcgpu_handle* h, double* buf, size_t n);
 static int imu_chain_dense(vcgpu_handle* h, const double* D2x) {
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
@@ -198,9 +206,25 @@ static int imu_chain_dense(vcgpu_handle* h, const double* D2x) {
   DenseArgs da;
   da.dp = dp; da.bs[0] = h->blk[0]; da.bs[1] = h->blk[1]; da.ctl = h->d_ctl; da.scale = h->d_scale; da.D2x = D2x;
   da.Ssum = d->Ssum; da.top = d->levels.back(); da.delta = h->d_delta; da.scalars = h->d_scalars;
-  const size_t N = dp.G + static_cast<size_t>(d->levels.back().n) * FD;
-  dense_solve_kernel<FD><<<1, 256, (N * N + N) * sizeof(double), h->stream>>>(da);
-  ++h->launches;
+  da.buf = h->d_dense;
+  const bool multi = h->nranks > 1;
+  da.n_slots = multi ? h->nranks : da.top.n;
+  for (int t = 0; t < 4; ++t) da.slot_of[t] = multi ? h->rank + t : t;  // own first frame, then the ghost
+  da.add_globals = h->rank == 0 ? 1 : 0;
+  const size_t N = dp.G + static_cast<size_t>(da.n_slots) * FD;
+  const size_t sm = (N * N + N) * sizeof(double);
+  if (!multi) {
+    da.mode = 0;
+    dense_solve_kernel<FD><<<1, 256, sm, h->stream>>>(da);
+    ++h->launches;
+  } else {
+    da.mode = 1;
+    dense_solve_kernel<FD><<<1, 256, 0, h->stream>>>(da);
+    VC_TRY(all_reduce(h, h->d_dense, N * N + N));
+    da.mode = 2;
+    dense_solve_kernel<FD><<<1, 256, sm, h->stream>>>(da);
+    h->launches += 2;
+  }
   CUDA_TRY(h, cudaGetLastError());
   return VCGPU_OK;
 }
@@ -221,7 +245,7 @@ static int imu_chain_backsub(vcgpu_handle* h, const double* D2x, bool explicit_u
     UpdateArgs ua;
     ua.dp = dp; ua.b[0] = h->blk[0]; ua.b[1] = h->blk[1]; ua.ctl = h->d_ctl; ua.scale = h->d_scale; ua.D2x = D2x;
     ua.X = nullptr; ua.delta = h->d_delta; ua.state[0] = h->d_state[0]; ua.state[1] = h->d_state[1];
-    ua.step_part = h->d_red;
+    ua.step_part = h->d_red; ua.sepdiag = h->nranks > 1 ? h->d_sep : nullptr;
     const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
     backsub_update_kernel<9><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
     ++h->launches;

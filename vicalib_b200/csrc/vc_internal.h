@@ -32,6 +32,9 @@ struct CamInfo {
 struct DevProblem {
   int n_cams, n_frames, fd, G, imu_goff;
   int inertial, rotation_only;
+  // frame-sharded run: with inertial terms every rank but the last carries the next rank's first frame as
+  // a trailing ghost (n_frames counts it, n_own does not); vision-only shards have no ghost
+  int rank, nranks, ghost, n_own;
   double visual_mult, imu_mult;
   CamInfo cams[kMaxCams];
   // state layout (doubles): T_wp 7*nf | v_w 3*nf | cams 17*nc | imu 15
@@ -149,5 +152,7 @@ struct vcgpu_handle {
   // multi-GPU (one process per GPU; frames sharded; see vc_engine.inl)
   void* comm = nullptr;           // ncclComm_t
   int rank = 0, nranks = 1;
-  double* d_mg = nullptr;         // all-reduce buffer [G*G+G+6+nranks]
+  double* d_mg = nullptr;         // all-reduce buffer [G*G+G+6+nranks (+ 18*nranks)]
+  double* d_sep = nullptr;        // [2][nranks*9]: summed diag(B) and g of the separator frames (sharded inertial runs)
+  double* d_dense = nullptr;      // [N*N+N] all-reduced dense system, N = G + 9*nranks
 };

@@ -427,6 +427,7 @@ struct RedFinArgs {
   int decide_mode;      // -1: none (multi-GPU: decide after the all-reduce), 0: initial point, 1: iteration
   int multi;            // 1: frame-sharded run: scalars cover this rank's frames only (gc joins after the all-reduce)
   int level1_only;      // 1: stop after the per-CTA partials (large G: level 2 runs as its own parallel launches)
+  int64_t gf_skip_below, gf_skip_from;  // sharded inertial run: separator frames' gradients are normed after the all-reduce
   const double* Cg;
   const double* imuCg;  // [ni][kImuCgStride] or null
   int ni, imu_goff, imu_stride;
@@ -521,6 +522,7 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
     for (int k = li + tid; k < hi2; k += 256) v[0] += a.imu_cost_part[k];
     const int64_t lg = static_cast<int64_t>(a.n_frames_fd) * bid / nb, hg = static_cast<int64_t>(a.n_frames_fd) * (bid + 1) / nb;
     for (int64_t k = lg + tid; k < hg; k += 256) {
+      if (k < a.gf_skip_below || k >= a.gf_skip_from) continue;
       const double g = out.gf[k];
       v[6] = fmax(v[6], fabs(g));
       v[1] += g * g;
@@ -669,12 +671,23 @@ __global__ void __launch_bounds__(256) finalize_small_kernel(RedFinArgs a, int n
 
 // ---------------------------------------------------------------- multi-GPU: pack / unpack around the all-reduce
 // buffer: [C G*G | gc G | cost, |gf|^2, dotG, dotD, step2, xnorm2 | per-rank |gf|_inf slots]
+// sharded inertial runs append [diag(B) of separator frames P*9 | g of separator frames P*9]
 __global__ void mg_pack_kernel(int G, const Ctl* ctl, int which, Blocks b0, Blocks b1, const double* scalars, int rank,
-                               int nranks, double* buf) {
+                               int nranks, double* buf, int sep_fd, int n_frames, int ghost) {
   if (ctl->done) return;
   const Blocks& b = pick(ctl, which) ? b1 : b0;
   const int NS = G * G + G, tid = blockIdx.x * blockDim.x + threadIdx.x;
   for (int k = tid; k < NS; k += gridDim.x * blockDim.x) buf[k] = k < G * G ? b.C[k] : b.gc[k - G * G];
+  if (sep_fd > 0) {
+    double* sd = buf + NS + 6 + nranks;
+    double* sg = sd + nranks * sep_fd;
+    for (int k = tid; k < nranks * sep_fd; k += gridDim.x * blockDim.x) {
+      const int slot = k / sep_fd, r = k - slot * sep_fd;
+      const int f = slot == rank ? 0 : (ghost && slot == rank + 1 ? n_frames - 1 : -1);
+      sd[k] = f >= 0 ? b.B[(static_cast<int64_t>(f) * sep_fd + r) * sep_fd + r] : 0.0;
+      sg[k] = f >= 0 ? b.gf[static_cast<int64_t>(f) * sep_fd + r] : 0.0;
+    }
+  }
   if (tid == 0) {
     buf[NS + 0] = scalars[kScCost];
     buf[NS + 1] = scalars[kScGnorm2];
@@ -686,7 +699,7 @@ __global__ void mg_pack_kernel(int G, const Ctl* ctl, int which, Blocks b0, Bloc
   }
 }
 __global__ void mg_unpack_decide_kernel(int G, Ctl* ctl, int which, Blocks b0, Blocks b1, double* scalars, int nranks,
-                                        const double* buf, int decide_mode) {
+                                        const double* buf, int decide_mode, int sep_fd, double* sep_out) {
   if (ctl->done) return;
   const Blocks& b = pick(ctl, which) ? b1 : b0;
   const int NS = G * G + G, tid = threadIdx.x;
@@ -700,6 +713,16 @@ __global__ void mg_unpack_decide_kernel(int G, Ctl* ctl, int which, Blocks b0, B
       b.gc[k - G * G] = v;
       gm = fmax(gm, fabs(v));
       g2 += v * v;
+    }
+  }
+  if (sep_fd > 0) {  // separator frames: keep the summed diagonal / gradient, norm the gradient once
+    const double* sd = buf + NS + 6 + nranks;
+    for (int k = tid; k < 2 * nranks * sep_fd; k += 256) {
+      sep_out[k] = sd[k];
+      if (k >= nranks * sep_fd) {
+        gm = fmax(gm, fabs(sd[k]));
+        g2 += sd[k] * sd[k];
+      }
     }
   }
   shm[tid] = gm;
@@ -723,7 +746,7 @@ __global__ void mg_unpack_decide_kernel(int G, Ctl* ctl, int which, Blocks b0, B
 
 // ---------------------------------------------------------------- Jacobi scaling
 // scale = 1/(1+sqrt(diag(J'J)))   (Ceres TrustRegionMinimizer, jacobi_scaling, computed once)
-__global__ void jacobi_scale_kernel(DevProblem dp, Blocks b0, Blocks b1, const Ctl* ctl, double* out) {
+__global__ void jacobi_scale_kernel(DevProblem dp, Blocks b0, Blocks b1, const Ctl* ctl, double* out, const double* sepdiag) {
   const Blocks& b = ctl->cur ? b1 : b0;
   const int64_t n = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -734,6 +757,10 @@ __global__ void jacobi_scale_kernel(DevProblem dp, Blocks b0, Blocks b1, const C
     const int64_t f = i / dp.fd;
     const int k = static_cast<int>(i - f * dp.fd);
     d = b.B[(f * dp.fd + k) * dp.fd + k];
+    if (sepdiag) {  // separator frames: the diagonal summed over the two ranks that hold a piece of it
+      if (f == 0) d = sepdiag[dp.rank * dp.fd + k];
+      else if (dp.ghost && f == dp.n_frames - 1) d = sepdiag[(dp.rank + 1) * dp.fd + k];
+    }
   } else {
     const int k = static_cast<int>(i - nfp);
     d = b.C[k * dp.G + k];
@@ -972,6 +999,7 @@ struct UpdateArgs {
   double* delta;
   double* state[2];
   double* step_part;  // [gridDim+1][4]
+  const double* sepdiag;  // sharded inertial run: summed diagonal of the separator frames, else null
 };
 constexpr int kUpdateWarps = 4;
 
@@ -1008,11 +1036,16 @@ __global__ void __launch_bounds__(32 * kUpdateWarps) backsub_update_kernel(Updat
     }
     if (lane == 0) {
       double du[FD];
+      const bool is_ghost = a.dp.ghost && f == nf - 1;
 #pragma unroll
       for (int r = 0; r < FD; ++r) {
         const int64_t k = static_cast<int64_t>(f) * FD + r;
         const double sc = a.scale[k];
-        const double d2 = a.D2x ? a.D2x[k] : lm_damp(b.B[k * FD + r], sc, rinv);
+        double d2;
+        if (a.D2x) d2 = a.D2x[k];
+        else if (a.sepdiag && f == 0) d2 = lm_damp(a.sepdiag[a.dp.rank * FD + r], sc, rinv);
+        else if (is_ghost) d2 = 0.0;  // damped (and counted) by its owner
+        else d2 = lm_damp(b.B[k * FD + r], sc, rinv);
         a.delta[k] = d[r];
         acc[0] += d[r] * b.gf[k] * sc;
         acc[1] += d[r] * d[r] * d2;
@@ -1024,8 +1057,10 @@ __global__ void __launch_bounds__(32 * kUpdateWarps) backsub_update_kernel(Updat
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
         x_new[7 * static_cast<int64_t>(f) + k] = xo[k];
-        acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
-        acc[3] += xo[k] * xo[k];
+        if (!is_ghost) {
+          acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+          acc[3] += xo[k] * xo[k];
+        }
       }
       const double* v = x_cur + a.dp.off_v + 3 * static_cast<int64_t>(f);
       double* vo = x_new + a.dp.off_v + 3 * static_cast<int64_t>(f);
@@ -1033,7 +1068,7 @@ __global__ void __launch_bounds__(32 * kUpdateWarps) backsub_update_kernel(Updat
       for (int k = 0; k < 3; ++k) {
         const double nv = (FD == 9) ? v[k] + du[(FD == 9) ? 6 + k : 0] : v[k];
         vo[k] = nv;
-        if (FD == 9) {
+        if (FD == 9 && !is_ghost) {
           acc[2] += (nv - v[k]) * (nv - v[k]);
           acc[3] += nv * nv;
         }

@@ -167,7 +167,7 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_red); dev_free(&h->d_scalars); dev_free(&h->d_Ssum); dev_free(&h->d_red_part); dev_free(&h->d_counter);
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
-  dev_free(&h->d_mg);
+  dev_free(&h->d_mg); dev_free(&h->d_sep); dev_free(&h->d_dense);
   if (h->comm) ncclCommDestroy(static_cast<ncclComm_t>(h->comm));
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -409,6 +409,12 @@ static int prepare(vcgpu_handle* h) {
     h->n_groups = static_cast<int>(grp_start.size());
     dp.inertial = h->flags.inertial ? 1 : 0;
     dp.fd = dp.inertial ? 9 : 6;
+    dp.rank = h->rank;
+    dp.nranks = h->nranks;
+    // sharded inertial run: the caller appended the next rank's first frame (the cross-shard IMU factor needs it)
+    dp.ghost = (dp.inertial && h->nranks > 1 && h->rank < h->nranks - 1) ? 1 : 0;
+    dp.n_own = nf - dp.ghost;
+    if (dp.ghost && nf < 2) return fail(h, VCGPU_ERR_INVALID, "a sharded inertial rank needs its own frames plus the ghost frame");
     dp.imu_goff = goff;
     dp.G = goff + (dp.inertial ? 15 : 0);
     dp.off_v = 7LL * nf;
@@ -474,7 +480,12 @@ static int prepare(vcgpu_handle* h) {
     VC_TRY(dev_alloc(h, &h->d_delta, np));
     VC_TRY(dev_alloc(h, &h->d_red, 4 * (static_cast<size_t>(nf) + 2)));
     VC_TRY(dev_alloc(h, &h->d_red_part, 8 * kReduceBlocks));
-    VC_TRY(dev_alloc(h, &h->d_mg, NS + 6 + h->nranks));
+    VC_TRY(dev_alloc(h, &h->d_mg, NS + 6 + h->nranks + 18 * h->nranks));
+    VC_TRY(dev_alloc(h, &h->d_sep, 18 * h->nranks));
+    {
+      const size_t N = static_cast<size_t>(G) + 9 * h->nranks;
+      VC_TRY(dev_alloc(h, &h->d_dense, N * N + N));
+    }
     VC_TRY(dev_alloc(h, &h->d_counter, 4));
     CUDA_TRY(h, cudaMemset(h->d_counter, 0, 4 * sizeof(unsigned)));
     VC_TRY(dev_alloc(h, &h->d_scalars, kScCount));

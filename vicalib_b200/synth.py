@@ -408,17 +408,17 @@ def shard_frames(n_frames: int, rank: int, world: int):
 
 
 def shard(p: Problem, rank: int, world: int) -> Problem:
-    """Rank-local slice of a vision-only problem: the rank's frames (re-indexed from 0) and the
-    observations of those frames; cameras / globals are replicated.  Inertial problems also need the
-    next rank's first frame as a ghost (cross-shard IMU factor) and are not sharded by this helper."""
-    if p.inertial:
-        raise NotImplementedError("sharding of inertial problems needs ghost frames")
+    """Rank-local slice: the rank's frames (re-indexed from 0) and the observations of those frames;
+    cameras / globals / the IMU stream are replicated.  With inertial terms every rank but the last
+    also gets the next rank's first frame appended as a ghost (no observations): the IMU factor
+    between its last frame and that frame is owned by this rank."""
     f0, f1 = shard_frames(p.n_frames, rank, world)
+    g1 = f1 + (1 if (p.inertial and rank < world - 1) else 0)
     sel = (p.obs_frame >= f0) & (p.obs_frame < f1)
     truth = dict(p.truth)
-    truth["T_wp"] = p.truth["T_wp"][f0:f1]
-    truth["v_w"] = p.truth["v_w"][f0:f1]
+    truth["T_wp"] = p.truth["T_wp"][f0:g1]
+    truth["v_w"] = p.truth["v_w"][f0:g1]
     return dataclasses.replace(
-        p, T_wp=p.T_wp[f0:f1].copy(), v_w=p.v_w[f0:f1].copy(), ftime=p.ftime[f0:f1].copy(),
+        p, T_wp=p.T_wp[f0:g1].copy(), v_w=p.v_w[f0:g1].copy(), ftime=p.ftime[f0:g1].copy(),
         obs_frame=(p.obs_frame[sel] - f0).astype(np.int32), obs_cam=p.obs_cam[sel].copy(), p_w=p.p_w[sel].copy(),
         p_c=p.p_c[sel].copy(), grid_idx=p.grid_idx[sel].copy(), truth=truth)
