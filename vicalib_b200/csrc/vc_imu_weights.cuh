@@ -173,113 +173,127 @@ __device__ inline void dLog_dSE3(Quat<double> q, Vec<double> tr, double dlog[42]
 
 // per-warp shared workspace (doubles)
 struct Work {
-  double C[100], dy_db[60], dy_dy0[100], dk_db[54], dk_dy[90], dy_dk[90], dy_dy[100];
-  double T_db[54], T_dy[90], tot_db[54], tot_dy[90], t1[100], t2[100];
+  double C[100], A[100], Gm[60], t1[100], t2[100], t3[100];
 };
 
-// GetPoseDerivative with Jacobians (types.h:380-425); every lane computes k, lane 0 fills the blocks
-__device__ inline void pose_derivative_jac(const Pose<double>& y, Vec<double> g, const Meas<double>& z0, const Meas<double>& z1,
-                                           Vec<double> bg, Vec<double> ba, const double sf[6], double dt, double k[9],
-                                           Work* W, int lane) {
-  imu::pose_derivative<double>(y, g, z0, z1, bg, ba, sf, dt, k);
-  wzero(W->dk_db, 54, lane);
-  wzero(W->dk_dy, 90, lane);
-  if (lane == 0) {
-    const double alpha = (z1.time - (z0.time + dt)) / (z1.time - z0.time);
-    const Vec<double> zg = imu::scale(z0.w, alpha) + imu::scale(z1.w, 1.0 - alpha);
-    const Vec<double> za = imu::scale(z0.a, alpha) + imu::scale(z1.a, 1.0 - alpha);
-    double R[9];
-    qmat(Q4{y.q.x, y.q.y, y.q.z, y.q.w}, R);
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        W->dk_db[(3 + i) * 6 + j] = R[i * 3 + j];      // dw/dbg
-        W->dk_db[(6 + i) * 6 + 3 + j] = R[i * 3 + j];  // da/dba
-      }
-    for (int i = 0; i < 3; ++i) W->dk_dy[i * 10 + 7 + i] = 1.0;  // dv/dv
-    // dw/dq and da/dq use the UNSCALED measurements (the reference ignores sf here, types.h:413-423)
-    dqx_dq(y.q, zg + bg, W->dk_dy + 3 * 10 + 3, 10);
-    dqx_dq(y.q, za + ba, W->dk_dy + 6 * 10 + 3, 10);
-  }
-  __syncwarp();
+// Jacobian pieces of one RK4 stage (types.h:380-425), computed redundantly by every lane
+struct StageJac {
+  double R[9];    // dw/dbg = da/dba = R(q)
+  double Dw[12];  // dw/dq = dqx_dq(q, zg) + dqx_dq(q, bg)   (unscaled measurements, as the reference)
+  double Da[12];  // da/dq = dqx_dq(q, za) + dqx_dq(q, ba)
+};
+__device__ inline void stage_jac(const Pose<double>& y, const Meas<double>& z0, const Meas<double>& z1, Vec<double> bg,
+                                 Vec<double> ba, double dt, StageJac* J) {
+  const double alpha = (z1.time - (z0.time + dt)) / (z1.time - z0.time);
+  const Vec<double> zg = imu::scale(z0.w, alpha) + imu::scale(z1.w, 1.0 - alpha);
+  const Vec<double> za = imu::scale(z0.a, alpha) + imu::scale(z1.a, 1.0 - alpha);
+  qmat(Q4{y.q.x, y.q.y, y.q.z, y.q.w}, J->R);
+  dqx_dq(y.q, zg + bg, J->Dw, 4);
+  dqx_dq(y.q, za + ba, J->Da, 4);
 }
-// IntegratePose with Jacobians (types.h:330-378)
-__device__ inline Pose<double> integrate_pose_jac(const Pose<double>& y0, const double k[9], double dt, Work* W, int lane) {
-  const Vec<double> wdt{k[3] * dt, k[4] * dt, k[5] * dt};
-  wzero(W->dy_dk, 90, lane);
-  wzero(W->dy_dy, 100, lane);
-  if (lane == 0) {
-    const Quat<double> r = imu::so3_exp<double>(wdt);
-    double a[16], e[12];
-    dq1q2_dq1(y0.q, a, 4);
-    dqExp_dw(wdt, e);
-    for (int i = 0; i < 3; ++i) { W->dy_dk[i * 9 + i] = dt; W->dy_dk[(7 + i) * 9 + 6 + i] = dt; }
-    for (int i = 0; i < 4; ++i)
-      for (int j = 0; j < 3; ++j) {
-        double s = 0;
-        for (int q = 0; q < 4; ++q) s += a[i * 4 + q] * e[q * 3 + j];
-        W->dy_dk[(3 + i) * 9 + 3 + j] = s * dt;
-      }
-    for (int i = 0; i < 3; ++i) { W->dy_dy[i * 10 + i] = 1.0; W->dy_dy[(7 + i) * 10 + 7 + i] = 1.0; }
-    dq1q2_dq2(r, W->dy_dy + 3 * 10 + 3, 10);
+// column j of the total derivative of this stage's k (9) w.r.t. [y0 (10) | b (6)]:
+//   T_j = dk_db[:, j-10] + dk_dy * col_j        (types.h:466-467 and the analogous lines per stage)
+__device__ __forceinline__ void stage_T(const double col[10], int j, const StageJac& J, double T[9]) {
+  T[0] = col[7]; T[1] = col[8]; T[2] = col[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T[3 + i] = J.Dw[i * 4] * col[3] + J.Dw[i * 4 + 1] * col[4] + J.Dw[i * 4 + 2] * col[5] + J.Dw[i * 4 + 3] * col[6];
+    T[6 + i] = J.Da[i * 4] * col[3] + J.Da[i * 4 + 1] * col[4] + J.Da[i * 4 + 2] * col[5] + J.Da[i * 4 + 3] * col[6];
   }
-  __syncwarp();
-  return imu::integrate_pose<double>(y0, k, dt);
+  if (j >= 10) {
+    const int bcol = j - 10;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (bcol < 3) T[3 + i] += J.R[i * 3 + bcol];
+      else T[6 + i] += J.R[i * 3 + bcol - 3];
+    }
+  }
+}
+// IntegratePose(y0, k, h) with its Jacobians folded into column j:
+//   col_j <- dy_dy[:, j] (direct dependence on y0; zero for the bias columns) + dy_dk * T_j   (types.h:330-378)
+__device__ inline Pose<double> integrate_push(const Pose<double>& y0, const double k[9], double h, const double T[9], int j,
+                                              double col[10]) {
+  const Vec<double> wdt{k[3] * h, k[4] * h, k[5] * h};
+  const Quat<double> r = imu::so3_exp<double>(wdt);
+  double a[16], e[12], Qq[16];
+  dq1q2_dq1(y0.q, a, 4);
+  dqExp_dw(wdt, e);
+  dq1q2_dq2(r, Qq, 4);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    col[i] = h * T[i] + (j == i ? 1.0 : 0.0);
+    col[7 + i] = h * T[6 + i] + (j == 7 + i ? 1.0 : 0.0);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double q = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) q += a[i * 4 + m] * e[m * 3 + c];
+      s += q * h * T[3 + c];
+    }
+    if (j >= 3 && j < 7) s += Qq[i * 4 + (j - 3)];
+    col[3 + i] = s;
+  }
+  return imu::integrate_pose<double>(y0, k, h);
 }
 
-// one RK4 stage's bookkeeping: T = total derivative of k_n; accumulate into tot with weight wgt;
-// then (dy_db, dy_dy0) <- Jacobians of IntegratePose(pose, k_n, h)
-__device__ inline void stage_total(Work* W, double wgt, int lane) {
-  // T_db = dk_db + dk_dy * dy_db ; T_dy = dk_dy * dy_dy0
-  wcopy(W->T_db, W->dk_db, 54, lane);
-  wmm(W->T_db, W->dk_dy, W->dy_db, 9, 10, 6, lane, false, true);
-  wmm(W->T_dy, W->dk_dy, W->dy_dy0, 9, 10, 10, lane);
-  waxpy(W->tot_db, W->T_db, wgt, 54, lane);
-  waxpy(W->tot_dy, W->T_dy, wgt, 90, lane);
-}
-__device__ inline void stage_push(Work* W, const double* k_db, const double* k_dy, int lane) {
-  // dy_db = dy_dk * k_db ; dy_dy0 = dy_dy + dy_dk * k_dy
-  wmm(W->dy_db, W->dy_dk, k_db, 10, 9, 6, lane);
-  wcopy(W->dy_dy0, W->dy_dy, 100, lane);
-  wmm(W->dy_dy0, W->dy_dk, k_dy, 10, 9, 10, lane, false, true);
-}
-
-// IntegrateImu, Jacobian + covariance branch (types.h:427-595): C <- A C A^T + G R G^T
+// IntegrateImu, Jacobian + covariance branch (types.h:427-595): C <- A C A^T + G R G^T.
+// Lane j < 16 carries column j of [dy/dy0 (10) | dy/db (6)] in registers through the four RK stages.
 __device__ inline Pose<double> integrate_imu_cov(const Pose<double>& pose, const Meas<double>& z0, const Meas<double>& z1,
                                                  Vec<double> bg, Vec<double> ba, const double sf[6], Vec<double> g,
                                                  double sg2, double sa2, Work* W, int lane) {
   const double dt = z1.time - z0.time;
   if (dt == 0) return pose;  // degenerate step: identity map (the reference leaves its outputs untouched)
-  double k1[9], k2[9], k3[9], k4[9], k[9];
-  wzero(W->dy_db, 60, lane);
-  wzero(W->dy_dy0, 100, lane);
-  wzero(W->tot_db, 54, lane);
-  wzero(W->tot_dy, 90, lane);
-  if (lane < 10) W->dy_dy0[lane * 11] = 1.0;
+  const int j = lane < 16 ? lane : 15;
+  double col[10], tot[9], T[9], k1[9], k2[9], k3[9], k4[9], k[9];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) col[i] = (j == i) ? 1.0 : 0.0;  // dy_dy0 = I, dy_db = 0
+  StageJac J;
+  imu::pose_derivative<double>(pose, g, z0, z1, bg, ba, sf, 0.0, k1);
+  stage_jac(pose, z0, z1, bg, ba, 0.0, &J);
+  stage_T(col, j, J, T);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) tot[i] = T[i];
+  const Pose<double> y1 = integrate_push(pose, k1, dt * 0.5, T, j, col);
+  imu::pose_derivative<double>(y1, g, z0, z1, bg, ba, sf, dt / 2, k2);
+  stage_jac(y1, z0, z1, bg, ba, dt / 2, &J);
+  stage_T(col, j, J, T);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) tot[i] += 2.0 * T[i];
+  const Pose<double> y2 = integrate_push(pose, k2, dt * 0.5, T, j, col);
+  imu::pose_derivative<double>(y2, g, z0, z1, bg, ba, sf, dt / 2, k3);
+  stage_jac(y2, z0, z1, bg, ba, dt / 2, &J);
+  stage_T(col, j, J, T);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) tot[i] += 2.0 * T[i];
+  const Pose<double> y3 = integrate_push(pose, k3, dt, T, j, col);
+  imu::pose_derivative<double>(y3, g, z0, z1, bg, ba, sf, dt, k4);
+  stage_jac(y3, z0, z1, bg, ba, dt, &J);
+  stage_T(col, j, J, T);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    tot[i] += T[i];
+    k[i] = k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i];
+  }
+  const Pose<double> res = integrate_push(pose, k, dt / 6.0, tot, j, col);
+  // C = A C A^T + G R G^T
+  if (lane < 10) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) W->A[i * 10 + lane] = col[i];
+  } else if (lane < 16) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) W->Gm[i * 6 + (lane - 10)] = col[i];
+  }
   __syncwarp();
-  pose_derivative_jac(pose, g, z0, z1, bg, ba, sf, 0.0, k1, W, lane);
-  stage_total(W, 1.0, lane);
-  const Pose<double> y1 = integrate_pose_jac(pose, k1, dt * 0.5, W, lane);
-  stage_push(W, W->T_db, W->T_dy, lane);
-  pose_derivative_jac(y1, g, z0, z1, bg, ba, sf, dt / 2, k2, W, lane);
-  stage_total(W, 2.0, lane);
-  const Pose<double> y2 = integrate_pose_jac(pose, k2, dt * 0.5, W, lane);
-  stage_push(W, W->T_db, W->T_dy, lane);
-  pose_derivative_jac(y2, g, z0, z1, bg, ba, sf, dt / 2, k3, W, lane);
-  stage_total(W, 2.0, lane);
-  const Pose<double> y3 = integrate_pose_jac(pose, k3, dt, W, lane);
-  stage_push(W, W->T_db, W->T_dy, lane);
-  pose_derivative_jac(y3, g, z0, z1, bg, ba, sf, dt, k4, W, lane);
-  stage_total(W, 1.0, lane);
-  for (int i = 0; i < 9; ++i) k[i] = k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i];
-  const Pose<double> res = integrate_pose_jac(pose, k, dt / 6.0, W, lane);
-  stage_push(W, W->tot_db, W->tot_dy, lane);
-  // C = dy_dy0 C dy_dy0^T + dy_db R dy_db^T, R = diag(sg2 x3, sa2 x3)
-  wmm(W->t1, W->dy_dy0, W->C, 10, 10, 10, lane);
-  wmm(W->t2, W->t1, W->dy_dy0, 10, 10, 10, lane, true);
+  wmm(W->t1, W->A, W->C, 10, 10, 10, lane);
+  wmm(W->t2, W->t1, W->A, 10, 10, 10, lane, true);
   for (int e = lane; e < 100; e += 32) {
     const int r = e / 10, c = e - r * 10;
     double s = 0.0;
-    for (int q = 0; q < 6; ++q) s += W->dy_db[r * 6 + q] * (q < 3 ? sg2 : sa2) * W->dy_db[c * 6 + q];
+    for (int q = 0; q < 6; ++q) s += W->Gm[r * 6 + q] * (q < 3 ? sg2 : sa2) * W->Gm[c * 6 + q];
     W->C[e] = W->t2[e] + s;
   }
   __syncwarp();
@@ -358,10 +372,10 @@ __global__ void __launch_bounds__(32 * kWtWarps) imu_weights_kernel(WeightArgs a
   __syncwarp();
   // P = Jt C Jt^T  (9x9) -> T_dy[0..80]
   wmm(tmp, Jt, W->C, 9, 10, 10, lane);
-  double* Pm = W->T_dy;
+  double* Pm = W->t3;
   wmm(Pm, tmp, Jt, 9, 10, 9, lane, true);
   // inverse by Gauss-Jordan with partial pivoting (Eigen .inverse()), lane 0
-  double* inv = W->tot_dy;  // 81
+  double* inv = W->A;  // 81
   __shared__ int singular[kWtWarps];
   if (lane == 0) {
     double M[9][18];
