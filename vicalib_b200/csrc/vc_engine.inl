@@ -67,6 +67,7 @@ static void launch_eval_cam(vcgpu_handle* h, const EvalArgs& a, int model, int n
 }
 
 static int eval_reproj(vcgpu_handle* h, int which, bool jac, bool apply_loss, const double* mask_dev) {
+  VC_TRY(ensure_rJ(h));
   const DevProblem& dp = h->dp;
   const int64_t n = h->n_obs;
   int part = 0;
@@ -77,11 +78,8 @@ static int eval_reproj(vcgpu_handle* h, int which, bool jac, bool apply_loss, co
     a.state[0] = h->d_state[0]; a.state[1] = h->d_state[1]; a.ctl = h->d_ctl; a.which = which;
     a.cam_off = dp.off_cam + kCamStateStride * c;
     a.frame = h->d_obs_frame + ci.obs_start;
-    a.pwx = h->d_obs + ci.obs_start;
-    a.pwy = h->d_obs + n + ci.obs_start;
-    a.pwz = h->d_obs + 2 * n + ci.obs_start;
-    a.pcu = h->d_obs + 3 * n + ci.obs_start;
-    a.pcv = h->d_obs + 4 * n + ci.obs_start;
+    a.pw = h->d_pw + 3 * static_cast<int64_t>(ci.obs_start);
+    a.pc = h->d_pc + 2 * static_cast<int64_t>(ci.obs_start);
     a.mask = mask_dev + ci.goff;
     a.r0 = h->d_r + ci.obs_start;
     a.r1 = h->d_r + n + ci.obs_start;
@@ -121,7 +119,7 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     fa.dp = vdp; fa.ctl = h->d_ctl; fa.which = which;
     fa.state[0] = h->d_state[0]; fa.state[1] = h->d_state[1];
     fa.grp_start = h->d_grp_start; fa.grp_count = h->d_grp_count; fa.group_of = h->d_group_of;
-    fa.obs = h->d_obs; fa.n_obs = h->n_obs; fa.mask = h->d_mask;
+    fa.pw = h->d_pw; fa.pc = h->d_pc; fa.n_obs = h->n_obs; fa.mask = h->d_mask;
     fa.out[0] = h->blk[0]; fa.out[1] = h->blk[1]; fa.Cg = h->d_Cg; fa.cost_part = h->d_cost_part;
     // the trial-point launch also performs the back-substitution / x (+) delta for its frame
     fa.apply_update = (with_step && kFuseUpdate) ? 1 : 0;

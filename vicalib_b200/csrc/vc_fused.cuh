@@ -27,7 +27,7 @@ struct FusedArgs {
   int which;
   const double* state[2];
   const int32_t *grp_start, *grp_count, *group_of;
-  const double* obs;   // SoA [5][n_obs]
+  const double *pw, *pc;  // AoS [n_obs][3], [n_obs][2]
   int64_t n_obs;
   const double* mask;  // [G]
   Blocks out[2];
@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(kFusedThreads) fused_build_kernel(FusedArgs a)
       __syncthreads();              // previous pass is done with the tile
       if (tid < m) {
         const int64_t i = start + ch + tid;
-        const V3 pw{a.obs[i], a.obs[a.n_obs + i], a.obs[2 * a.n_obs + i]};
-        const double pcu = a.obs[3 * a.n_obs + i], pcv = a.obs[4 * a.n_obs + i];
+        const V3 pw{a.pw[3 * i], a.pw[3 * i + 1], a.pw[3 * i + 2]};
+        const double pcu = a.pc[2 * i], pcv = a.pc[2 * i + 1];
         switch (ci.model) {
           case kLinear: cost += eval_obs_to_tile<kLinear>(T, cam, mask, pw, pcu, pcv, a.dp.visual_mult, tile, tid, kFusedChunk + tid); break;
           case kFov: cost += eval_obs_to_tile<kFov>(T, cam, mask, pw, pcu, pcv, a.dp.visual_mult, tile, tid, kFusedChunk + tid); break;

@@ -49,7 +49,7 @@ static int imu_prepare(vcgpu_handle* h) {
     avg = (avg * i + dt) / (i + 1);
   }
   VC_TRY(dev_alloc(h, &h->d_imu, buf.size()));
-  CUDA_TRY(h, cudaMemcpy(h->d_imu, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_imu, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->n_imu = n;
   d->buf.d = h->d_imu;
   d->buf.n = n;
@@ -57,18 +57,18 @@ static int imu_prepare(vcgpu_handle* h) {
   d->buf.end_time = n ? h->h_imu_t.back() : -1.0;
   d->buf.average_dt = avg;
   VC_TRY(dev_alloc(h, &d->ftime, nf));
-  CUDA_TRY(h, cudaMemcpy(d->ftime, h->h_time.data(), nf * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpyAsync(d->ftime, h->h_time.data(), nf * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   // weights start at 500*I (vicalibrator.h:616)
   std::vector<double> w(static_cast<size_t>(ni) * 81, 0.0);
   for (int k = 0; k < ni; ++k)
     for (int i = 0; i < 9; ++i) w[static_cast<size_t>(k) * 81 + i * 10] = 500.0;
   VC_TRY(dev_alloc(h, &h->d_wsqrt, w.size()));
-  CUDA_TRY(h, cudaMemcpy(h->d_wsqrt, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_wsqrt, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   VC_TRY(dev_alloc(h, &h->d_imu_r, static_cast<size_t>(ni) * 9));
   VC_TRY(dev_alloc(h, &h->d_imu_J, static_cast<size_t>(ni) * 297));
   VC_TRY(dev_alloc(h, &d->cost, ni));
   VC_TRY(dev_alloc(h, &d->Cg, static_cast<size_t>(nf) * kImuCgStride));
-  CUDA_TRY(h, cudaMemset(d->Cg, 0, static_cast<size_t>(nf) * kImuCgStride * sizeof(double)));
+  CUDA_TRY(h, cudaMemsetAsync(d->Cg, 0, static_cast<size_t>(nf) * kImuCgStride * sizeof(double), h->stream));
   // chain levels
   const size_t w_cols = 2 * FD + G + 1;
   // level sizes; a sharded rank reduces its chain to its first frame (+ the ghost) — the separators

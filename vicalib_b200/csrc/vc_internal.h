@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <new>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -73,6 +74,22 @@ __host__ __device__ inline double lm_damp(double diag, double scale, double radi
 
 }  // namespace vc
 
+// std::vector whose storage is page-locked, so uploads are true asynchronous DMA (no staging copy)
+template <class T>
+struct PinnedAlloc {
+  typedef T value_type;
+  PinnedAlloc() {}
+  template <class U> PinnedAlloc(const PinnedAlloc<U>&) {}
+  T* allocate(size_t n) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, n * sizeof(T)) != cudaSuccess) throw std::bad_alloc();
+    return static_cast<T*>(p);
+  }
+  void deallocate(T* p, size_t) { cudaFreeHost(p); }
+  template <class U> bool operator==(const PinnedAlloc<U>&) const { return true; }
+  template <class U> bool operator!=(const PinnedAlloc<U>&) const { return false; }
+};
+
 struct vcgpu_handle {
   std::string err;
   int device = 0;
@@ -95,8 +112,10 @@ struct vcgpu_handle {
   int64_t n_obs_all = 0;  // as given by the caller
   std::vector<int32_t> h_model;
   std::vector<double> h_intr, h_qck, h_pck, h_T, h_v, h_time;
-  std::vector<int32_t> h_obs_frame, h_obs_cam;
-  std::vector<double> h_pw, h_pc;
+  std::vector<int32_t, PinnedAlloc<int32_t>> h_obs_frame, h_obs_cam;
+  std::vector<double, PinnedAlloc<double>> h_pw, h_pc;          // caller order, AoS [n][3] / [n][2]
+  std::vector<int32_t, PinnedAlloc<int32_t>> h_stage_frame;     // (camera, frame)-sorted staging, used only when
+  std::vector<double, PinnedAlloc<double>> h_stage_pw, h_stage_pc;  // the caller's order is not already sorted
   std::vector<uint8_t> h_active;
   std::vector<double> h_imu_t, h_imu_w, h_imu_a;
   double sigma_g = 5.3088444e-5, sigma_a = 0.001883649;
@@ -110,19 +129,22 @@ struct vcgpu_handle {
   bool state_dirty = true;  // host state changed: re-upload
   vc::DevProblem dp;
   int64_t n_obs = 0;               // active observations (sorted order)
-  std::vector<int64_t> perm;       // sorted index -> caller index
+  std::vector<int64_t> perm;       // sorted index -> caller index (empty when perm_identity)
+  bool perm_identity = false;      // the caller's observations were already sorted by (camera, frame)
   int n_groups = 0;
   int cur = 0;                     // which of the double buffers holds the accepted point
   bool blocks_valid = false;
 
   // ---- device memory
   double* d_state[2] = {nullptr, nullptr};
-  double* d_obs = nullptr;        // SoA [5][n_obs]: pw.x pw.y pw.z pc.u pc.v
+  double* d_pw = nullptr;         // [n_obs][3] grid-corner positions, sorted by (camera, frame)
+  double* d_pc = nullptr;         // [n_obs][2] detected pixel
   int32_t* d_obs_frame = nullptr;
   int32_t *d_grp_start = nullptr, *d_grp_count = nullptr, *d_group_of = nullptr;
   double* d_mask = nullptr;       // [G] 0/1 per global tangent column
   double* d_r = nullptr;          // [2][n_obs] loss-corrected residuals
-  double* d_J = nullptr;          // per camera: [2*(12+K)][n_obs_cam] column SoA, loss-corrected
+  double* d_J = nullptr;          // per camera: [2*(12+K)][n_obs_cam] column SoA, loss-corrected (two-pass path / hooks only)
+  int64_t j_doubles = 0;
   double* d_cost_part = nullptr;  // per eval block partial costs
   int n_cost_part = 0;
   double* d_Cg = nullptr;         // [n_groups][kCgStride]

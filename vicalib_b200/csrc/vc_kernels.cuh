@@ -39,7 +39,7 @@ struct EvalArgs {
   int which;
   int64_t cam_off;         // offset of this camera's 17 state doubles
   const int32_t* frame;    // per observation (camera-local arrays from here on)
-  const double *pwx, *pwy, *pwz, *pcu, *pcv;
+  const double *pw, *pc;   // AoS [n][3], [n][2]
   const double* mask;      // 6+K column mask (w_ck, p_ck, intr)
   double *r0, *r1;
   double* J;               // column c at J + c*n
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) eval_reproj_kernel(EvalArgs a) {
     const double* T = state + 7 * static_cast<int64_t>(a.frame[i]);
     const Q4 q{T[0], T[1], T[2], T[3]};
     const V3 t{T[4], T[5], T[6]};
-    const V3 pw{a.pwx[i], a.pwy[i], a.pwz[i]};
+    const V3 pw{a.pw[3 * i], a.pw[3 * i + 1], a.pw[3 * i + 2]};
     const V3 pk = qrot(qconj(q), pw - t);  // T_wk^-1 * p_w
     const Q4 qc{cam[0], cam[1], cam[2], cam[3]};
     double R[9];
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) eval_reproj_kernel(EvalArgs a) {
     const V3 pc = mat_mul(R, pk) + V3{cam[4], cam[5], cam[6]};
     double z[2], dzp[6], dzi[2 * K];
     Cam<MODEL>::project(pc, cam + 7, z, JAC ? dzp : nullptr, JAC ? dzi : nullptr);
-    double r0 = z[0] - a.pcu[i], r1 = z[1] - a.pcv[i];
+    double r0 = z[0] - a.pc[2 * i], r1 = z[1] - a.pc[2 * i + 1];
     const double s = r0 * r0 + r1 * r1;
     double sc = 1.0;
     if (a.apply_loss) {

@@ -158,7 +158,7 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   dev_free(&h->d_state[0]); dev_free(&h->d_state[1]);
-  dev_free(&h->d_obs); dev_free(&h->d_obs_frame);
+  dev_free(&h->d_pw); dev_free(&h->d_pc); dev_free(&h->d_obs_frame);
   dev_free(&h->d_grp_start); dev_free(&h->d_grp_count); dev_free(&h->d_group_of);
   dev_free(&h->d_mask); dev_free(&h->d_r); dev_free(&h->d_J); dev_free(&h->d_cost_part);
   dev_free(&h->d_Cg); dev_free(&h->d_Cpart);
@@ -219,6 +219,7 @@ extern "C" int vcgpu_set_observations(vcgpu_handle* h, int64_t n, const int32_t*
                                       const double* p_w, const double* p_c) {
   if (!h || n < 0 || (n > 0 && (!frame_id || !cam_id || !p_w || !p_c)))
     return h ? fail(h, VCGPU_ERR_INVALID, "set_observations: bad arguments") : VCGPU_ERR_INVALID;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // an earlier upload may still be reading the page-locked copies
   h->n_obs_all = n;
   h->h_obs_frame.assign(frame_id, frame_id + n);
   h->h_obs_cam.assign(cam_id, cam_id + n);
@@ -357,6 +358,15 @@ static void write_mirrors(vcgpu_handle* h) {
   if (h->mirror[8]) *h->mirror[8] = h->h_ts;
 }
 
+static inline int64_t perm_at(const vcgpu_handle* h, int64_t k) { return h->perm_identity ? k : h->perm[k]; }
+
+// residual / Jacobian buffers of the two-pass (materialising) path and the inspection hooks
+static int ensure_rJ(vcgpu_handle* h) {
+  VC_TRY(dev_alloc(h, &h->d_r, 2 * static_cast<size_t>(std::max<int64_t>(h->n_obs, 1))));
+  VC_TRY(dev_alloc(h, &h->d_J, static_cast<size_t>(std::max<int64_t>(h->j_doubles, 1))));
+  return VCGPU_OK;
+}
+
 static int prepare(vcgpu_handle* h) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (h->n_cams <= 0 || h->n_frames <= 0) return fail(h, VCGPU_ERR_INVALID, "cameras and frames must be set first");
@@ -366,18 +376,27 @@ static int prepare(vcgpu_handle* h) {
     dp.n_cams = h->n_cams;
     dp.n_frames = h->n_frames;
     const int nf = h->n_frames, nc = h->n_cams;
-    // validate + sort active observations by (camera, frame), stable in caller order
-    for (int64_t i = 0; i < h->n_obs_all; ++i) {
-      if (h->h_obs_cam[i] < 0 || h->h_obs_cam[i] >= nc) return fail(h, VCGPU_ERR_INVALID, "observation with unknown camera id");  // vicalibrator.h:396
-      if (h->h_obs_frame[i] < 0 || h->h_obs_frame[i] >= nf) return fail(h, VCGPU_ERR_INVALID, "observation with unknown frame id");
-    }
+    // one pass: validate ids, count per (camera, frame), detect an already-sorted caller order
     std::vector<int64_t> count(static_cast<size_t>(nc) * nf + 1, 0);
-    for (int64_t i = 0; i < h->n_obs_all; ++i)
-      if (h->h_active[i]) ++count[static_cast<size_t>(h->h_obs_cam[i]) * nf + h->h_obs_frame[i] + 1];
+    bool sorted = true;
+    int64_t prev_key = -1, n_act = 0;
+    for (int64_t i = 0; i < h->n_obs_all; ++i) {
+      const int32_t c = h->h_obs_cam[i], f = h->h_obs_frame[i];
+      if (c < 0 || c >= nc) return fail(h, VCGPU_ERR_INVALID, "observation with unknown camera id");  // vicalibrator.h:396
+      if (f < 0 || f >= nf) return fail(h, VCGPU_ERR_INVALID, "observation with unknown frame id");
+      if (!h->h_active[i]) continue;
+      const int64_t key = static_cast<int64_t>(c) * nf + f;
+      sorted &= key >= prev_key;
+      prev_key = key;
+      ++count[key + 1];
+      ++n_act;
+    }
     for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
-    h->n_obs = count.back();
-    h->perm.assign(h->n_obs, 0);
-    {
+    h->n_obs = n_act;
+    h->perm_identity = sorted && n_act == h->n_obs_all;
+    h->perm.clear();
+    if (!h->perm_identity) {  // stable counting sort by (camera, frame)
+      h->perm.assign(h->n_obs, 0);
       std::vector<int64_t> pos(count.begin(), count.end() - 1);
       for (int64_t i = 0; i < h->n_obs_all; ++i)
         if (h->h_active[i]) h->perm[pos[static_cast<size_t>(h->h_obs_cam[i]) * nf + h->h_obs_frame[i]]++] = i;
@@ -423,45 +442,53 @@ static int prepare(vcgpu_handle* h) {
     dp.state_size = dp.off_imu + kImuStateSize;
     const int fd = dp.fd, G = dp.G;
     const int64_t n = h->n_obs;
-    // sorted observation arrays
-    std::vector<double> obs(5 * std::max<int64_t>(n, 1));
-    std::vector<int32_t> fr(std::max<int64_t>(n, 1));
-    for (int64_t k = 0; k < n; ++k) {
-      const int64_t i = h->perm[k];
-      obs[k] = h->h_pw[3 * i]; obs[n + k] = h->h_pw[3 * i + 1]; obs[2 * n + k] = h->h_pw[3 * i + 2];
-      obs[3 * n + k] = h->h_pc[2 * i]; obs[4 * n + k] = h->h_pc[2 * i + 1];
-      fr[k] = h->h_obs_frame[i];
+    // observations to the device: straight DMA from the page-locked caller-order copies when they are
+    // already sorted, else through a sorted page-locked staging copy
+    VC_TRY(dev_alloc(h, &h->d_pw, 3 * static_cast<size_t>(n)));
+    VC_TRY(dev_alloc(h, &h->d_pc, 2 * static_cast<size_t>(n)));
+    VC_TRY(dev_alloc(h, &h->d_obs_frame, static_cast<size_t>(n)));
+    if (n > 0) {
+      const double *src_pw = h->h_pw.data(), *src_pc = h->h_pc.data();
+      const int32_t* src_fr = h->h_obs_frame.data();
+      if (!h->perm_identity) {
+        h->h_stage_pw.resize(3 * n); h->h_stage_pc.resize(2 * n); h->h_stage_frame.resize(n);
+        for (int64_t k = 0; k < n; ++k) {
+          const int64_t i = h->perm[k];
+          h->h_stage_pw[3 * k] = h->h_pw[3 * i]; h->h_stage_pw[3 * k + 1] = h->h_pw[3 * i + 1]; h->h_stage_pw[3 * k + 2] = h->h_pw[3 * i + 2];
+          h->h_stage_pc[2 * k] = h->h_pc[2 * i]; h->h_stage_pc[2 * k + 1] = h->h_pc[2 * i + 1];
+          h->h_stage_frame[k] = h->h_obs_frame[i];
+        }
+        src_pw = h->h_stage_pw.data(); src_pc = h->h_stage_pc.data(); src_fr = h->h_stage_frame.data();
+      }
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_pw, src_pw, 3 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_pc, src_pc, 2 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_obs_frame, src_fr, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     }
-    VC_TRY(dev_alloc(h, &h->d_obs, obs.size()));
-    VC_TRY(dev_alloc(h, &h->d_obs_frame, fr.size()));
     VC_TRY(dev_alloc(h, &h->d_grp_start, grp_start.size()));
     VC_TRY(dev_alloc(h, &h->d_grp_count, grp_count.size()));
     VC_TRY(dev_alloc(h, &h->d_group_of, group_of.size()));
-    CUDA_TRY(h, cudaMemcpy(h->d_obs, obs.data(), obs.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(h, cudaMemcpy(h->d_obs_frame, fr.data(), fr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (!grp_start.empty()) {
-      CUDA_TRY(h, cudaMemcpy(h->d_grp_start, grp_start.data(), grp_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-      CUDA_TRY(h, cudaMemcpy(h->d_grp_count, grp_count.data(), grp_count.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_start, grp_start.data(), grp_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_count, grp_count.data(), grp_count.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     }
-    CUDA_TRY(h, cudaMemcpy(h->d_group_of, group_of.data(), group_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_group_of, group_of.data(), group_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     // work buffers
     VC_TRY(dev_alloc(h, &h->d_state[0], dp.state_size));
     VC_TRY(dev_alloc(h, &h->d_state[1], dp.state_size));
     VC_TRY(dev_alloc(h, &h->d_mask, G));
-    VC_TRY(dev_alloc(h, &h->d_r, 2 * n));
-    VC_TRY(dev_alloc(h, &h->d_J, joff));
+    h->j_doubles = joff;  // residual / Jacobian buffers of the two-pass path are allocated on first use (ensure_rJ)
     h->n_cost_part = 0;
     for (int c = 0; c < nc; ++c) h->n_cost_part += (dp.cams[c].n_obs + 255) / 256;
     VC_TRY(dev_alloc(h, &h->d_cost_part, std::max(h->n_cost_part, nf)));
     VC_TRY(dev_alloc(h, &h->d_Cg, static_cast<size_t>(h->n_groups) * kCgStride));
-    CUDA_TRY(h, cudaMemset(h->d_Cg, 0, std::max<size_t>(1, static_cast<size_t>(h->n_groups) * kCgStride) * sizeof(double)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_Cg, 0, std::max<size_t>(1, static_cast<size_t>(h->n_groups) * kCgStride) * sizeof(double), h->stream));
     const size_t NS = static_cast<size_t>(G) * G + G;
     VC_TRY(dev_alloc(h, &h->d_Cpart, kReduceBlocks * NS));
     const size_t blk_sz = 2 * static_cast<size_t>(nf) * fd * fd + static_cast<size_t>(nf) * fd * G +
                           static_cast<size_t>(nf) * fd + NS + 1;
     for (int b = 0; b < 2; ++b) {
       VC_TRY(dev_alloc(h, &h->d_blk_mem[b], blk_sz));
-      CUDA_TRY(h, cudaMemset(h->d_blk_mem[b], 0, blk_sz * sizeof(double)));
+      CUDA_TRY(h, cudaMemsetAsync(h->d_blk_mem[b], 0, blk_sz * sizeof(double), h->stream));
       double* p = h->d_blk_mem[b];
       h->blk[b].B = p; p += static_cast<size_t>(nf) * fd * fd;
       h->blk[b].U = p; p += static_cast<size_t>(nf) * fd * fd;
@@ -487,9 +514,9 @@ static int prepare(vcgpu_handle* h) {
       VC_TRY(dev_alloc(h, &h->d_dense, N * N + N));
     }
     VC_TRY(dev_alloc(h, &h->d_counter, 4));
-    CUDA_TRY(h, cudaMemset(h->d_counter, 0, 4 * sizeof(unsigned)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned), h->stream));
     VC_TRY(dev_alloc(h, &h->d_scalars, kScCount));
-    CUDA_TRY(h, cudaMemset(h->d_scalars, 0, kScCount * sizeof(double)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_scalars, 0, kScCount * sizeof(double), h->stream));
     VC_TRY(imu_prepare(h));
     h->cur = 0;
     h->dirty = false;
@@ -502,7 +529,7 @@ static int prepare(vcgpu_handle* h) {
     dp.imu_mult = h->flags.imu_mult;
     std::vector<double> mask;
     fill_mask(h, &mask);
-    CUDA_TRY(h, cudaMemcpy(h->d_mask, mask.data(), mask.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_mask, mask.data(), mask.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
   if (h->state_dirty) VC_TRY(upload_state(h));
   return VCGPU_OK;
@@ -546,7 +573,7 @@ extern "C" int vcgpu_evaluate(vcgpu_handle* h, int cam, double* cost, double* re
   const int c0 = cam < 0 ? 0 : cam, c1 = cam < 0 ? dp.n_cams : cam + 1;
   std::vector<std::pair<int64_t, int64_t>> idx;  // (caller index, sorted index)
   for (int c = c0; c < c1; ++c)
-    for (int64_t k = dp.cams[c].obs_start; k < dp.cams[c].obs_start + dp.cams[c].n_obs; ++k) idx.emplace_back(h->perm[k], k);
+    for (int64_t k = dp.cams[c].obs_start; k < dp.cams[c].obs_start + dp.cams[c].n_obs; ++k) idx.emplace_back(perm_at(h, k), k);
   std::sort(idx.begin(), idx.end());
   double s = 0;
   int64_t o = 0;
@@ -575,7 +602,7 @@ extern "C" int vcgpu_remove_outliers(vcgpu_handle* h, const double* rmse, double
   for (int c = 0; c < dp.n_cams; ++c)
     for (int64_t k = dp.cams[c].obs_start; k < dp.cams[c].obs_start + dp.cams[c].n_obs; ++k) {
       const double err = std::sqrt(r[k] * r[k] + r[n + k] * r[n + k]);
-      if (err > threshold * rmse[c]) { h->h_active[h->perm[k]] = 0; ++removed; }  // vicalibrator.h:890-893
+      if (err > threshold * rmse[c]) { h->h_active[perm_at(h, k)] = 0; ++removed; }  // vicalibrator.h:890-893
     }
   if (removed) h->dirty = true;
   if (n_removed) *n_removed = removed;
@@ -639,8 +666,8 @@ extern "C" int vcgpu_eval_reproj(vcgpu_handle* h, double* r_out, double* J_out) 
   cudaFree(ones);
   h->blocks_valid = false;
   for (int64_t k = 0; k < n; ++k) {
-    r_out[2 * h->perm[k]] = r[k];
-    r_out[2 * h->perm[k] + 1] = r[n + k];
+    r_out[2 * perm_at(h, k)] = r[k];
+    r_out[2 * perm_at(h, k) + 1] = r[n + k];
   }
   if (J_out) {
     for (int c = 0; c < dp.n_cams; ++c) {
@@ -649,7 +676,7 @@ extern "C" int vcgpu_eval_reproj(vcgpu_handle* h, double* r_out, double* J_out) 
       std::vector<double> J(static_cast<size_t>(2 * NT) * std::max(ci.n_obs, 1));
       CUDA_TRY(h, cudaMemcpy(J.data(), h->d_J + ci.joff, static_cast<size_t>(2 * NT) * ci.n_obs * sizeof(double), cudaMemcpyDeviceToHost));
       for (int li = 0; li < ci.n_obs; ++li) {
-        double* o = J_out + 44 * h->perm[ci.obs_start + li];
+        double* o = J_out + 44 * perm_at(h, ci.obs_start + li);
         std::memset(o, 0, 44 * sizeof(double));
         for (int row = 0; row < 2; ++row)
           for (int k = 0; k < NT; ++k) o[row * 22 + k] = J[static_cast<size_t>(row * NT + k) * ci.n_obs + li];
