@@ -191,6 +191,9 @@ enum {
   VCGPU_STAGE_IMU_WEIGHTS = 9,  /* UpdateImuWeights */
   VCGPU_STAGE_COUNT = 16
 };
+/* Measured FP64 throughput of `device` in TFLOP/s (FMA = 2 flop): independent DFMA chains and independent
+ * mma.sync.m8n8k4.f64 chains on every SM.  The roofline denominators for the FP64-bound kernels. */
+int vcgpu_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
 int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2);
 int vcgpu_get_stage_times(vcgpu_handle* h, double ms_total[VCGPU_STAGE_COUNT], int64_t launches[VCGPU_STAGE_COUNT]);
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "vcgpu_get_obs_active", "vcgpu_update_imu_weights", "vcgpu_get_imu_weights", "vcgpu_set_imu_weights",
     "vcgpu_get_state", "vcgpu_num_residuals", "vcgpu_frame_dim", "vcgpu_num_globals", "vcgpu_eval_reproj",
     "vcgpu_eval_imu", "vcgpu_normal_equations", "vcgpu_solve_arrow", "vcgpu_comm_unique_id", "vcgpu_comm_init",
-    "vcgpu_set_profiling", "vcgpu_get_stage_times",
+    "vcgpu_set_profiling", "vcgpu_get_stage_times", "vcgpu_fp64_peak",
 ]
 
 
@@ -276,6 +276,12 @@ class Calibrator:
 
     def set_profiling(self, profile=True, flush_l2=False):
         self._chk(self.L.vcgpu_set_profiling(self.h, C.c_int(int(profile)), C.c_int(int(flush_l2))))
+
+    def fp64_peak(self, device=0):
+        """Measured FP64 throughput (TFLOP/s): (vector DFMA, tensor DMMA m8n8k4)."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        self._chk(self.L.vcgpu_fp64_peak(C.c_int(device), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def stage_times(self):
         ms = np.zeros(16)

@@ -19,6 +19,7 @@
 #include "vc_imu.cuh"
 #include "vc_chain.cuh"
 #include "vc_fused.cuh"
+#include "vc_peak.cuh"
 #include "vc_imu_weights.cuh"
 
 using namespace vc;
@@ -108,6 +109,37 @@ extern "C" int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2) {
 extern "C" int vcgpu_get_stage_times(vcgpu_handle* h, double ms_total[VCGPU_STAGE_COUNT], int64_t launches[VCGPU_STAGE_COUNT]) {
   if (!h || !ms_total || !launches) return VCGPU_ERR_INVALID;
   for (int s = 0; s < VCGPU_STAGE_COUNT; ++s) { ms_total[s] = h->st_ms[s]; launches[s] = h->st_n[s]; }
+  return VCGPU_OK;
+}
+
+// FP64 throughput of this device (vector DFMA and tensor DMMA), for the roofline of the FP64-bound kernels
+extern "C" int vcgpu_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops) {
+  if (!dfma_tflops || !dmma_tflops) return VCGPU_ERR_INVALID;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VCGPU_ERR_CUDA;
+  double* out = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(&out, sizeof(double)) != cudaSuccess) return VCGPU_ERR_CUDA;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int ctas = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double best[2] = {0.0, 0.0};
+  for (int which = 0; which < 2; ++which)
+    for (int rep = 0; rep < 5; ++rep) {
+      cudaEventRecord(e0);
+      if (which == 0) vc::dfma_peak_kernel<<<ctas, threads>>>(out, iters, 1.0);
+      else vc::dmma_peak_kernel<<<ctas, threads>>>(out, iters, 1.0);
+      cudaEventRecord(e1);
+      if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return VCGPU_ERR_CUDA; }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      // DFMA: 8 chains x 2 flop per thread-iteration; DMMA: 8 x (8*8*4*2 flop) per warp-iteration
+      const double flop = which == 0 ? 16.0 * iters * static_cast<double>(ctas) * threads
+                                     : 8.0 * 512.0 * iters * static_cast<double>(ctas) * (threads / 32);
+      if (rep > 0) best[which] = std::max(best[which], flop / (ms * 1e-3) / 1e12);
+    }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *dfma_tflops = best[0];
+  *dmma_tflops = best[1];
   return VCGPU_OK;
 }
 
