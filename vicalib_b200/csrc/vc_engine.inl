@@ -10,11 +10,8 @@
 // Multi-GPU: all_reduce_dense() after the partial sums and all_reduce_eval() before decide are the
 // only cross-rank points (frames are sharded; every rank then solves the same small dense system).
 
-// Measured on B200 (config 2): folding the back-substitution into the fused kernel serialises ~2 us
-// of single-thread SE3 work in front of every CTA wave (+25 us/iteration), and summing the Schur
-// partials inside the single-CTA dense solve is latency-bound (+18 us); both stay as separate,
-// fully parallel launches.
-constexpr bool kFuseUpdate = false;
+// Measured on B200 (config 2): summing the Schur partials inside the single-CTA dense solve is
+// latency-bound (+18 us); it stays a separate, fully parallel launch.
 constexpr bool kSumInSolve = false;
 
 // ------------------------------------------------------------------ multi-GPU all-reduce
@@ -121,12 +118,7 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     fa.grp_start = h->d_grp_start; fa.grp_count = h->d_grp_count; fa.group_of = h->d_group_of;
     fa.pw = h->d_pw; fa.pc = h->d_pc; fa.n_obs = h->n_obs; fa.mask = h->d_mask;
     fa.out[0] = h->blk[0]; fa.out[1] = h->blk[1]; fa.Cg = h->d_Cg; fa.cost_part = h->d_cost_part;
-    // the trial-point launch also performs the back-substitution / x (+) delta for its frame
-    fa.apply_update = (with_step && kFuseUpdate) ? 1 : 0;
-    fa.scale = h->d_scale; fa.D2x = D2x; fa.X = dp.inertial ? nullptr : h->d_X; fa.delta = h->d_delta;
-    fa.states_rw[0] = h->d_state[0]; fa.states_rw[1] = h->d_state[1]; fa.step_part = h->d_red;
-    const size_t fsm = (static_cast<size_t>(kFusedCols) * kFusedLd + kFusedWarps * 384 + 9 * 9 + 9 + kFusedWarps + 8 +
-                        kMaxCams * kCamStateStride) * sizeof(double);
+    const size_t fsm = kFusedSmemDoubles * sizeof(double);
     static bool attr_done = false;
     if (!attr_done) {
       CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
@@ -171,8 +163,7 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     ra.imu_cost_part = imu_cost_part(h); ra.n_imu_cost_part = n_imu_cost;
     ra.step_part = with_step ? h->d_red : nullptr;
     // the last step_part slot is the globals' share: counted once (rank 0) in a sharded run
-    ra.n_step_part = ((fused && kFuseUpdate) ? dp.n_frames : (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps) +
-                     (h->rank == 0 ? 1 : 0);
+    ra.n_step_part = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps + (h->rank == 0 ? 1 : 0);
     ra.n_frames_fd = dp.n_frames * dp.fd;
     ra.out[0] = h->blk[0]; ra.out[1] = h->blk[1]; ra.scalars = h->d_scalars; ra.counter = h->d_counter;
     reduce_finalize_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
@@ -297,7 +288,7 @@ static int num_residuals(const vcgpu_handle* h) {
 
 // one trust-region iteration, enqueued (no host wait)
 static int enqueue_iteration(vcgpu_handle* h, bool weights) {
-  VC_TRY(solve_and_update(h, nullptr, kFuseUpdate));
+  VC_TRY(solve_and_update(h, nullptr, false));
   VC_TRY(evaluate_into(h, 1, true, 1));
   if (weights) VC_TRY(imu_update_weights(h));  // the reference's iteration callback (vicalibrator.h:691)
   return VCGPU_OK;
