@@ -175,7 +175,10 @@ int vcgpu_normal_equations(vcgpu_handle* h, double* B, double* U, double* E, dou
 int vcgpu_solve_arrow(vcgpu_handle* h, const double* scale, const double* D2, double* x);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------
- * profile: bracket every kernel stage of the solve loop with CUDA events on the launching stream
+ * profile (bit mask): 1 = bracket every kernel stage of the multi-launch engine with CUDA events on the
+ *          launching stream; 2 = two-pass path that materialises the Jacobian in HBM; 4 = multi-launch engine
+ *          even where the persistent kernel applies; 8 = persistent kernel records per-phase device clocks
+ *          (read back through vcgpu_get_stage_times)
  * flush_l2: overwrite a 256 MiB scratch buffer before every iteration and time iterations
  *           individually, so no iteration starts with its inputs resident in the 126 MB L2 */
 enum {
@@ -189,6 +192,7 @@ enum {
   VCGPU_STAGE_FINALIZE = 7,     /* level 2 + cost + gradient norms */
   VCGPU_STAGE_IMU_EVAL = 8,     /* IMU residual + Jacobian */
   VCGPU_STAGE_IMU_WEIGHTS = 9,  /* UpdateImuWeights */
+  VCGPU_STAGE_GRID_SYNC = 10,   /* persistent kernel: the two grid barriers of an iteration */
   VCGPU_STAGE_COUNT = 16
 };
 /* Measured FP64 throughput of `device` in TFLOP/s (FMA = 2 flop): independent DFMA chains and independent

@@ -286,8 +286,45 @@ static int num_residuals(const vcgpu_handle* h) {
   return static_cast<int>(n);
 }
 
+// ------------------------------------------------------------------ persistent vision kernel
+static bool mega_applies(const vcgpu_handle* h) {
+  return h->mega_teams > 0 && !h->dp.inertial && h->nranks == 1 && !h->materialize && !h->profiling && !h->multi_launch &&
+         h->flags.visual && h->n_obs > 0;
+}
+// up to n_iters trust-region iterations in one cooperative launch (vc_mega.cuh)
+static int mega_launch(vcgpu_handle* h, int n_iters) {
+  const DevProblem& dp = h->dp;
+  MegaArgs ma;
+  ma.dp = dp; ma.ctl = h->d_ctl;
+  ma.state[0] = h->d_state[0]; ma.state[1] = h->d_state[1];
+  ma.blk[0] = h->blk[0]; ma.blk[1] = h->blk[1];
+  ma.grp_start = h->d_grp_start; ma.grp_count = h->d_grp_count; ma.group_of = h->d_group_of;
+  ma.pw = h->d_pw; ma.pc = h->d_pc; ma.mask = h->d_mask; ma.scale = h->d_scale; ma.X = h->d_X;
+  ma.partS = h->d_partS; ma.partC = h->d_partC; ma.totS = h->d_totS; ma.totC = h->d_totC; ma.delta = h->d_delta; ma.scalars = h->d_scalars;
+  ma.n_iters = n_iters; ma.n_teams = h->mega_teams;
+  ma.prof = h->phase_clocks ? h->d_prof : nullptr;
+  void* args[] = {&ma};
+  const size_t smem = mega_smem_doubles(dp.G, h->mega_teams) * sizeof(double);
+  CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lm_mega_kernel), dim3(h->mega_grid), dim3(h->mega_teams * kTeamThreads),
+                                          args, smem, h->stream));
+  ++h->launches;
+  return VCGPU_OK;
+}
+// fold the persistent kernel's phase clocks into the stage times (call after a stream synchronise)
+static int mega_collect_clocks(vcgpu_handle* h, int iters) {
+  if (!h->phase_clocks || !h->d_prof) return VCGPU_OK;
+  unsigned long long ns[kProfCount];
+  CUDA_TRY(h, cudaMemcpy(ns, h->d_prof, sizeof ns, cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemset(h->d_prof, 0, sizeof ns));
+  const int map[kProfCount] = {VCGPU_STAGE_FRAME_SOLVE, VCGPU_STAGE_GLOBAL_SOLVE, VCGPU_STAGE_BACKSUB, VCGPU_STAGE_BUILD,
+                               VCGPU_STAGE_FINALIZE, VCGPU_STAGE_GRID_SYNC, VCGPU_STAGE_GRID_SYNC};
+  for (int k = 0; k < kProfCount; ++k) { h->st_ms[map[k]] += ns[k] * 1e-6; h->st_n[map[k]] += iters; }
+  return VCGPU_OK;
+}
+
 // one trust-region iteration, enqueued (no host wait)
 static int enqueue_iteration(vcgpu_handle* h, bool weights) {
+  if (mega_applies(h)) return mega_launch(h, 1);
   VC_TRY(solve_and_update(h, nullptr, false));
   VC_TRY(evaluate_into(h, 1, true, 1));
   if (weights) VC_TRY(imu_update_weights(h));  // the reference's iteration callback (vicalibrator.h:691)
@@ -364,6 +401,10 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
     // free-running: enqueue batches; the device decides, the host only looks at `done` between batches
     const int batch = fixed_iters > 0 ? 32 : 4;
     int queued = 0;
+    if (mega_applies(h)) {  // the whole loop in one launch; the device stops at convergence
+      VC_TRY(mega_launch(h, max_it));
+      queued = max_it;
+    }
     while (queued < max_it) {
       const int n = std::min(batch, max_it - queued);
       for (int k = 0; k < n; ++k) VC_TRY(enqueue_iteration(h, weights));
@@ -389,6 +430,7 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
   sum.final_cost = c.cost;
   sum.device_seconds = (h->flush_l2 ? flushed_ms : ms) * 1e-3;
   sum.kernel_launches = static_cast<int>(h->launches - launches0);
+  VC_TRY(mega_collect_clocks(h, c.iter));
   h->blocks_valid = true;
   VC_TRY(download_state(h));
   write_mirrors(h);

@@ -99,6 +99,8 @@ struct vcgpu_handle {
   std::unordered_map<void*, size_t> capacity;  // bytes held by each dev_alloc()ed pointer slot
   // measurement hooks
   bool profiling = false, flush_l2 = false, materialize = false;
+  bool multi_launch = false;  // force the multi-launch engine (A/B against the persistent kernel)
+  bool phase_clocks = false;  // persistent kernel: per-phase %globaltimer deltas into the stage times
   cudaEvent_t st_ev[VCGPU_STAGE_COUNT][2] = {};
   bool st_used[VCGPU_STAGE_COUNT] = {};
   double st_ms[VCGPU_STAGE_COUNT] = {};
@@ -160,6 +162,13 @@ struct vcgpu_handle {
   double* d_red = nullptr;        // step reductions [n_frames+1][4]
   double* d_red_part = nullptr;   // [kReduceBlocks][8] level-1 scalar partials
   unsigned* d_counter = nullptr;  // last-CTA tickets
+  // persistent vision kernel (vc_mega.cuh)
+  double *d_partS = nullptr, *d_partC = nullptr;  // [grid][G*G+G+8]
+  double *d_totS = nullptr, *d_totC = nullptr;    // [G*G+G+8] grid totals
+  unsigned long long* d_prof = nullptr;
+  int dev_sms = 0, dev_smem_optin = 0;
+  size_t mega_smem_set = 0;
+  int mega_grid = 0, mega_teams = 0;  // 0 teams: does not fit / not supported, use the multi-launch engine
   double* d_scalars = nullptr;    // device scalars (see vcgpu.cu)
   double* h_scalars = nullptr;    // pinned mirror
   vc::Ctl* d_ctl = nullptr;       // device-resident trust-region state

@@ -20,6 +20,7 @@
 #include "vc_chain.cuh"
 #include "vc_fused.cuh"
 #include "vc_peak.cuh"
+#include "vc_mega.cuh"
 #include "vc_imu_weights.cuh"
 
 using namespace vc;
@@ -102,6 +103,8 @@ extern "C" int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2) {
   if (flush_l2 && !h->d_flush) CUDA_TRY(h, cudaMalloc(&h->d_flush, 256u << 20));
   h->profiling = (profile & 1) != 0;
   h->materialize = (profile & 2) != 0;  // bit 1: use the two-pass path that materialises J in HBM
+  h->multi_launch = (profile & 4) != 0; // bit 2: multi-launch engine even where the persistent kernel applies
+  h->phase_clocks = (profile & 8) != 0; // bit 3: persistent kernel records per-phase device clocks
   h->flush_l2 = flush_l2 != 0;
   for (int s = 0; s < VCGPU_STAGE_COUNT; ++s) { h->st_ms[s] = 0; h->st_n[s] = 0; h->st_used[s] = false; }
   return VCGPU_OK;
@@ -197,6 +200,7 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_blk_mem[0]); dev_free(&h->d_blk_mem[1]);
   dev_free(&h->d_scale); dev_free(&h->d_X); dev_free(&h->d_Spart); dev_free(&h->d_delta);
   dev_free(&h->d_red); dev_free(&h->d_scalars); dev_free(&h->d_Ssum); dev_free(&h->d_red_part); dev_free(&h->d_counter);
+  dev_free(&h->d_partS); dev_free(&h->d_partC); dev_free(&h->d_totS); dev_free(&h->d_totC); dev_free(&h->d_prof);
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
   dev_free(&h->d_mg); dev_free(&h->d_sep); dev_free(&h->d_dense);
@@ -399,6 +403,45 @@ static int ensure_rJ(vcgpu_handle* h) {
   return VCGPU_OK;
 }
 
+// persistent vision kernel: pick the team count that fits shared memory, allocate the partial slots
+static int mega_prepare(vcgpu_handle* h) {
+  const DevProblem& dp = h->dp;
+  h->mega_teams = 0;
+  if (dp.inertial || h->nranks > 1) return VCGPU_OK;
+  if (h->dev_sms == 0) {  // device attributes: once per handle
+    int coop = 0, smem_optin = 0, sms = 0;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    h->dev_sms = sms;
+    h->dev_smem_optin = coop ? smem_optin : 0;
+  }
+  if (h->dev_smem_optin == 0) return VCGPU_OK;
+  int teams = vc::kMegaMaxTeams;
+  while (teams > 0 && vc::mega_smem_doubles(dp.G, teams) * sizeof(double) > static_cast<size_t>(h->dev_smem_optin)) --teams;
+  if (teams == 0 || static_cast<size_t>(60) * teams * (dp.G + 1) > static_cast<size_t>(teams) * vc::kTeamDoubles) return VCGPU_OK;
+  const size_t smem = vc::mega_smem_doubles(dp.G, teams) * sizeof(double);
+  if (smem > h->mega_smem_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(vc::lm_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vc::lm_mega_kernel, teams * vc::kTeamThreads, smem));
+    if (per_sm < 1) return VCGPU_OK;
+    h->mega_smem_set = smem;
+  }
+  h->mega_grid = h->dev_sms;
+  h->mega_teams = teams;
+  const size_t PS = static_cast<size_t>(dp.G) * dp.G + dp.G + vc::kMegaPartExtra;
+  VC_TRY(dev_alloc(h, &h->d_partS, h->mega_grid * PS));
+  VC_TRY(dev_alloc(h, &h->d_partC, h->mega_grid * PS));
+  VC_TRY(dev_alloc(h, &h->d_totS, PS));
+  VC_TRY(dev_alloc(h, &h->d_totC, PS));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_partS, 0, h->mega_grid * PS * sizeof(double), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_partC, 0, h->mega_grid * PS * sizeof(double), h->stream));
+  VC_TRY(dev_alloc(h, &h->d_prof, vc::kProfCount));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_prof, 0, vc::kProfCount * sizeof(unsigned long long), h->stream));
+  return VCGPU_OK;
+}
+
 static int prepare(vcgpu_handle* h) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (h->n_cams <= 0 || h->n_frames <= 0) return fail(h, VCGPU_ERR_INVALID, "cameras and frames must be set first");
@@ -549,6 +592,7 @@ static int prepare(vcgpu_handle* h) {
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned), h->stream));
     VC_TRY(dev_alloc(h, &h->d_scalars, kScCount));
     CUDA_TRY(h, cudaMemsetAsync(h->d_scalars, 0, kScCount * sizeof(double), h->stream));
+    VC_TRY(mega_prepare(h));
     VC_TRY(imu_prepare(h));
     h->cur = 0;
     h->dirty = false;
