@@ -288,7 +288,7 @@ static int num_residuals(const vcgpu_handle* h) {
 
 // ------------------------------------------------------------------ persistent vision kernel
 static bool mega_applies(const vcgpu_handle* h) {
-  return h->mega_teams > 0 && !h->dp.inertial && h->nranks == 1 && !h->materialize && !h->profiling && !h->multi_launch &&
+  return h->mega_warps > 0 && !h->dp.inertial && h->nranks == 1 && !h->materialize && !h->profiling && !h->multi_launch &&
          h->flags.visual && h->n_obs > 0;
 }
 // up to n_iters trust-region iterations in one cooperative launch (vc_mega.cuh)
@@ -301,11 +301,11 @@ static int mega_launch(vcgpu_handle* h, int n_iters) {
   ma.grp_start = h->d_grp_start; ma.grp_count = h->d_grp_count; ma.group_of = h->d_group_of;
   ma.pw = h->d_pw; ma.pc = h->d_pc; ma.mask = h->d_mask; ma.scale = h->d_scale; ma.X = h->d_X;
   ma.partS = h->d_partS; ma.partC = h->d_partC; ma.totS = h->d_totS; ma.totC = h->d_totC; ma.delta = h->d_delta; ma.scalars = h->d_scalars;
-  ma.n_iters = n_iters; ma.n_teams = h->mega_teams;
+  ma.n_iters = n_iters; ma.n_warps = h->mega_warps;
   ma.prof = h->phase_clocks ? h->d_prof : nullptr;
   void* args[] = {&ma};
-  const size_t smem = mega_smem_doubles(dp.G, h->mega_teams) * sizeof(double);
-  CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lm_mega_kernel), dim3(h->mega_grid), dim3(h->mega_teams * kTeamThreads),
+  const size_t smem = mega_smem_doubles(dp.G, dp.n_cams, h->mega_warps) * sizeof(double);
+  CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lm_mega_kernel), dim3(h->mega_grid), dim3(32 * h->mega_warps),
                                           args, smem, h->stream));
   ++h->launches;
   return VCGPU_OK;
@@ -317,7 +317,7 @@ static int mega_collect_clocks(vcgpu_handle* h, int iters) {
   CUDA_TRY(h, cudaMemcpy(ns, h->d_prof, sizeof ns, cudaMemcpyDeviceToHost));
   CUDA_TRY(h, cudaMemset(h->d_prof, 0, sizeof ns));
   const int map[kProfCount] = {VCGPU_STAGE_FRAME_SOLVE, VCGPU_STAGE_GLOBAL_SOLVE, VCGPU_STAGE_BACKSUB, VCGPU_STAGE_BUILD,
-                               VCGPU_STAGE_FINALIZE, VCGPU_STAGE_GRID_SYNC, VCGPU_STAGE_GRID_SYNC};
+                               VCGPU_STAGE_FINALIZE, VCGPU_STAGE_GRID_SYNC};
   for (int k = 0; k < kProfCount; ++k) { h->st_ms[map[k]] += ns[k] * 1e-6; h->st_n[map[k]] += iters; }
   return VCGPU_OK;
 }

@@ -53,7 +53,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 
 // residual + reduced tangent Jacobian of one observation, loss-corrected, written to the tile:
 // columns [0,6) pose (translation, rotation), [6,6+K) intrinsics (masked), 6+K residual, rest zero
-template <int MODEL>
+template <int MODEL, int LD = kFusedLd>
 __device__ __forceinline__ double eval_obs_to_tile(const double* T, const double* cam, const double* R, const double* mask, V3 pw,
                                                    double pcu, double pcv, double mult, double* tile, int k0, int k1) {
   constexpr int K = Cam<MODEL>::K;
@@ -74,17 +74,17 @@ __device__ __forceinline__ double eval_obs_to_tile(const double* T, const double
     const double m1 = (d[0] * R[1] + d[1] * R[4] + d[2] * R[7]) * sc;
     const double m2 = (d[0] * R[2] + d[1] * R[5] + d[2] * R[8]) * sc;
     double* o = tile + (row == 0 ? k0 : k1);
-    o[0 * kFusedLd] = -m0;
-    o[1 * kFusedLd] = -m1;
-    o[2 * kFusedLd] = -m2;
-    o[3 * kFusedLd] = m1 * pk.z - m2 * pk.y;
-    o[4 * kFusedLd] = m2 * pk.x - m0 * pk.z;
-    o[5 * kFusedLd] = m0 * pk.y - m1 * pk.x;
+    o[0 * LD] = -m0;
+    o[1 * LD] = -m1;
+    o[2 * LD] = -m2;
+    o[3 * LD] = m1 * pk.z - m2 * pk.y;
+    o[4 * LD] = m2 * pk.x - m0 * pk.z;
+    o[5 * LD] = m0 * pk.y - m1 * pk.x;
 #pragma unroll
-    for (int k = 0; k < K; ++k) o[(6 + k) * kFusedLd] = dzi[row * K + k] * sc * mask[6 + k];
-    o[(6 + K) * kFusedLd] = (row == 0 ? r0 : r1) * sc;
+    for (int k = 0; k < K; ++k) o[(6 + k) * LD] = dzi[row * K + k] * sc * mask[6 + k];
+    o[(6 + K) * LD] = (row == 0 ? r0 : r1) * sc;
 #pragma unroll
-    for (int k = 7 + K; k < kFusedCols; ++k) o[k * kFusedLd] = 0.0;
+    for (int k = 7 + K; k < kFusedCols; ++k) o[k * LD] = 0.0;
   }
   return 0.5 * rho0 * mult;
 }

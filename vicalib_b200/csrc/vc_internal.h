@@ -163,12 +163,12 @@ struct vcgpu_handle {
   double* d_red_part = nullptr;   // [kReduceBlocks][8] level-1 scalar partials
   unsigned* d_counter = nullptr;  // last-CTA tickets
   // persistent vision kernel (vc_mega.cuh)
-  double *d_partS = nullptr, *d_partC = nullptr;  // [grid][G*G+G+8]
+  double *d_partS = nullptr, *d_partC = nullptr;  // [grid][G*G+G+8] / [grid][n_cams*kCgStride+8]
   double *d_totS = nullptr, *d_totC = nullptr;    // [G*G+G+8] grid totals
   unsigned long long* d_prof = nullptr;
   int dev_sms = 0, dev_smem_optin = 0;
   size_t mega_smem_set = 0;
-  int mega_grid = 0, mega_teams = 0;  // 0 teams: does not fit / not supported, use the multi-launch engine
+  int mega_grid = 0, mega_warps = 0;  // 0 warps: does not fit / not supported, use the multi-launch engine
   double* d_scalars = nullptr;    // device scalars (see vcgpu.cu)
   double* h_scalars = nullptr;    // pinned mirror
   vc::Ctl* d_ctl = nullptr;       // device-resident trust-region state

@@ -1,23 +1,25 @@
 // Persistent trust-region kernel for the vision-only problem on one GPU.
 //
 // One cooperative launch runs up to n_iters Levenberg-Marquardt iterations; one CTA per SM, every
-// frame owned by the same CTA for the whole solve.  An iteration is five phases separated by two grid
-// barriers (instead of six launches):
+// frame owned by the same WARP of the same CTA for the whole solve (frame f -> CTA f mod grid, warp
+// (f / grid) mod warps).  An iteration is a chain of per-frame warp phases and three small
+// every-CTA phases, separated by four ~1 us grid barriers instead of six launches:
 //
 //   S  per frame (warp):  L = chol(B_f + D_f),  X_f = (B_f + D_f)^-1 [E_f | g_f],  CTA partial of E^T X
-//   ------------------------------------------------------------------------------- grid barrier
-//   G  every CTA, redundantly: sum the 148 partials in fixed order, factor the reduced system
-//      C + D - sum E^T X, solve for the globals' step
+//   R1 entry e of the Schur sum is added up over the CTAs by one warp of CTA (e mod grid)      | barrier
+//   G  every CTA, redundantly: reduced system C + D - sum E^T X, Cholesky, globals' step       | barrier
 //   U  per frame (warp):  back-substitution, x (+) step, step statistics; trial camera states
-//   B  per frame (team of 5 warps): fused evaluate + Gram build at the trial point (vc_fused.cuh),
-//      the camera blocks accumulated per team in shared memory (no per-group global round trip)
-//   ------------------------------------------------------------------------------- grid barrier
-//   D  every CTA, redundantly: sum the partial global blocks / scalars in fixed order, then the
-//      accept-reject decision of Ceres' TrustRegionMinimizer (decide_step) on its own copy of Ctl
+//   B  per frame (warp): fused evaluate + Gram build at the trial point, 32 corners at a time through the
+//      warp's own shared-memory slab and FP64 DMMA (accumulators stay in registers across slabs; no block
+//      barrier anywhere in the phase); the camera blocks are accumulated per warp, packed per camera
+//   R2 packed camera blocks / scalars added up over the CTAs, as R1                            | barrier
+//   D  every CTA, redundantly: expands the packed blocks, takes the accept-reject decision of  | barrier
+//      Ceres' TrustRegionMinimizer (decide_step) on its own copy of Ctl
 //
-// Every CTA sees bit-identical sums (same order), so every CTA takes the same decision and the loop
-// needs no broadcast.  Replaces the body of ceres::Solve (vicalibrator.h:956) for the staged vision
-// solves; the inertial and the frame-sharded paths keep the multi-launch engine (vc_engine.inl).
+// Every CTA reads bit-identical totals, so every CTA takes the same decision and the loop needs no
+// broadcast; all sums run in a fixed order (deterministic).  Replaces the body of ceres::Solve
+// (vicalibrator.h:956) for the staged vision solves; the inertial and the frame-sharded paths keep the
+// multi-launch engine (vc_engine.inl).
 #pragma once
 #include <cooperative_groups.h>
 
@@ -27,15 +29,16 @@
 namespace vc {
 namespace cg = cooperative_groups;
 
-constexpr int kTeamThreads = kFusedThreads;
-constexpr int kTeamWarps = kFusedWarps;
-constexpr int kMegaMaxTeams = 4;
-constexpr int kMegaMaxThreads = kMegaMaxTeams * kTeamThreads;
-// per team: tile | per-warp partials | Gram matrix | frame block | frame gradient (+ pad)
-constexpr int kTeamDoubles = kFusedCols * kFusedLd + kTeamWarps * kFusedRed + 256 + 36 + 8;
+constexpr int kMegaMaxWarps = 16;
+constexpr int kMegaMaxThreads = 32 * kMegaMaxWarps;
+constexpr int kSlabLd = 64 + 4;                        // 32 corners x 2 residual rows (+4: conflict-free fragments)
+constexpr int kSlabDoubles = kFusedCols * kSlabLd;     // one warp's tile
+constexpr int kWarpDoubles = kSlabDoubles + 48;        // + frame block (36) + frame gradient (6), padded
+constexpr int kGtabMax = 256;
 constexpr int kMegaPartExtra = 8;  // scalars appended to each CTA's partial slot
+static_assert(kSlabLd % 16 == 4, "fragment loads need ld == 4 (mod 16)");
 enum { kPCost = 0, kPGf2, kPDotG, kPDotD, kPStep2, kPXnorm2, kPGfMax, kPNotPD };
-enum { kProfS = 0, kProfG, kProfU, kProfB, kProfD, kProfSyncA, kProfSyncB, kProfCount };
+enum { kProfS = 0, kProfG, kProfU, kProfB, kProfD, kProfSync, kProfCount };
 
 struct MegaArgs {
   DevProblem dp;
@@ -47,36 +50,33 @@ struct MegaArgs {
   const double* mask;
   const double* scale;   // Jacobi scale [nf*6 + G]
   double* X;             // [nf][6][G+1]
-  double* partS;         // [grid][NS + 8]
-  double* partC;         // [grid][NS + 8]
-  double* totS;          // [NS + 8] reduced over the grid
-  double* totC;          // [NS + 8]
+  double* partS;         // [grid][NS + 8]   Schur partial (lower triangle) | flags
+  double* partC;         // [grid][n_cams*kCgStride + 8]   packed camera blocks | scalars
+  double* totS;          // [NS + 8] grid totals
+  double* totC;          // [n_cams*kCgStride + 8]
   double* delta;         // scaled step [nf*6 + G]
   double* scalars;       // kSc* of the last evaluated point (for the host)
   int n_iters;
-  int n_teams;
+  int n_warps;
   unsigned long long* prof;  // [kProfCount] ns per phase (CTA 0), or null
 };
 
-__host__ __device__ inline size_t mega_smem_doubles(int G, int n_teams) {
+__host__ __device__ inline size_t mega_smem_doubles(int G, int n_cams, int n_warps) {
   const size_t NS = static_cast<size_t>(G) * G + G;
-  return static_cast<size_t>(n_teams) * kTeamDoubles + (2 + n_teams) * NS + G + kMaxCams * (kCamStateStride + 9) + kScCount + 64 +
-         sizeof(Ctl) / sizeof(double) + 8;
+  return static_cast<size_t>(n_warps) * (kWarpDoubles + n_cams * kCgStride) + 3 * NS + G + kMaxCams * (kCamStateStride + 9) +
+         kScCount + 8 * kMegaMaxWarps + sizeof(Ctl) / sizeof(double) + 8;
 }
 
-__device__ __forceinline__ void team_sync(int team) {
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(kTeamThreads) : "memory");
-}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
 
-// Two-stage fixed-order reduction of the CTAs' partial slots (the grid barrier is ~1 us, while every CTA
-// reading every slot is ~50 MB of L2 traffic):  stage 1, entry e is summed over all CTAs by one warp of
-// CTA (e mod grid) into tot[e];  (grid barrier)  stage 2, every CTA copies tot[] to shared memory.
-// Entries listed in max_a / max_b combine with max instead of +.
+// Stage 1 of the fixed-order reduction of the CTAs' partial slots (the grid barrier is ~1 us, while every
+// CTA reading every slot would be ~50 MB of L2 traffic): entry e is added up over all CTAs by one warp of
+// CTA (e mod grid) into tot[e]; after the barrier every CTA reads tot[].  Entries max_a / max_b combine
+// with max instead of +.
 __device__ inline void mega_reduce_stage1(const double* part, int stride, int nparts, int n, double* tot, int max_a, int max_b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int e = blockIdx.x + warp * gridDim.x; e < n; e += nwarps * gridDim.x) {
@@ -103,6 +103,12 @@ __device__ inline void mega_reduce_stage1(const double* part, int stride, int np
   }
 }
 
+template <int MODEL>
+__device__ __forceinline__ double mega_eval(const double* T, const double* cam, const double* Rc, const double* mask, V3 pw, double pcu,
+                                            double pcv, double mult, double* slab, int lane) {
+  return eval_obs_to_tile<MODEL, kSlabLd>(T, cam, Rc, mask, pw, pcu, pcv, mult, slab, lane, 32 + lane);
+}
+
 __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a) {
   extern __shared__ double smem[];
   cg::grid_group grid = cg::this_grid();
@@ -110,26 +116,40 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int bid = blockIdx.x, nb = gridDim.x;
-  const int team = tid / kTeamThreads, ttid = tid - team * kTeamThreads, twarp = ttid >> 5;
-  const int n_teams = a.n_teams;
+  const int n_cams = a.dp.n_cams;
   const int G = a.dp.G, M = G + 1, NS = G * G + G, PS = NS + kMegaPartExtra, nf = a.dp.n_frames;
+  const int NP = n_cams * kCgStride, PC = NP + kMegaPartExtra;  // packed camera blocks
   const int64_t nfp = static_cast<int64_t>(nf) * FD;
-  const int nk = bid < nf ? (nf - bid + nb - 1) / nb : 0;  // frames of this CTA: f = bid + k * nb
+  const int nk = bid < nf ? (nf - bid + nb - 1) / nb : 0;  // frames of this CTA: f = bid + k * nb, warp k mod nwarps
 
-  double* teams = smem;                                            // [n_teams][kTeamDoubles]; also phase scratch
-  double* Cacc = teams + static_cast<size_t>(n_teams) * kTeamDoubles;  // [2][NS]  C | gc of the two points
-  double* Cteam = Cacc + 2 * NS;                                   // [n_teams][NS]
-  double* dg = Cteam + static_cast<size_t>(n_teams) * NS;          // [G] globals' step (scaled)
-  double* smCam = dg + G;                                          // [kMaxCams][17] trial camera states
-  double* smRc = smCam + kMaxCams * kCamStateStride;               // [kMaxCams][9]
-  double* sc = smRc + kMaxCams * 9;                                // [kScCount]
-  double* wred = sc + kScCount;                                    // [64] per-warp scalars
-  Ctl* ctl = reinterpret_cast<Ctl*>(wred + 64);
+  double* wmem = smem;                                               // [nwarps][kWarpDoubles]; also phase scratch
+  double* Cw = wmem + static_cast<size_t>(nwarps) * kWarpDoubles;    // [nwarps][NP] packed camera blocks per warp
+  double* Cacc = Cw + static_cast<size_t>(nwarps) * NP;              // [2][NS]  C | gc of the two points
+  double* Swork = Cacc + 2 * NS;                                     // [NS] Schur accumulator / reduced system
+  double* dg = Swork + NS;                                           // [G] globals' step (scaled)
+  double* smCam = dg + G;                                            // [kMaxCams][17] trial camera states
+  double* smRc = smCam + kMaxCams * kCamStateStride;                 // [kMaxCams][9]
+  double* sc = smRc + kMaxCams * 9;                                  // [kScCount]
+  double* wred = sc + kScCount;                                      // [kMegaMaxWarps][8] per-warp scalars
+  Ctl* ctl = reinterpret_cast<Ctl*>(wred + 8 * kMegaMaxWarps);
   __shared__ int bad;
-  double* Swork = Cteam;  // phases S / G / D: Schur accumulator, then the reduced system, then the reduced trial block
+  __shared__ int2 gtab[kGtabMax];          // (start, count) of the observations of this CTA's (frame slot, camera) pairs
+  __shared__ unsigned char tri_lut[128];   // packed lower-triangle index -> (row << 4 | col)
   const double* scg = a.scale + nfp;
 
   if (tid == 0) *ctl = *a.ctl;
+  const bool use_gtab = nk * n_cams <= kGtabMax;
+  if (use_gtab)  // frame ownership is static: look the groups up once per launch
+    for (int e = tid; e < nk * n_cams; e += nthreads) {
+      const int k = e / n_cams, c = e - k * n_cams;
+      const int g = a.group_of[c * nf + bid + k * nb];
+      gtab[e] = g < 0 ? make_int2(0, 0) : make_int2(a.grp_start[g], a.grp_count[g]);
+    }
+  for (int e = tid; e < 105; e += nthreads) {
+    int p = 0;
+    while ((p + 1) * (p + 2) / 2 <= e) ++p;
+    tri_lut[e] = static_cast<unsigned char>((p << 4) | (e - p * (p + 1) / 2));
+  }
   __syncthreads();
   if (ctl->done) return;
   {
@@ -137,6 +157,12 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     double* C0 = Cacc + ctl->cur * NS;
     for (int e = tid; e < NS; e += nthreads) C0[e] = e < G * G ? b0.C[e] : b0.gc[e - G * G];
   }
+  // (start, count) of the observations of (frame slot k, camera c); count 0: the camera does not see the frame
+  auto lookup = [&](int k, int c) -> int2 {
+    if (use_gtab) return gtab[k * n_cams + c];
+    const int g = a.group_of[c * nf + bid + k * nb];
+    return g < 0 ? make_int2(0, 0) : make_int2(a.grp_start[g], a.grp_count[g]);
+  };
   unsigned long long t_prev = 0;
   const bool prof = a.prof != nullptr && bid == 0 && tid == 0;
   if (prof) t_prev = global_ns();
@@ -163,14 +189,13 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     // ------------------------------------------------------------ S: per-frame solves + Schur partial
     {
       double* Sacc = Swork;
-      double* scratch = teams;  // [nwarps][2][FD][M]
       for (int k = tid; k < NS; k += nthreads) Sacc[k] = 0.0;
       for (int base = 0; base < nk; base += nwarps) {
         const int k = base + warp;
         __syncthreads();
         if (k < nk) {
           const int f = bid + k * nb;
-          double* Esw = scratch + static_cast<size_t>(warp) * (2 * FD * M);
+          double* Esw = wmem + static_cast<size_t>(warp) * kWarpDoubles;  // [FD][M] scaled [E | g], then X [FD][M]
           double* Xw = Esw + FD * M;
           const double* sf = a.scale + static_cast<int64_t>(f) * FD;
           const double* Bf = bc.B + static_cast<int64_t>(f) * FD * FD;
@@ -194,9 +219,8 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
 #pragma unroll
             for (int q = 0; q < j; ++q) d -= L[j][q] * L[j][q];
             if (!(d > 0.0)) { ok = false; d = 1.0; }
-            d = sqrt(d);
-            L[j][j] = d;
-            const double inv = 1.0 / d;
+            const double inv = rsqrt(d);
+            L[j][j] = d * inv;
             iL[j] = inv;
 #pragma unroll
             for (int i = j + 1; i < FD; ++i) {
@@ -246,7 +270,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
           if (e < G * G && cb > ra) continue;  // lower triangle only
           double sum = 0.0;
           for (int w = 0; w < nact; ++w) {
-            const double* Ew = scratch + static_cast<size_t>(w) * (2 * FD * M);
+            const double* Ew = wmem + static_cast<size_t>(w) * kWarpDoubles;
             const double* Xv = Ew + FD * M;
 #pragma unroll
             for (int q = 0; q < FD; ++q) sum += Ew[q * M + ra] * Xv[q * M + cb];
@@ -257,25 +281,26 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
       __syncthreads();
       double* out = a.partS + static_cast<int64_t>(bid) * PS;
       for (int k = tid; k < NS; k += nthreads) out[k] = Sacc[k];
-      // any failed pivot in this CTA
       const unsigned any = __ballot_sync(0xffffffffu, notpd > 0.0);
-      if (lane == 0) wred[warp] = any ? 1.0 : 0.0;
+      if (lane == 0) wred[8 * warp] = any ? 1.0 : 0.0;
       __syncthreads();
       if (tid == 0) {
         double v = 0.0;
-        for (int w = 0; w < nwarps; ++w) v = fmax(v, wred[w]);
+        for (int w = 0; w < nwarps; ++w) v = fmax(v, wred[8 * w]);
         out[NS + kPNotPD] = v;
       }
     }
     mark(kProfS);
     grid.sync();
-    mark(kProfSyncA);
+    mark(kProfSync);
 
     // ------------------------------------------------------------ G: reduced system, every CTA the same
     {
       double* S = Swork;  // [G*G] lower triangle, then rhs [G]
       mega_reduce_stage1(a.partS, PS, nb, PS, a.totS, NS + kPNotPD, -1);
+      mark(kProfG);
       grid.sync();
+      mark(kProfSync);
       for (int e = tid; e < NS; e += nthreads) {
         const double p = __ldcg(a.totS + e);
         if (e < G * G) {
@@ -344,7 +369,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     double ustat[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0 of each warp: dotG, dotD, step2, xnorm2
     {
       if (warp == nwarps - 1) {  // trial camera states (every CTA needs them); CTA 0 also stores the globals
-        if (lane < a.dp.n_cams) {
+        if (lane < n_cams) {
           const int c = lane;
           const CamInfo& ci = a.dp.cams[c];
           const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
@@ -365,7 +390,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
         }
         __syncwarp();
         if (bid == 0 && lane == 0) {  // the globals' share of the step statistics, counted once
-          for (int c = 0; c < a.dp.n_cams; ++c) {
+          for (int c = 0; c < n_cams; ++c) {
             const CamInfo& ci = a.dp.cams[c];
             const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
             const double* xo = smCam + kCamStateStride * c;
@@ -419,95 +444,107 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
           for (int q = 0; q < 3; ++q) x_new[a.dp.off_v + 3 * static_cast<int64_t>(f) + q] = x_cur[a.dp.off_v + 3 * static_cast<int64_t>(f) + q];
         }
       }
-      for (int e = tid; e < n_teams * NS; e += nthreads) Cteam[e] = 0.0;
-      __syncthreads();
+      for (int e = tid; e < nwarps * NP; e += nthreads) Cw[e] = 0.0;
+      __syncthreads();  // trial camera states and the trial poses are visible to every warp
     }
     mark(kProfU);
 
     // ------------------------------------------------------------ B: fused evaluate + build at the trial point
+    // No block barrier in this phase: each warp runs its frames on its own slab, at its own pace.
     double cost = 0.0, gf2 = 0.0, gfmax = 0.0;
-    if (team < n_teams) {
-      double* tb = teams + static_cast<size_t>(team) * kTeamDoubles;
-      double* tile = tb;
-      double* red = tile + kFusedCols * kFusedLd;
-      double* Gm = red + kTeamWarps * kFusedRed;
-      double* smB = Gm + 256;
+    {
+      double* slab = wmem + static_cast<size_t>(warp) * kWarpDoubles;  // [16][kSlabLd]; reused as the 16 x 16 Gram matrix
+      double* smB = slab + kSlabDoubles;                               // [36] | [6]
       double* smg = smB + 36;
-      double* Ct = Cteam + static_cast<size_t>(team) * NS;
-      for (int k = team; k < nk; k += n_teams) {
+      double* Cmine = Cw + static_cast<size_t>(warp) * NP;
+      const double* frag = slab + (lane >> 2) * kSlabLd + (lane & 3);
+      for (int k = warp; k < nk; k += nwarps) {
         const int f = bid + k * nb;
         const double* T = x_new + 7 * static_cast<int64_t>(f);
-        team_sync(team);  // previous frame's stores of smB / smg are done
-        for (int q = ttid; q < 42; q += kTeamThreads) smB[q] = 0.0;  // smB[36] | smg[6]
+        __syncwarp();
+        for (int q = lane; q < 42; q += 32) smB[q] = 0.0;
         double* Ef = bt.E + static_cast<int64_t>(f) * FD * G;
-        for (int q = ttid; q < FD * G; q += kTeamThreads) Ef[q] = 0.0;
-        for (int c = 0; c < a.dp.n_cams; ++c) {
-          const int g = a.group_of[c * nf + f];
-          if (g < 0) continue;
+        bool zero_E = n_cams > 1;  // one camera: the expansion below writes every column
+        for (int c = 0; c < n_cams; ++c) {
+          const int2 grp = lookup(k, c);
+          if (grp.y == 0) continue;
+          if (zero_E) {
+            for (int q = lane; q < FD * G; q += 32) Ef[q] = 0.0;
+            zero_E = false;
+          }
           const CamInfo& ci = a.dp.cams[c];
-          const int K = ci.K, NG = 6 + K;
-          const int start = a.grp_start[g], cnt = a.grp_count[g];
+          const int K = ci.K, NG = 6 + K, model = ci.model;
+          const int start = grp.x, cnt = grp.y;
           const double* cam = smCam + kCamStateStride * c;
           const double* Rc = smRc + 9 * c;
           const double* mask = a.mask + ci.goff;
           double acc[3][2];
 #pragma unroll
           for (int b = 0; b < 3; ++b) acc[b][0] = acc[b][1] = 0.0;
-          for (int ch = 0; ch < cnt; ch += kFusedChunk) {
-            const int m = min(kFusedChunk, cnt - ch);
+          // software pipeline: the next slab's observation is loaded while this slab goes through the DMMAs
+          double nx[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+          if (lane < cnt) {
+            const int64_t i = start + lane;
+            nx[0] = a.pw[3 * i]; nx[1] = a.pw[3 * i + 1]; nx[2] = a.pw[3 * i + 2]; nx[3] = a.pc[2 * i]; nx[4] = a.pc[2 * i + 1];
+          }
+          for (int s0 = 0; s0 < cnt; s0 += 32) {
+            const int m = min(32, cnt - s0);
             const int m4 = (m + 3) & ~3;
-            team_sync(team);  // previous pass / epilogue is done with the tile and Gm
-            if (ttid < m) {
-              const int64_t i = start + ch + ttid;
-              const V3 pw{a.pw[3 * i], a.pw[3 * i + 1], a.pw[3 * i + 2]};
-              const double pcu = a.pc[2 * i], pcv = a.pc[2 * i + 1];
-              switch (ci.model) {
-                case kLinear: cost += eval_obs_to_tile<kLinear>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, tile, ttid, kFusedChunk + ttid); break;
-                case kFov: cost += eval_obs_to_tile<kFov>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, tile, ttid, kFusedChunk + ttid); break;
-                case kPoly2: cost += eval_obs_to_tile<kPoly2>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, tile, ttid, kFusedChunk + ttid); break;
-                case kPoly3: cost += eval_obs_to_tile<kPoly3>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, tile, ttid, kFusedChunk + ttid); break;
-                default: cost += eval_obs_to_tile<kKb4>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, tile, ttid, kFusedChunk + ttid); break;
+            const V3 pw{nx[0], nx[1], nx[2]};
+            const double pcu = nx[3], pcv = nx[4];
+            if (s0 + 32 + lane < cnt) {
+              const int64_t i = start + s0 + 32 + lane;
+              nx[0] = a.pw[3 * i]; nx[1] = a.pw[3 * i + 1]; nx[2] = a.pw[3 * i + 2]; nx[3] = a.pc[2 * i]; nx[4] = a.pc[2 * i + 1];
+            }
+            __syncwarp();  // the previous slab's fragment loads are done
+            if (lane < m) {
+              switch (model) {
+                case kLinear: cost += mega_eval<kLinear>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, slab, lane); break;
+                case kFov: cost += mega_eval<kFov>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, slab, lane); break;
+                case kPoly2: cost += mega_eval<kPoly2>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, slab, lane); break;
+                case kPoly3: cost += mega_eval<kPoly3>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, slab, lane); break;
+                default: cost += mega_eval<kKb4>(T, cam, Rc, mask, pw, pcu, pcv, a.dp.visual_mult, slab, lane); break;
               }
-            } else if (ttid < m4) {
+            } else if (lane < m4) {  // zero the padding rows of both halves
 #pragma unroll
               for (int q = 0; q < kFusedCols; ++q) {
-                tile[q * kFusedLd + ttid] = 0.0;
-                tile[q * kFusedLd + kFusedChunk + ttid] = 0.0;
+                slab[q * kSlabLd + lane] = 0.0;
+                slab[q * kSlabLd + 32 + lane] = 0.0;
               }
             }
-            team_sync(team);
+            __syncwarp();
+            // SYRK over k: steps [0, m4/4) cover residual row 0, [m4/4, m4/2) residual row 1
             const int ns = m4 >> 2;
-            const double* frag = tile + (lane >> 2) * kFusedLd + (lane & 3);
-            for (int s = twarp; s < 2 * ns; s += kTeamWarps) {
-              const int k0 = s < ns ? 4 * s : kFusedChunk + 4 * (s - ns);
-              const double a0 = frag[k0], a1 = frag[8 * kFusedLd + k0];
-              dmma_m8n8k4(acc[0][0], acc[0][1], a0, a0);
-              dmma_m8n8k4(acc[1][0], acc[1][1], a1, a0);
-              dmma_m8n8k4(acc[2][0], acc[2][1], a1, a1);
+            for (int s = 0; s < 2 * ns; ++s) {
+              const int k0 = s < ns ? 4 * s : 32 + 4 * (s - ns);
+              const double a0 = frag[k0], a1 = frag[8 * kSlabLd + k0];
+              dmma_m8n8k4(acc[0][0], acc[0][1], a0, a0);  // (0,0)
+              dmma_m8n8k4(acc[1][0], acc[1][1], a1, a0);  // (1,0)
+              dmma_m8n8k4(acc[2][0], acc[2][1], a1, a1);  // (1,1)
             }
           }
+          // the three accumulator blocks -> symmetric 16 x 16 Gram matrix (in the slab)
+          __syncwarp();
+          double* Gm = slab;
           {
-            double* rw = red + twarp * kFusedRed + (lane >> 2) * 8 + 2 * (lane & 3);
+            const int rr = lane >> 2, cc = 2 * (lane & 3);
+            const double vm = a.dp.visual_mult;
 #pragma unroll
-            for (int b = 0; b < 3; ++b) { rw[b * 64] = acc[b][0]; rw[b * 64 + 1] = acc[b][1]; }
+            for (int b = 0; b < 3; ++b) {
+              const int i = (b == 0 ? 0 : 8) + rr, j = (b == 2 ? 8 : 0) + cc;
+              const double v0 = acc[b][0] * vm, v1 = acc[b][1] * vm;
+              // diagonal blocks: both triangles are computed (bitwise equal), keep j <= i and mirror
+              if (b == 1 || j <= i) { Gm[i * 16 + j] = v0; Gm[j * 16 + i] = v0; }
+              if (b == 1 || j + 1 <= i) { Gm[i * 16 + j + 1] = v1; Gm[(j + 1) * 16 + i] = v1; }
+            }
           }
-          team_sync(team);
-          for (int e = ttid; e < kFusedRed; e += kTeamThreads) {
-            const int b = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
-            const int i = (b == 0 ? 0 : 8) + rr, j = (b == 2 ? 8 : 0) + cc;
-            if (j > i) continue;
-            double v = 0.0;
-#pragma unroll
-            for (int w = 0; w < kTeamWarps; ++w) v += red[w * kFusedRed + e];
-            v *= a.dp.visual_mult;
-            Gm[i * 16 + j] = v;
-            Gm[j * 16 + i] = v;
-          }
-          team_sync(team);
+          __syncwarp();
+          // expand: frame block, frame gradient, E (extrinsic columns through A), the camera's packed global block
           const double* Grf = Gm + (6 + K) * 16;
           const int nsym = NG * (NG + 1) / 2;
           const int n_out = 36 + 6 + 6 * NG + nsym + NG;
-          for (int e = ttid; e < n_out; e += kTeamThreads) {
+          double* Cc = Cmine + c * kCgStride;
+          for (int e = lane; e < n_out; e += 32) {
             int o = e;
             if (o < 36) { smB[o] += Gm[(o / 6) * 16 + (o % 6)]; continue; }
             o -= 36;
@@ -520,16 +557,13 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
             }
             o -= 6 * NG;
             if (o < nsym) {
-              int p = static_cast<int>((sqrt(8.0 * o + 1.0) - 1.0) * 0.5);
-              while ((p + 1) * (p + 2) / 2 <= o) ++p;
-              while (p * (p + 1) / 2 > o) --p;
-              const int q = o - p * (p + 1) / 2;
+              const int p = tri_lut[o] >> 4, q = tri_lut[o] & 15;
               double v;
               if (q >= 6) {
-                v = Gm[p * 16 + q];
+                v = Gm[p * 16 + q];                                        // intrinsics x intrinsics
               } else if (p >= 6) {
-                v = mask[q] * times_A(Gm + p * 16, q, Rc);
-              } else {
+                v = mask[q] * times_A(Gm + p * 16, q, Rc);                // intrinsics x extrinsics
+              } else {                                                     // extrinsics x extrinsics: (A^T Gff A)[p][q]
                 if (p < 3) {
                   v = -times_A(Gm + (3 + p) * 16, q, Rc);
                 } else {
@@ -538,25 +572,27 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
                 }
                 v *= mask[p] * mask[q];
               }
-              Ct[(ci.goff + p) * G + ci.goff + q] += v;  // lower triangle; the same thread owns the entry every frame
+              Cc[o] += v;  // the same lane owns the entry for every frame of this warp
               continue;
             }
             o -= nsym;
-            Ct[G * G + ci.goff + o] += o < 6 ? mask[o] * times_A(Grf, o, Rc) : Grf[o];
+            Cc[105 + o] += o < 6 ? mask[o] * times_A(Grf, o, Rc) : Grf[o];
           }
         }
-        team_sync(team);
+        if (zero_E)  // no camera saw the frame
+          for (int q = lane; q < FD * G; q += 32) Ef[q] = 0.0;
+        __syncwarp();
         double* Bf = bt.B + static_cast<int64_t>(f) * FD * FD;
-        for (int q = ttid; q < 36; q += kTeamThreads) Bf[q] = smB[q];
-        if (ttid < 6) {
-          const double gv = smg[ttid];
-          bt.gf[static_cast<int64_t>(f) * FD + ttid] = gv;
+        for (int q = lane; q < 36; q += 32) Bf[q] = smB[q];
+        if (lane < 6) {
+          const double gv = smg[lane];
+          bt.gf[static_cast<int64_t>(f) * FD + lane] = gv;
           gf2 += gv * gv;
           gfmax = fmax(gfmax, fabs(gv));
         }
       }
     }
-    // CTA partials: scalars, then the teams' global blocks in fixed order
+    // CTA partials: scalars, then the warps' packed camera blocks in fixed order
     {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -564,57 +600,70 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
         gf2 += __shfl_xor_sync(0xffffffffu, gf2, o);
         gfmax = fmax(gfmax, __shfl_xor_sync(0xffffffffu, gfmax, o));
       }
-      __syncthreads();  // S-phase users of wred are long done; teams are done with Cteam
       if (lane == 0) {
-        double* w = teams + warp * 8;  // team areas are free again
+        double* w = wred + 8 * warp;
         w[0] = cost; w[1] = gf2; w[2] = gfmax;
         w[3] = ustat[0]; w[4] = ustat[1]; w[5] = ustat[2]; w[6] = ustat[3];
       }
       __syncthreads();
-      double* out = a.partC + static_cast<int64_t>(bid) * PS;
-      for (int e = tid; e < NS; e += nthreads) {
+      double* out = a.partC + static_cast<int64_t>(bid) * PC;
+      for (int e = tid; e < NP; e += nthreads) {
         double v = 0.0;
-        for (int t = 0; t < n_teams; ++t) v += Cteam[static_cast<size_t>(t) * NS + e];
+        for (int w = 0; w < nwarps; ++w) v += Cw[static_cast<size_t>(w) * NP + e];
         out[e] = v;
       }
       if (tid == 0) {
         double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (int w = 0; w < nwarps; ++w) {
-          const double* p = teams + w * 8;
+          const double* p = wred + 8 * w;
           t[0] += p[0]; t[1] += p[1]; t[2] = fmax(t[2], p[2]);
           t[3] += p[3]; t[4] += p[4]; t[5] += p[5]; t[6] += p[6];
         }
-        out[NS + kPCost] = t[0]; out[NS + kPGf2] = t[1]; out[NS + kPGfMax] = t[2];
-        out[NS + kPDotG] = t[3]; out[NS + kPDotD] = t[4]; out[NS + kPStep2] = t[5]; out[NS + kPXnorm2] = t[6];
+        out[NP + kPCost] = t[0]; out[NP + kPGf2] = t[1]; out[NP + kPGfMax] = t[2];
+        out[NP + kPDotG] = t[3]; out[NP + kPDotD] = t[4]; out[NP + kPStep2] = t[5]; out[NP + kPXnorm2] = t[6];
+        out[NP + kPNotPD] = 0.0;
       }
     }
     mark(kProfB);
     grid.sync();
-    mark(kProfSyncB);
+    mark(kProfSync);
 
     // ------------------------------------------------------------ D: global block of the trial point, decision
     {
       double* Ctrial = Cacc + (1 - cur) * NS;
-      mega_reduce_stage1(a.partC, PS, nb, PS, a.totC, NS + kPGfMax, NS + kPNotPD);
+      mega_reduce_stage1(a.partC, PC, nb, PC, a.totC, NP + kPGfMax, NP + kPNotPD);
+      mark(kProfD);
       grid.sync();
-      for (int e = tid; e < NS; e += nthreads) Swork[e] = __ldcg(a.totC + e);
-      __syncthreads();
-      for (int e = tid; e < NS; e += nthreads) {
-        if (e < G * G) {
-          const int r = e / G, c = e - r * G;
-          Ctrial[e] = Swork[c > r ? c * G + r : e];
-        } else {
-          Ctrial[e] = Swork[e];
+      mark(kProfSync);
+      for (int e = tid; e < NS; e += nthreads) {  // packed per-camera blocks -> dense C | gc
+        const int r = e < G * G ? e / G : e - G * G;
+        const int cc = e < G * G ? e - r * G : -1;
+        double v = 0.0;
+        for (int c = 0; c < n_cams; ++c) {
+          const CamInfo& ci = a.dp.cams[c];
+          const int p = r - ci.goff;
+          if (p < 0 || p >= 6 + ci.K) continue;
+          if (cc < 0) {
+            v = __ldcg(a.totC + c * kCgStride + 105 + p);
+          } else {
+            const int q = cc - ci.goff;
+            if (q >= 0 && q < 6 + ci.K) {
+              const int hi = max(p, q), lo = min(p, q);
+              v = __ldcg(a.totC + c * kCgStride + hi * (hi + 1) / 2 + lo);
+            }
+          }
         }
+        Ctrial[e] = v;
       }
+      __syncthreads();
       if (warp == 0) {
         double v[7];
-        v[0] = __ldcg(a.totC + NS + kPCost); v[1] = __ldcg(a.totC + NS + kPGf2); v[2] = __ldcg(a.totC + NS + kPDotG);
-        v[3] = __ldcg(a.totC + NS + kPDotD); v[4] = __ldcg(a.totC + NS + kPStep2); v[5] = __ldcg(a.totC + NS + kPXnorm2);
-        v[6] = __ldcg(a.totC + NS + kPGfMax);
+        v[0] = __ldcg(a.totC + NP + kPCost); v[1] = __ldcg(a.totC + NP + kPGf2); v[2] = __ldcg(a.totC + NP + kPDotG);
+        v[3] = __ldcg(a.totC + NP + kPDotD); v[4] = __ldcg(a.totC + NP + kPStep2); v[5] = __ldcg(a.totC + NP + kPXnorm2);
+        v[6] = __ldcg(a.totC + NP + kPGfMax);
         double g2 = 0.0, gm = 0.0;
         for (int q = lane; q < G; q += 32) {
-          const double gv = Swork[G * G + q];
+          const double gv = Ctrial[G * G + q];
           g2 += gv * gv;
           gm = fmax(gm, fabs(gv));
         }

@@ -406,7 +406,7 @@ static int ensure_rJ(vcgpu_handle* h) {
 // persistent vision kernel: pick the team count that fits shared memory, allocate the partial slots
 static int mega_prepare(vcgpu_handle* h) {
   const DevProblem& dp = h->dp;
-  h->mega_teams = 0;
+  h->mega_warps = 0;
   if (dp.inertial || h->nranks > 1) return VCGPU_OK;
   if (h->dev_sms == 0) {  // device attributes: once per handle
     int coop = 0, smem_optin = 0, sms = 0;
@@ -417,26 +417,27 @@ static int mega_prepare(vcgpu_handle* h) {
     h->dev_smem_optin = coop ? smem_optin : 0;
   }
   if (h->dev_smem_optin == 0) return VCGPU_OK;
-  int teams = vc::kMegaMaxTeams;
-  while (teams > 0 && vc::mega_smem_doubles(dp.G, teams) * sizeof(double) > static_cast<size_t>(h->dev_smem_optin)) --teams;
-  if (teams == 0 || static_cast<size_t>(60) * teams * (dp.G + 1) > static_cast<size_t>(teams) * vc::kTeamDoubles) return VCGPU_OK;
-  const size_t smem = vc::mega_smem_doubles(dp.G, teams) * sizeof(double);
+  int warps = vc::kMegaMaxWarps;
+  while (warps > 0 && vc::mega_smem_doubles(dp.G, dp.n_cams, warps) * sizeof(double) > static_cast<size_t>(h->dev_smem_optin)) --warps;
+  if (warps == 0 || 12 * (dp.G + 1) > vc::kWarpDoubles) return VCGPU_OK;
+  const size_t smem = vc::mega_smem_doubles(dp.G, dp.n_cams, warps) * sizeof(double);
   if (smem > h->mega_smem_set) {
     CUDA_TRY(h, cudaFuncSetAttribute(vc::lm_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vc::lm_mega_kernel, teams * vc::kTeamThreads, smem));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vc::lm_mega_kernel, 32 * warps, smem));
     if (per_sm < 1) return VCGPU_OK;
     h->mega_smem_set = smem;
   }
   h->mega_grid = h->dev_sms;
-  h->mega_teams = teams;
+  h->mega_warps = warps;
   const size_t PS = static_cast<size_t>(dp.G) * dp.G + dp.G + vc::kMegaPartExtra;
+  const size_t PC = static_cast<size_t>(dp.n_cams) * vc::kCgStride + vc::kMegaPartExtra;
   VC_TRY(dev_alloc(h, &h->d_partS, h->mega_grid * PS));
-  VC_TRY(dev_alloc(h, &h->d_partC, h->mega_grid * PS));
+  VC_TRY(dev_alloc(h, &h->d_partC, h->mega_grid * PC));
   VC_TRY(dev_alloc(h, &h->d_totS, PS));
-  VC_TRY(dev_alloc(h, &h->d_totC, PS));
+  VC_TRY(dev_alloc(h, &h->d_totC, PC));
   CUDA_TRY(h, cudaMemsetAsync(h->d_partS, 0, h->mega_grid * PS * sizeof(double), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_partC, 0, h->mega_grid * PS * sizeof(double), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_partC, 0, h->mega_grid * PC * sizeof(double), h->stream));
   VC_TRY(dev_alloc(h, &h->d_prof, vc::kProfCount));
   CUDA_TRY(h, cudaMemsetAsync(h->d_prof, 0, vc::kProfCount * sizeof(unsigned long long), h->stream));
   return VCGPU_OK;
