@@ -103,6 +103,47 @@ __device__ inline void mega_reduce_stage1(const double* part, int stride, int np
   }
 }
 
+// Reduced-system solve, one warp.  S: lower triangle [G][G] row-major followed by the right-hand side [G];
+// the solution overwrites the right-hand side.  The right-hand side is carried through the factorisation as an
+// extra row (so L y = rhs comes for free) and the pivots are kept as reciprocals.  Rows are spread over the
+// lanes, column updates batched by four.  (A register-resident variant with shuffle broadcasts measured
+// slower on B200: +2 us in this phase and, through register pressure, +1 us in the others.)
+__device__ inline void mega_chol_solve_smem(double* S, int G, int lane, double* invd, int* bad) {
+  double* rhs = S + G * G;
+  for (int j = 0; j < G; ++j) {
+    double d = S[j * G + j];
+    if (!(d > 0.0)) { if (lane == 0) *bad = 1; d = 1.0; }
+    const double inv = rsqrt(d);
+    __syncwarp();
+    if (lane == 0) { S[j * G + j] = d * inv; invd[j] = inv; }
+    for (int r = j + 1 + lane; r <= G; r += 32) {
+      double* row = r < G ? S + r * G : rhs;
+      row[j] *= inv;
+    }
+    __syncwarp();
+    for (int r = j + 1 + lane; r <= G; r += 32) {
+      double* row = r < G ? S + r * G : rhs;
+      const double lrj = row[j];
+      const int qmax = min(r, G - 1);
+      int q = j + 1;
+      for (; q + 3 <= qmax; q += 4) {
+        const double l0 = S[q * G + j], l1 = S[(q + 1) * G + j], l2 = S[(q + 2) * G + j], l3 = S[(q + 3) * G + j];
+        const double r0 = row[q], r1 = row[q + 1], r2 = row[q + 2], r3 = row[q + 3];
+        row[q] = r0 - lrj * l0; row[q + 1] = r1 - lrj * l1; row[q + 2] = r2 - lrj * l2; row[q + 3] = r3 - lrj * l3;
+      }
+      for (; q <= qmax; ++q) row[q] -= lrj * S[q * G + j];
+    }
+    __syncwarp();
+  }
+  for (int i = G - 1; i >= 0; --i) {  // L^T x = y
+    const double xi = rhs[i] * invd[i];
+    __syncwarp();
+    if (lane == 0) rhs[i] = xi;
+    for (int q = lane; q < i; q += 32) rhs[q] -= S[i * G + q] * xi;
+    __syncwarp();
+  }
+}
+
 template <int MODEL>
 __device__ __forceinline__ double mega_eval(const double* T, const double* cam, const double* Rc, const double* mask, V3 pw, double pcu,
                                             double pcv, double mult, double* slab, int lane) {
@@ -317,42 +358,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
       if (tid == 0) { sc[kScNotPD] = __ldcg(a.totS + NS + kPNotPD); bad = 0; }
       __syncthreads();
       if (warp == 0) {
-        // Cholesky of the reduced system with the right-hand side carried as row G (so L y = rhs comes for
-        // free), reciprocal pivots kept for the back-substitution; one warp, rows spread over the lanes
-        double* rhs = S + G * G;
-        double* invd = dg;
-        for (int j = 0; j < G; ++j) {
-          double d = S[j * G + j];
-          if (!(d > 0.0)) { if (lane == 0) bad = 1; d = 1.0; }
-          const double inv = rsqrt(d);
-          __syncwarp();
-          if (lane == 0) { S[j * G + j] = d * inv; invd[j] = inv; }
-          for (int r = j + 1 + lane; r <= G; r += 32) {
-            double* row = r < G ? S + r * G : rhs;
-            row[j] *= inv;
-          }
-          __syncwarp();
-          for (int r = j + 1 + lane; r <= G; r += 32) {
-            double* row = r < G ? S + r * G : rhs;
-            const double lrj = row[j];
-            const int qmax = min(r, G - 1);
-            int q = j + 1;
-            for (; q + 3 <= qmax; q += 4) {
-              const double l0 = S[q * G + j], l1 = S[(q + 1) * G + j], l2 = S[(q + 2) * G + j], l3 = S[(q + 3) * G + j];
-              const double r0 = row[q], r1 = row[q + 1], r2 = row[q + 2], r3 = row[q + 3];
-              row[q] = r0 - lrj * l0; row[q + 1] = r1 - lrj * l1; row[q + 2] = r2 - lrj * l2; row[q + 3] = r3 - lrj * l3;
-            }
-            for (; q <= qmax; ++q) row[q] -= lrj * S[q * G + j];
-          }
-          __syncwarp();
-        }
-        for (int i = G - 1; i >= 0; --i) {  // L^T x = y
-          const double xi = rhs[i] * invd[i];
-          __syncwarp();
-          if (lane == 0) rhs[i] = xi;
-          for (int q = lane; q < i; q += 32) rhs[q] -= S[i * G + q] * xi;
-          __syncwarp();
-        }
+        mega_chol_solve_smem(S, G, lane, dg, &bad);
       }
       __syncthreads();
       for (int i = tid; i < G; i += nthreads) {
@@ -368,7 +374,8 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     // ------------------------------------------------------------ U: back-substitution, trial states
     double ustat[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0 of each warp: dotG, dotD, step2, xnorm2
     {
-      if (warp == nwarps - 1) {  // trial camera states (every CTA needs them); CTA 0 also stores the globals
+      if (warp == nwarps - 1) {  // trial camera states (every CTA needs them; the last warp is the one most likely
+                                 // to own no frame); CTA 0 also stores the globals
         if (lane < n_cams) {
           const int c = lane;
           const CamInfo& ci = a.dp.cams[c];
