@@ -44,6 +44,8 @@ static int ctl_reset(vcgpu_handle* h, int fixed, int max_iters) {
   c->max_iters = max_iters;
   c->radius = h->opts.init_radius;
   c->decrease_factor = 2.0;
+  c->dl_mu = 1e-8;  // DoglegStrategy: mu_ = min_mu_
+  c->dl_ok = 1;
   c->function_tol = h->opts.function_tol;
   c->gradient_tol = h->opts.gradient_tol;
   c->param_tol = h->opts.param_tol;
@@ -288,7 +290,7 @@ static int num_residuals(const vcgpu_handle* h) {
 
 // ------------------------------------------------------------------ persistent vision kernel
 static bool mega_applies(const vcgpu_handle* h) {
-  return h->mega_warps > 0 && !h->dp.inertial && h->nranks == 1 && !h->materialize && !h->profiling && !h->multi_launch &&
+  return h->mega_warps > 0 && h->opts.strategy == 0 && !h->dp.inertial && h->nranks == 1 && !h->materialize && !h->profiling && !h->multi_launch &&
          h->flags.visual && h->n_obs > 0;
 }
 // up to n_iters trust-region iterations in one cooperative launch (vc_mega.cuh)
@@ -322,8 +324,66 @@ static int mega_collect_clocks(vcgpu_handle* h, int iters) {
   return VCGPU_OK;
 }
 
+// ------------------------------------------------------------------ dogleg strategy (vc_dogleg.cuh)
+static int dl_matvec(vcgpu_handle* h, const double* v, double* y, double* zpart) {
+  const DevProblem& dp = h->dp;
+  const int nb = (dp.n_frames + kMvWarps - 1) / kMvWarps;
+  const size_t sm = static_cast<size_t>(kMvWarps) * dp.G * sizeof(double);
+  if (dp.fd == 6) arrow_matvec_frames_kernel<6><<<nb, 32 * kMvWarps, sm, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart);
+  else arrow_matvec_frames_kernel<9><<<nb, 32 * kMvWarps, sm, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart);
+  arrow_matvec_globals_kernel<<<1, 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart, nb);
+  h->launches += 2;
+  return VCGPU_OK;
+}
+static int enqueue_dogleg_iteration(vcgpu_handle* h, bool weights) {
+  const DevProblem& dp = h->dp;
+  const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;
+  const int nmv = (dp.n_frames + kMvWarps - 1) / kMvWarps;
+  VC_TRY(dev_alloc(h, &h->d_dl, 6 * static_cast<size_t>(np) + static_cast<size_t>(nmv) * dp.G));
+  VC_TRY(dev_alloc(h, &h->d_dl_part, 4 * kDlBlocks));
+  DlVecs v;
+  v.diag = h->d_dl; v.grad = v.diag + np; v.gn = v.grad + np; v.vec = v.gn + np; v.Hv = v.vec + np; v.D2 = v.Hv + np;
+  double* zpart = v.D2 + np;
+  const int nblk = static_cast<int>((np + 255) / 256);
+  DlDotArgs da;
+  da.ctl = h->d_ctl; da.v = v; da.delta = h->d_delta; da.scalars = h->d_scalars; da.part = h->d_dl_part;
+  da.counter = h->d_counter + 1; da.n = np;
+  dl_prep_kernel<<<nblk, 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v);
+  ++h->launches;
+  VC_TRY(dl_matvec(h, v.vec, v.Hv, zpart));
+  da.mode = 0;
+  dl_dots_kernel<<<kDlBlocks, 256, 0, h->stream>>>(da);
+  ++h->launches;
+  VC_TRY(solve_and_update(h, v.D2, false));  // Gauss-Newton step with mu D^2 regularisation -> d_delta
+  da.mode = 1;
+  dl_dots_kernel<<<kDlBlocks, 256, 0, h->stream>>>(da);
+  dl_combine_kernel<<<nblk, 256, 0, h->stream>>>(h->d_ctl, v, h->d_delta, np);
+  h->launches += 2;
+  VC_TRY(dl_matvec(h, v.vec, v.Hv, zpart));
+  da.mode = 2;
+  dl_dots_kernel<<<kDlBlocks, 256, 0, h->stream>>>(da);
+  ++h->launches;
+  {  // x (+) S step into the trial buffer, step statistics
+    UpdateArgs ua;
+    ua.dp = dp; ua.b[0] = h->blk[0]; ua.b[1] = h->blk[1]; ua.ctl = h->d_ctl; ua.scale = h->d_scale; ua.D2x = v.D2;
+    ua.X = nullptr; ua.delta = h->d_delta; ua.state[0] = h->d_state[0]; ua.state[1] = h->d_state[1];
+    ua.step_part = h->d_red; ua.sepdiag = nullptr;
+    const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
+    if (dp.fd == 6) backsub_update_kernel<6><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
+    else backsub_update_kernel<9><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
+    ++h->launches;
+  }
+  VC_TRY(evaluate_into(h, 1, true, -1));
+  dl_decide_kernel<<<1, 32, 0, h->stream>>>(h->d_ctl, h->d_scalars);
+  ++h->launches;
+  if (weights) VC_TRY(imu_update_weights(h));
+  CUDA_TRY(h, cudaGetLastError());
+  return VCGPU_OK;
+}
+
 // one trust-region iteration, enqueued (no host wait)
 static int enqueue_iteration(vcgpu_handle* h, bool weights) {
+  if (h->opts.strategy == 1) return enqueue_dogleg_iteration(h, weights);
   if (mega_applies(h)) return mega_launch(h, 1);
   VC_TRY(solve_and_update(h, nullptr, false));
   VC_TRY(evaluate_into(h, 1, true, 1));
@@ -334,7 +394,8 @@ static int enqueue_iteration(vcgpu_handle* h, bool weights) {
 // ------------------------------------------------------------------ the trust-region loop
 static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out, int fixed_iters) {
   VC_TRY(prepare(h));
-  if (h->opts.strategy != 0) return fail(h, VCGPU_ERR_INVALID, "DOGLEG strategy is not implemented on the device yet; use strategy 0 (LM)");
+  if (h->opts.strategy == 1 && h->nranks > 1)
+    return fail(h, VCGPU_ERR_INVALID, "the DOGLEG strategy runs on one GPU; frame-sharded solves use strategy 0 (LM)");
   const DevProblem& dp = h->dp;
   const vcgpu_options& o = h->opts;
   const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;

@@ -63,6 +63,9 @@ struct Ctl {
   double function_tol, gradient_tol, param_tol;
   double last_cost_change, last_rho, last_step_norm, last_cand_cost;
   double initial_cost;
+  // dogleg strategy state (vc_dogleg.cuh)
+  double dl_mu, dl_alpha, dl_g2, dl_gn2, dl_b, dl_step_norm, dl_model_change;
+  int dl_ok, pad2_;
 };
 
 // damping of LevenbergMarquardtStrategy::ComputeStep: D^2 = clamp(diag(J'J), 1e-6, 1e32) / radius,
@@ -169,6 +172,8 @@ struct vcgpu_handle {
   int dev_sms = 0, dev_smem_optin = 0;
   size_t mega_smem_set = 0;
   int mega_grid = 0, mega_warps = 0;  // 0 warps: does not fit / not supported, use the multi-launch engine
+  double* d_dl = nullptr;         // dogleg work vectors [6][nf*fd+G] + matvec partials
+  double* d_dl_part = nullptr;    // [kDlBlocks][4]
   double* d_scalars = nullptr;    // device scalars (see vcgpu.cu)
   double* h_scalars = nullptr;    // pinned mirror
   vc::Ctl* d_ctl = nullptr;       // device-resident trust-region state
