@@ -290,7 +290,7 @@ static int num_residuals(const vcgpu_handle* h) {
 
 // ------------------------------------------------------------------ persistent vision kernel
 static bool mega_applies(const vcgpu_handle* h) {
-  return h->mega_warps > 0 && h->opts.strategy == 0 && !h->dp.inertial && h->nranks == 1 && !h->materialize && !h->profiling && !h->multi_launch &&
+  return h->mega_warps > 0 && h->opts.strategy == 0 && !h->dp.inertial && (h->nranks == 1 || h->xchg_ready) && !h->materialize && !h->profiling && !h->multi_launch &&
          h->flags.visual && h->n_obs > 0;
 }
 // up to n_iters trust-region iterations in one cooperative launch (vc_mega.cuh)
@@ -304,6 +304,8 @@ static int mega_launch(vcgpu_handle* h, int n_iters) {
   ma.pw = h->d_pw; ma.pc = h->d_pc; ma.mask = h->d_mask; ma.scale = h->d_scale; ma.X = h->d_X;
   ma.partS = h->d_partS; ma.partC = h->d_partC; ma.totS = h->d_totS; ma.totC = h->d_totC; ma.delta = h->d_delta; ma.scalars = h->d_scalars;
   ma.n_iters = n_iters; ma.n_warps = h->mega_warps;
+  ma.rank = h->rank; ma.nranks = h->nranks;
+  for (int r = 0; r < kMaxRanks; ++r) ma.xbuf[r] = h->xchg_peer[r];
   ma.prof = h->phase_clocks ? h->d_prof : nullptr;
   void* args[] = {&ma};
   const size_t smem = mega_smem_doubles(dp.G, dp.n_cams, h->mega_warps) * sizeof(double);
@@ -481,6 +483,7 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
   float ms = 0;
   CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   const Ctl& c = *h->h_ctl;
+  if (c.done == kMegaCommFailed) return fail(h, VCGPU_ERR_COMM, "a peer GPU never reached the in-kernel exchange (2 s timeout)");
   vcgpu_summary sum;
   std::memset(&sum, 0, sizeof sum);
   sum.num_residuals = num_residuals(h);

@@ -187,6 +187,11 @@ struct vcgpu_handle {
   void* imu = nullptr;            // ImuDevHost (vc_imu_host.inl)
   // multi-GPU (one process per GPU; frames sharded; see vc_engine.inl)
   void* comm = nullptr;           // ncclComm_t
+  // peer-memory exchange of the persistent kernel (vc_mega.cuh): one 2 MiB buffer per rank, mapped into every
+  // rank of the node through CUDA IPC, written with NVLink peer stores from inside the kernel
+  double* xchg_local = nullptr;
+  double* xchg_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool xchg_ready = false;
   int rank = 0, nranks = 1;
   double* d_mg = nullptr;         // all-reduce buffer [G*G+G+6+nranks (+ 18*nranks)]
   double* d_sep = nullptr;        // [2][nranks*9]: summed diag(B) and g of the separator frames (sharded inertial runs)

@@ -36,6 +36,16 @@ constexpr int kSlabDoubles = kFusedCols * kSlabLd;     // one warp's tile
 constexpr int kWarpDoubles = kSlabDoubles + 48;        // + frame block (36) + frame gradient (6), padded
 constexpr int kGtabMax = 256;
 constexpr int kMegaPartExtra = 8;  // scalars appended to each CTA's partial slot
+// Frame-sharded runs (one process per GPU): every rank owns a 2 MiB exchange buffer that all ranks of the node
+// map (CUDA IPC).  Layout in doubles: Schur totals [2 parities][ranks][NS+8] at 0, packed camera blocks
+// [2][ranks][NP+8] at kXchgCOff, then 64-bit words at kXchgFlagOff: arrival flags S [ranks], C [ranks], the
+// exchange counters (S, C) and the local go/abort word.
+constexpr int kMaxRanks = 8;
+constexpr size_t kXchgBytes = 2u << 20;
+constexpr int kXchgCOff = 204800;
+constexpr int kXchgFlagOff = 221184;
+constexpr unsigned long long kXchgAbort = ~0ull;
+constexpr int kMegaCommFailed = 1000;  // Ctl::done value when a peer never showed up
 static_assert(kSlabLd % 16 == 4, "fragment loads need ld == 4 (mod 16)");
 enum { kPCost = 0, kPGf2, kPDotG, kPDotD, kPStep2, kPXnorm2, kPGfMax, kPNotPD };
 enum { kProfS = 0, kProfG, kProfU, kProfB, kProfD, kProfSync, kProfCount };
@@ -58,13 +68,15 @@ struct MegaArgs {
   double* scalars;       // kSc* of the last evaluated point (for the host)
   int n_iters;
   int n_warps;
+  int rank, nranks;          // frame shards; nranks > 1: totals are exchanged through xbuf
+  double* xbuf[kMaxRanks];   // exchange buffer of every rank (peer pointers; [rank] is local)
   unsigned long long* prof;  // [kProfCount] ns per phase (CTA 0), or null
 };
 
 __host__ __device__ inline size_t mega_smem_doubles(int G, int n_cams, int n_warps) {
   const size_t NS = static_cast<size_t>(G) * G + G;
   return static_cast<size_t>(n_warps) * (kWarpDoubles + n_cams * kCgStride) + 3 * NS + G + kMaxCams * (kCamStateStride + 9) +
-         kScCount + 8 * kMegaMaxWarps + sizeof(Ctl) / sizeof(double) + 8;
+         kScCount + 8 * kMegaMaxWarps + n_cams * kCgStride + kMegaPartExtra + sizeof(Ctl) / sizeof(double) + 8;
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -101,6 +113,97 @@ __device__ inline void mega_reduce_stage1(const double* part, int stride, int np
     }
     if (lane == 0) tot[e] = s0;
   }
+}
+
+// ---- frame-sharded runs: the two reductions of an iteration go across GPUs through peer memory ----
+// Publish: as mega_reduce_stage1, but the CTA-summed entry is stored into slot [parity][my rank] of EVERY rank's
+// exchange buffer (NVLink peer stores), followed by a system-scope fence.
+__device__ inline void mega_xchg_publish(const double* part, int stride, int nparts, int n, const MegaArgs& a, int off, int parity,
+                                         int max_a, int max_b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int e = blockIdx.x + warp * gridDim.x; e < n; e += nwarps * gridDim.x) {
+    const bool is_max = e == max_a || e == max_b;
+    const double* p = part + e;
+    double s0 = 0.0, s1 = 0.0;
+    int b = lane;
+    if (is_max) {
+      for (; b < nparts; b += 32) s0 = fmax(s0, __ldcg(p + static_cast<int64_t>(b) * stride));
+    } else {
+      for (; b + 32 < nparts; b += 64) {
+        s0 += __ldcg(p + static_cast<int64_t>(b) * stride);
+        s1 += __ldcg(p + static_cast<int64_t>(b + 32) * stride);
+      }
+      if (b < nparts) s0 += __ldcg(p + static_cast<int64_t>(b) * stride);
+      s0 += s1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double t = __shfl_xor_sync(0xffffffffu, s0, o);
+      s0 = is_max ? fmax(s0, t) : s0 + t;
+    }
+    if (lane < a.nranks) {
+      a.xbuf[lane][off + (parity * a.nranks + a.rank) * stride + e] = s0;
+      __threadfence_system();  // only the storing lanes pay for it
+    }
+  }
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Cross-GPU barrier after the local grid barrier.  Warp 0 of CTA 0: one system fence, then lane r tells rank r
+// "my slot for exchange `epoch` is complete" and waits for rank r's word (2 s timeout), one more system fence,
+// then a local go/abort word releases every CTA.  Returns false (in every thread of every CTA) if a peer never
+// arrived.
+__device__ inline bool mega_xchg_barrier(const MegaArgs& a, int flag_base, unsigned long long epoch, unsigned long long go_value) {
+  __shared__ int ok_s;
+  unsigned long long* lf = reinterpret_cast<unsigned long long*>(a.xbuf[a.rank] + kXchgFlagOff);
+  unsigned long long* go = lf + 2 * kMaxRanks + 2;
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    __threadfence_system();
+    bool ok = true;
+    if (lane < a.nranks) {
+      st_relaxed_sys(reinterpret_cast<unsigned long long*>(a.xbuf[lane] + kXchgFlagOff) + flag_base + a.rank, epoch);
+      const unsigned long long t0 = global_ns();
+      while (ld_relaxed_sys(lf + flag_base + lane) < epoch)
+        if (global_ns() - t0 > 2000000000ull) { ok = false; break; }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    if (lane == 0) st_release_gpu(go, ok ? go_value : kXchgAbort);
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    while ((v = ld_acquire_gpu(go)) < go_value) {}
+    ok_s = v != kXchgAbort ? 1 : 0;
+  }
+  __syncthreads();
+  const bool ok = ok_s != 0;
+  __syncthreads();
+  return ok;
+}
+// fixed-order total of entry e over the ranks' slots (local memory; the peers stored into it)
+__device__ __forceinline__ double mega_xchg_total(const MegaArgs& a, int off, int stride, int parity, int e, bool is_max) {
+  const double* p = a.xbuf[a.rank] + off + static_cast<size_t>(parity) * a.nranks * stride + e;
+  double s = 0.0;
+  for (int r = 0; r < a.nranks; ++r) {
+    const double v = __ldcg(p + static_cast<size_t>(r) * stride);
+    s = is_max ? fmax(s, v) : s + v;
+  }
+  return s;
 }
 
 // Reduced-system solve, one warp.  S: lower triangle [G][G] row-major followed by the right-hand side [G];
@@ -172,7 +275,8 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
   double* smRc = smCam + kMaxCams * kCamStateStride;                 // [kMaxCams][9]
   double* sc = smRc + kMaxCams * 9;                                  // [kScCount]
   double* wred = sc + kScCount;                                      // [kMegaMaxWarps][8] per-warp scalars
-  Ctl* ctl = reinterpret_cast<Ctl*>(wred + 8 * kMegaMaxWarps);
+  double* totc = wred + 8 * kMegaMaxWarps;                           // [NP + 8] packed camera blocks / scalars, grid (and rank) totals
+  Ctl* ctl = reinterpret_cast<Ctl*>(totc + NP + kMegaPartExtra);
   __shared__ int bad;
   __shared__ int2 gtab[kGtabMax];          // (start, count) of the observations of this CTA's (frame slot, camera) pairs
   __shared__ unsigned char tri_lut[128];   // packed lower-triangle index -> (row << 4 | col)
@@ -204,6 +308,14 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     const int g = a.group_of[c * nf + bid + k * nb];
     return g < 0 ? make_int2(0, 0) : make_int2(a.grp_start[g], a.grp_count[g]);
   };
+  const bool multi = a.nranks > 1;
+  unsigned long long epS = 0, epC = 0;  // exchanges done so far (all CTAs of all ranks count alike)
+  if (multi) {
+    const unsigned long long* lf = reinterpret_cast<const unsigned long long*>(a.xbuf[a.rank] + kXchgFlagOff);
+    epS = lf[2 * kMaxRanks];
+    epC = lf[2 * kMaxRanks + 1];
+  }
+  bool comm_failed = false;
   unsigned long long t_prev = 0;
   const bool prof = a.prof != nullptr && bid == 0 && tid == 0;
   if (prof) t_prev = global_ns();
@@ -338,12 +450,18 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     // ------------------------------------------------------------ G: reduced system, every CTA the same
     {
       double* S = Swork;  // [G*G] lower triangle, then rhs [G]
-      mega_reduce_stage1(a.partS, PS, nb, PS, a.totS, NS + kPNotPD, -1);
+      const int parS = static_cast<int>((epS + 1) & 1);
+      if (multi) mega_xchg_publish(a.partS, PS, nb, PS, a, 0, parS, NS + kPNotPD, -1);
+      else mega_reduce_stage1(a.partS, PS, nb, PS, a.totS, NS + kPNotPD, -1);
       mark(kProfG);
       grid.sync();
+      if (multi) {
+        ++epS;
+        if (!mega_xchg_barrier(a, 0, epS, epS + epC)) { comm_failed = true; break; }
+      }
       mark(kProfSync);
       for (int e = tid; e < NS; e += nthreads) {
-        const double p = __ldcg(a.totS + e);
+        const double p = multi ? mega_xchg_total(a, 0, PS, parS, e, false) : __ldcg(a.totS + e);
         if (e < G * G) {
           const int r = e / G, c = e - r * G;
           if (c > r) continue;
@@ -355,7 +473,10 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
           S[e] = -Ccur[e] * scg[r] + p;
         }
       }
-      if (tid == 0) { sc[kScNotPD] = __ldcg(a.totS + NS + kPNotPD); bad = 0; }
+      if (tid == 0) {
+        sc[kScNotPD] = multi ? mega_xchg_total(a, 0, PS, parS, NS + kPNotPD, true) : __ldcg(a.totS + NS + kPNotPD);
+        bad = 0;
+      }
       __syncthreads();
       if (warp == 0) {
         mega_chol_solve_smem(S, G, lane, dg, &bad);
@@ -396,7 +517,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
           }
         }
         __syncwarp();
-        if (bid == 0 && lane == 0) {  // the globals' share of the step statistics, counted once
+        if (bid == 0 && a.rank == 0 && lane == 0) {  // the globals' share of the step statistics, counted once
           for (int c = 0; c < n_cams; ++c) {
             const CamInfo& ci = a.dp.cams[c];
             const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
@@ -638,10 +759,19 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     // ------------------------------------------------------------ D: global block of the trial point, decision
     {
       double* Ctrial = Cacc + (1 - cur) * NS;
-      mega_reduce_stage1(a.partC, PC, nb, PC, a.totC, NP + kPGfMax, NP + kPNotPD);
+      const int parC = static_cast<int>((epC + 1) & 1);
+      if (multi) mega_xchg_publish(a.partC, PC, nb, PC, a, kXchgCOff, parC, NP + kPGfMax, NP + kPNotPD);
+      else mega_reduce_stage1(a.partC, PC, nb, PC, a.totC, NP + kPGfMax, NP + kPNotPD);
       mark(kProfD);
       grid.sync();
+      if (multi) {
+        ++epC;
+        if (!mega_xchg_barrier(a, kMaxRanks, epC, epS + epC)) { comm_failed = true; break; }
+      }
       mark(kProfSync);
+      for (int e = tid; e < PC; e += nthreads)
+        totc[e] = multi ? mega_xchg_total(a, kXchgCOff, PC, parC, e, e == NP + kPGfMax || e == NP + kPNotPD) : __ldcg(a.totC + e);
+      __syncthreads();
       for (int e = tid; e < NS; e += nthreads) {  // packed per-camera blocks -> dense C | gc
         const int r = e < G * G ? e / G : e - G * G;
         const int cc = e < G * G ? e - r * G : -1;
@@ -651,12 +781,12 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
           const int p = r - ci.goff;
           if (p < 0 || p >= 6 + ci.K) continue;
           if (cc < 0) {
-            v = __ldcg(a.totC + c * kCgStride + 105 + p);
+            v = totc[c * kCgStride + 105 + p];
           } else {
             const int q = cc - ci.goff;
             if (q >= 0 && q < 6 + ci.K) {
               const int hi = max(p, q), lo = min(p, q);
-              v = __ldcg(a.totC + c * kCgStride + hi * (hi + 1) / 2 + lo);
+              v = totc[c * kCgStride + hi * (hi + 1) / 2 + lo];
             }
           }
         }
@@ -665,9 +795,9 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
       __syncthreads();
       if (warp == 0) {
         double v[7];
-        v[0] = __ldcg(a.totC + NP + kPCost); v[1] = __ldcg(a.totC + NP + kPGf2); v[2] = __ldcg(a.totC + NP + kPDotG);
-        v[3] = __ldcg(a.totC + NP + kPDotD); v[4] = __ldcg(a.totC + NP + kPStep2); v[5] = __ldcg(a.totC + NP + kPXnorm2);
-        v[6] = __ldcg(a.totC + NP + kPGfMax);
+        v[0] = totc[NP + kPCost]; v[1] = totc[NP + kPGf2]; v[2] = totc[NP + kPDotG];
+        v[3] = totc[NP + kPDotD]; v[4] = totc[NP + kPStep2]; v[5] = totc[NP + kPXnorm2];
+        v[6] = totc[NP + kPGfMax];
         double g2 = 0.0, gm = 0.0;
         for (int q = lane; q < G; q += 32) {
           const double gv = Ctrial[G * G + q];
@@ -701,6 +831,12 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
   }
   // hand the accepted point's global block back to the multi-launch engine / inspection hooks
   __syncthreads();
+  if (multi && bid == 0 && tid == 0) {
+    unsigned long long* lf = reinterpret_cast<unsigned long long*>(a.xbuf[a.rank] + kXchgFlagOff);
+    lf[2 * kMaxRanks] = epS;
+    lf[2 * kMaxRanks + 1] = epC;
+    if (comm_failed) a.ctl->done = kMegaCommFailed;
+  }
   if (bid == 0) {
     const Blocks& bf = a.blk[ctl->cur];
     const double* Cf = Cacc + ctl->cur * NS;

@@ -90,6 +90,7 @@ static void stage_collect(vcgpu_handle* h) {  // call after a stream synchronise
       h->st_used[s] = false;
     }
 }
+static void xchg_release(vcgpu_handle* h);
 #include "vc_imu_host.inl"
 
 extern "C" int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2) {
@@ -205,6 +206,7 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
   dev_free(&h->d_mg); dev_free(&h->d_sep); dev_free(&h->d_dense);
+  xchg_release(h);
   if (h->comm) ncclCommDestroy(static_cast<ncclComm_t>(h->comm));
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -408,7 +410,7 @@ static int ensure_rJ(vcgpu_handle* h) {
 static int mega_prepare(vcgpu_handle* h) {
   const DevProblem& dp = h->dp;
   h->mega_warps = 0;
-  if (dp.inertial || h->nranks > 1) return VCGPU_OK;
+  if (dp.inertial || (h->nranks > 1 && !h->xchg_ready)) return VCGPU_OK;
   if (h->dev_sms == 0) {  // device attributes: once per handle
     int coop = 0, smem_optin = 0, sms = 0;
     CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
@@ -429,10 +431,13 @@ static int mega_prepare(vcgpu_handle* h) {
     if (per_sm < 1) return VCGPU_OK;
     h->mega_smem_set = smem;
   }
-  h->mega_grid = h->dev_sms;
-  h->mega_warps = warps;
   const size_t PS = static_cast<size_t>(dp.G) * dp.G + dp.G + vc::kMegaPartExtra;
   const size_t PC = static_cast<size_t>(dp.n_cams) * vc::kCgStride + vc::kMegaPartExtra;
+  if (h->nranks > 1 && (2 * h->nranks * PS > static_cast<size_t>(vc::kXchgCOff) ||
+                        2 * h->nranks * PC > static_cast<size_t>(vc::kXchgFlagOff - vc::kXchgCOff)))
+    return VCGPU_OK;  // the totals do not fit the exchange buffer: NCCL multi-launch engine
+  h->mega_grid = h->dev_sms;
+  h->mega_warps = warps;
   VC_TRY(dev_alloc(h, &h->d_partS, h->mega_grid * PS));
   VC_TRY(dev_alloc(h, &h->d_partC, h->mega_grid * PC));
   VC_TRY(dev_alloc(h, &h->d_totS, PS));
@@ -839,9 +844,73 @@ extern "C" int vcgpu_comm_unique_id(uint8_t id[VCGPU_UNIQUE_ID_BYTES]) {
   std::memcpy(id, &u, sizeof u);
   return VCGPU_OK;
 }
+// Map one exchange buffer per rank into every rank (CUDA IPC; all ranks are processes of one node) so the
+// persistent kernel can do its two per-iteration reductions with NVLink peer stores instead of NCCL launches.
+static void xchg_release(vcgpu_handle* h) {
+  if (h->xchg_local) {
+    if (h->comm && h->xchg_ready) {  // nobody may unmap / free while a peer can still store into it
+      int* d = nullptr;
+      if (cudaMalloc(&d, sizeof(int)) == cudaSuccess) {
+        cudaMemset(d, 0, sizeof(int));
+        ncclAllReduce(d, d, 1, ncclInt, ncclSum, static_cast<ncclComm_t>(h->comm), h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaFree(d);
+      }
+    }
+    for (int r = 0; r < 8; ++r) {
+      if (h->xchg_peer[r] && h->xchg_peer[r] != h->xchg_local) cudaIpcCloseMemHandle(h->xchg_peer[r]);
+      h->xchg_peer[r] = nullptr;
+    }
+    cudaFree(h->xchg_local);
+    h->xchg_local = nullptr;
+  }
+  h->xchg_ready = false;
+}
+static void xchg_setup(vcgpu_handle* h) {
+  xchg_release(h);
+  if (h->nranks < 2 || h->nranks > vc::kMaxRanks) return;
+  const ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
+  cudaIpcMemHandle_t mine;
+  cudaIpcMemHandle_t* d_all = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(h->nranks);
+  int ok = 1;
+  if (cudaMalloc(&h->xchg_local, vc::kXchgBytes) != cudaSuccess) { h->xchg_local = nullptr; ok = 0; }
+  if (ok && cudaMemset(h->xchg_local, 0, vc::kXchgBytes) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, h->xchg_local) != cudaSuccess) ok = 0;
+  if (!ok) std::memset(&mine, 0, sizeof mine);
+  // every rank takes part in the collectives below whatever happened above, so nobody is left waiting
+  if (cudaMalloc(&d_all, sizeof(cudaIpcMemHandle_t) * (h->nranks + 1)) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaMemcpy(d_all + h->nranks, &mine, sizeof mine, cudaMemcpyHostToDevice);
+  ncclAllGather(d_all + h->nranks, d_all, sizeof mine, ncclChar, comm, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaMemcpy(all.data(), d_all, sizeof(cudaIpcMemHandle_t) * h->nranks, cudaMemcpyDeviceToHost);
+  for (int r = 0; ok && r < h->nranks; ++r) {
+    if (r == h->rank) { h->xchg_peer[r] = h->xchg_local; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    h->xchg_peer[r] = static_cast<double*>(p);
+  }
+  // all ranks must agree: one failure anywhere disables the peer path everywhere
+  int* d_ok = reinterpret_cast<int*>(d_all);
+  cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice);
+  ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_all);
+  h->xchg_ready = ok != 0;
+  if (!h->xchg_ready) {
+    for (int r = 0; r < 8; ++r) {
+      if (h->xchg_peer[r] && h->xchg_peer[r] != h->xchg_local) cudaIpcCloseMemHandle(h->xchg_peer[r]);
+      h->xchg_peer[r] = nullptr;
+    }
+    cudaGetLastError();
+  }
+}
+
 extern "C" int vcgpu_comm_init(vcgpu_handle* h, const uint8_t id[VCGPU_UNIQUE_ID_BYTES], int rank, int nranks) {
   if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return h ? fail(h, VCGPU_ERR_INVALID, "comm_init: bad arguments") : VCGPU_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  xchg_release(h);
   if (h->comm) { ncclCommDestroy(static_cast<ncclComm_t>(h->comm)); h->comm = nullptr; }
   h->rank = rank;
   h->nranks = nranks;
@@ -853,5 +922,6 @@ extern "C" int vcgpu_comm_init(vcgpu_handle* h, const uint8_t id[VCGPU_UNIQUE_ID
   if (rc != ncclSuccess) return fail(h, VCGPU_ERR_COMM, std::string("ncclCommInitRank: ") + ncclGetErrorString(rc));
   h->comm = c;
   h->dirty = true;
+  xchg_setup(h);  // optional: without peer access the sharded solve stays on the NCCL multi-launch engine
   return VCGPU_OK;
 }

@@ -172,6 +172,8 @@ struct CalibratorFlags {
   int max_iters = 200;
   bool remove_outliers = true;
   double outlier_threshold = 2.0;
+  // 0 = LEVENBERG_MARQUARDT (device default), 1 = DOGLEG, the reference's solver_options_ (vicalibrator.h:151)
+  int trust_region_strategy = 0;
 };
 
 class ViCalibrator {
@@ -184,6 +186,7 @@ class ViCalibrator {
     vcgpu_default_options(&opts_);
     opts_.max_iters = FLAGS_.max_iters;  // vicalibrator.h:142
     opts_.function_tol = 1e-6;           // vicalibrator.h:149
+    opts_.strategy = FLAGS_.trust_region_strategy;
     Clear();
   }
   virtual ~ViCalibrator() {
