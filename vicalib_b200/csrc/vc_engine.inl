@@ -302,10 +302,10 @@ static int mega_launch(vcgpu_handle* h, int n_iters) {
   ma.blk[0] = h->blk[0]; ma.blk[1] = h->blk[1];
   ma.grp_start = h->d_grp_start; ma.grp_count = h->d_grp_count; ma.group_of = h->d_group_of;
   ma.pw = h->d_pw; ma.pc = h->d_pc; ma.mask = h->d_mask; ma.scale = h->d_scale; ma.X = h->d_X;
-  ma.partS = h->d_partS; ma.partC = h->d_partC; ma.totS = h->d_totS; ma.totC = h->d_totC; ma.delta = h->d_delta; ma.scalars = h->d_scalars;
+  ma.partS = h->d_partS; ma.partC = h->d_partC; ma.delta = h->d_delta; ma.scalars = h->d_scalars;
   ma.n_iters = n_iters; ma.n_warps = h->mega_warps;
   ma.rank = h->rank; ma.nranks = h->nranks;
-  for (int r = 0; r < kMaxRanks; ++r) ma.xbuf[r] = h->xchg_peer[r];
+  for (int r = 0; r < kMaxRanks; ++r) ma.xbuf[r] = reinterpret_cast<unsigned long long*>(h->xchg_peer[r]);
   ma.prof = h->phase_clocks ? h->d_prof : nullptr;
   void* args[] = {&ma};
   const size_t smem = mega_smem_doubles(dp.G, dp.n_cams, h->mega_warps) * sizeof(double);

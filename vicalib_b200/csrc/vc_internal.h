@@ -167,7 +167,6 @@ struct vcgpu_handle {
   unsigned* d_counter = nullptr;  // last-CTA tickets
   // persistent vision kernel (vc_mega.cuh)
   double *d_partS = nullptr, *d_partC = nullptr;  // [grid][G*G+G+8] / [grid][n_cams*kCgStride+8]
-  double *d_totS = nullptr, *d_totC = nullptr;    // [G*G+G+8] grid totals
   unsigned long long* d_prof = nullptr;
   int dev_sms = 0, dev_smem_optin = 0;
   size_t mega_smem_set = 0;
@@ -187,8 +186,8 @@ struct vcgpu_handle {
   void* imu = nullptr;            // ImuDevHost (vc_imu_host.inl)
   // multi-GPU (one process per GPU; frames sharded; see vc_engine.inl)
   void* comm = nullptr;           // ncclComm_t
-  // peer-memory exchange of the persistent kernel (vc_mega.cuh): one 2 MiB buffer per rank, mapped into every
-  // rank of the node through CUDA IPC, written with NVLink peer stores from inside the kernel
+  // totals buffer of the persistent kernel (vc_mega.cuh): one 4 MiB buffer per rank; in a sharded run it is mapped
+  // into every rank of the node through CUDA IPC and written with NVLink peer stores from inside the kernel
   double* xchg_local = nullptr;
   double* xchg_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool xchg_ready = false;

@@ -1,25 +1,28 @@
-// Persistent trust-region kernel for the vision-only problem on one GPU.
+// Persistent trust-region kernel for the vision-only problem (one GPU, or frame shards on several).
 //
 // One cooperative launch runs up to n_iters Levenberg-Marquardt iterations; one CTA per SM, every
 // frame owned by the same WARP of the same CTA for the whole solve (frame f -> CTA f mod grid, warp
-// (f / grid) mod warps).  An iteration is a chain of per-frame warp phases and three small
-// every-CTA phases, separated by four ~1 us grid barriers instead of six launches:
+// (f / grid) mod warps).  An iteration is a chain of per-frame warp phases and small every-CTA phases,
+// separated by grid barriers (~1.5 us) instead of launches:
 //
 //   S  per frame (warp):  L = chol(B_f + D_f),  X_f = (B_f + D_f)^-1 [E_f | g_f],  CTA partial of E^T X
-//   R1 entry e of the Schur sum is added up over the CTAs by one warp of CTA (e mod grid)      | barrier
-//   G  every CTA, redundantly: reduced system C + D - sum E^T X, Cholesky, globals' step       | barrier
+//   -- grid barrier; every CTA leaves here, together, if CTA 0 published "stop" (or a peer timed out)
+//   R1 entry e of the Schur sum is added up over the CTAs by one warp of CTA (e mod grid) and published:
+//      one GPU: plain totals + grid barrier; shards: tagged words into every rank's buffer, readers poll
+//   G  every CTA, redundantly: reduced system C + D - sum E^T X, Cholesky, globals' step
 //   U  per frame (warp):  back-substitution, x (+) step, step statistics; trial camera states
 //   B  per frame (warp): fused evaluate + Gram build at the trial point, 32 corners at a time through the
 //      warp's own shared-memory slab and FP64 DMMA (accumulators stay in registers across slabs; no block
 //      barrier anywhere in the phase); the camera blocks are accumulated per warp, packed per camera
-//   R2 packed camera blocks / scalars added up over the CTAs, as R1                            | barrier
-//   D  every CTA, redundantly: expands the packed blocks, takes the accept-reject decision of  | barrier
-//      Ceres' TrustRegionMinimizer (decide_step) on its own copy of Ctl
+//   -- grid barrier
+//   R2 packed camera blocks / scalars added up and published, as R1
+//   D  every CTA, redundantly: expands the packed blocks, takes the accept-reject decision of Ceres'
+//      TrustRegionMinimizer (decide_step) on its own copy of Ctl
 //
-// Every CTA reads bit-identical totals, so every CTA takes the same decision and the loop needs no
-// broadcast; all sums run in a fixed order (deterministic).  Replaces the body of ceres::Solve
-// (vicalibrator.h:956) for the staged vision solves; the inertial and the frame-sharded paths keep the
-// multi-launch engine (vc_engine.inl).
+// Every CTA (of every rank) reads bit-identical totals, so all take the same decision and the loop needs
+// no broadcast; all sums run in a fixed order (deterministic).  Replaces the body of ceres::Solve
+// (vicalibrator.h:956) for the staged vision solves; the inertial path keeps the multi-launch engine
+// (vc_engine.inl).
 #pragma once
 #include <cooperative_groups.h>
 
@@ -36,15 +39,16 @@ constexpr int kSlabDoubles = kFusedCols * kSlabLd;     // one warp's tile
 constexpr int kWarpDoubles = kSlabDoubles + 48;        // + frame block (36) + frame gradient (6), padded
 constexpr int kGtabMax = 256;
 constexpr int kMegaPartExtra = 8;  // scalars appended to each CTA's partial slot
-// Frame-sharded runs (one process per GPU): every rank owns a 2 MiB exchange buffer that all ranks of the node
-// map (CUDA IPC).  Layout in doubles: Schur totals [2 parities][ranks][NS+8] at 0, packed camera blocks
-// [2][ranks][NP+8] at kXchgCOff, then 64-bit words at kXchgFlagOff: arrival flags S [ranks], C [ranks], the
-// exchange counters (S, C) and the local go/abort word.
+// Totals buffer: every rank owns one (4 MiB); in a frame-sharded run (one process per GPU) all ranks of the
+// node map all of them (CUDA IPC).  A total is published as two 64-bit words {low half | tag}, {high half | tag}
+// (tag = exchange number): an 8-byte store is single-copy atomic, so a reader that sees both tags has the value —
+// no fence, no flag, no barrier between publishing and reading.  Layout in 64-bit words: Schur totals
+// [2 parities][ranks][NS+8][2] at 0, packed camera blocks [2][ranks][NP+8][2] at kXchgCOff, control words at
+// kXchgCtlOff: exchange counters (S, C), exit word (bit 0: CTA 0 decided to stop, bit 1: a reader timed out).
 constexpr int kMaxRanks = 8;
-constexpr size_t kXchgBytes = 2u << 20;
-constexpr int kXchgCOff = 204800;
-constexpr int kXchgFlagOff = 221184;
-constexpr unsigned long long kXchgAbort = ~0ull;
+constexpr size_t kXchgBytes = 4u << 20;
+constexpr int kXchgCOff = 409600;
+constexpr int kXchgCtlOff = 442368;
 constexpr int kMegaCommFailed = 1000;  // Ctl::done value when a peer never showed up
 static_assert(kSlabLd % 16 == 4, "fragment loads need ld == 4 (mod 16)");
 enum { kPCost = 0, kPGf2, kPDotG, kPDotD, kPStep2, kPXnorm2, kPGfMax, kPNotPD };
@@ -62,14 +66,12 @@ struct MegaArgs {
   double* X;             // [nf][6][G+1]
   double* partS;         // [grid][NS + 8]   Schur partial (lower triangle) | flags
   double* partC;         // [grid][n_cams*kCgStride + 8]   packed camera blocks | scalars
-  double* totS;          // [NS + 8] grid totals
-  double* totC;          // [n_cams*kCgStride + 8]
   double* delta;         // scaled step [nf*6 + G]
   double* scalars;       // kSc* of the last evaluated point (for the host)
   int n_iters;
   int n_warps;
-  int rank, nranks;          // frame shards; nranks > 1: totals are exchanged through xbuf
-  double* xbuf[kMaxRanks];   // exchange buffer of every rank (peer pointers; [rank] is local)
+  int rank, nranks;                      // frame shards (nranks = 1: a single GPU)
+  unsigned long long* xbuf[kMaxRanks];   // totals buffer of every rank (peer pointers; [rank] is local)
   unsigned long long* prof;  // [kProfCount] ns per phase (CTA 0), or null
 };
 
@@ -85,10 +87,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// Stage 1 of the fixed-order reduction of the CTAs' partial slots (the grid barrier is ~1 us, while every
-// CTA reading every slot would be ~50 MB of L2 traffic): entry e is added up over all CTAs by one warp of
-// CTA (e mod grid) into tot[e]; after the barrier every CTA reads tot[].  Entries max_a / max_b combine
-// with max instead of +.
+// Single GPU: entry e is added up over the CTAs by one warp of CTA (e mod grid) into tot[e]; a grid barrier
+// later every CTA reads tot[] (measured 2 us per iteration faster than polling tagged words when nobody is remote).
 __device__ inline void mega_reduce_stage1(const double* part, int stride, int nparts, int n, double* tot, int max_a, int max_b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int e = blockIdx.x + warp * gridDim.x; e < n; e += nwarps * gridDim.x) {
@@ -115,11 +115,11 @@ __device__ inline void mega_reduce_stage1(const double* part, int stride, int np
   }
 }
 
-// ---- frame-sharded runs: the two reductions of an iteration go across GPUs through peer memory ----
-// Publish: as mega_reduce_stage1, but the CTA-summed entry is stored into slot [parity][my rank] of EVERY rank's
-// exchange buffer (NVLink peer stores), followed by a system-scope fence.
-__device__ inline void mega_xchg_publish(const double* part, int stride, int nparts, int n, const MegaArgs& a, int off, int parity,
-                                         int max_a, int max_b) {
+// ---- the two reductions of an iteration: CTA partials -> totals (over the CTAs and, sharded, over the GPUs) ----
+// Publish: entry e is added up over this GPU's CTAs by one warp of CTA (e mod grid) — fixed order — and stored,
+// tagged, into slot [parity][my rank][e] of EVERY rank's totals buffer (lane r -> rank r; NVLink peer stores).
+__device__ inline void mega_publish(const double* part, int stride, int nparts, int n, const MegaArgs& a, int off, int parity,
+                                    unsigned tag, int max_a, int max_b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int e = blockIdx.x + warp * gridDim.x; e < n; e += nwarps * gridDim.x) {
     const bool is_max = e == max_a || e == max_b;
@@ -142,65 +142,40 @@ __device__ inline void mega_xchg_publish(const double* part, int stride, int npa
       s0 = is_max ? fmax(s0, t) : s0 + t;
     }
     if (lane < a.nranks) {
-      a.xbuf[lane][off + (parity * a.nranks + a.rank) * stride + e] = s0;
-      __threadfence_system();  // only the storing lanes pay for it
+      const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(s0));
+      const unsigned long long hi_tag = static_cast<unsigned long long>(tag) << 32;
+      unsigned long long* w = a.xbuf[lane] + off + 2 * (static_cast<size_t>(parity * a.nranks + a.rank) * stride + e);
+      asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"((bits & 0xffffffffull) | hi_tag),
+                   "l"((bits >> 32) | hi_tag)
+                   : "memory");
     }
   }
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// Cross-GPU barrier after the local grid barrier.  Warp 0 of CTA 0: one system fence, then lane r tells rank r
-// "my slot for exchange `epoch` is complete" and waits for rank r's word (2 s timeout), one more system fence,
-// then a local go/abort word releases every CTA.  Returns false (in every thread of every CTA) if a peer never
-// arrived.
-__device__ inline bool mega_xchg_barrier(const MegaArgs& a, int flag_base, unsigned long long epoch, unsigned long long go_value) {
-  __shared__ int ok_s;
-  unsigned long long* lf = reinterpret_cast<unsigned long long*>(a.xbuf[a.rank] + kXchgFlagOff);
-  unsigned long long* go = lf + 2 * kMaxRanks + 2;
-  const int lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x < 32) {
-    __threadfence_system();
-    bool ok = true;
-    if (lane < a.nranks) {
-      st_relaxed_sys(reinterpret_cast<unsigned long long*>(a.xbuf[lane] + kXchgFlagOff) + flag_base + a.rank, epoch);
-      const unsigned long long t0 = global_ns();
-      while (ld_relaxed_sys(lf + flag_base + lane) < epoch)
-        if (global_ns() - t0 > 2000000000ull) { ok = false; break; }
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    __threadfence_system();
-    if (lane == 0) st_release_gpu(go, ok ? go_value : kXchgAbort);
-  }
-  if (threadIdx.x == 0) {
-    unsigned long long v;
-    while ((v = ld_acquire_gpu(go)) < go_value) {}
-    ok_s = v != kXchgAbort ? 1 : 0;
-  }
-  __syncthreads();
-  const bool ok = ok_s != 0;
-  __syncthreads();
-  return ok;
-}
-// fixed-order total of entry e over the ranks' slots (local memory; the peers stored into it)
-__device__ __forceinline__ double mega_xchg_total(const MegaArgs& a, int off, int stride, int parity, int e, bool is_max) {
-  const double* p = a.xbuf[a.rank] + off + static_cast<size_t>(parity) * a.nranks * stride + e;
+// Read: the total of entry e over the ranks, in rank order; spins until every rank's words carry `tag`.
+// A reader that waits longer than 2 s sets the abort bit of the exit word and gives up (the value is then junk;
+// every CTA leaves the loop together at the next grid barrier).
+__device__ inline double mega_total(const MegaArgs& a, int off, int stride, int parity, unsigned tag, int e, bool is_max) {
+  unsigned long long* ctlw = a.xbuf[a.rank] + kXchgCtlOff;
+  const unsigned long long* w = a.xbuf[a.rank] + off + 2 * (static_cast<size_t>(parity) * a.nranks * stride + e);
   double s = 0.0;
-  for (int r = 0; r < a.nranks; ++r) {
-    const double v = __ldcg(p + static_cast<size_t>(r) * stride);
+  for (int r = 0; r < a.nranks; ++r, w += 2 * static_cast<size_t>(stride)) {
+    unsigned long long w0, w1;
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(w) : "memory");
+      if (static_cast<unsigned>(w0 >> 32) == tag && static_cast<unsigned>(w1 >> 32) == tag) break;
+      __nanosleep(polls < 8 ? 100 : 400);  // thousands of threads poll: keep the L2 free for the publishers
+      if ((++polls & 1023u) == 0) {
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 2000000000ull || (*reinterpret_cast<volatile unsigned long long*>(ctlw + 2) & 2ull)) {
+          atomicOr(ctlw + 2, 2ull);
+          return 0.0;
+        }
+      }
+    }
+    const double v = __longlong_as_double(static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32)));
     s = is_max ? fmax(s, v) : s + v;
   }
   return s;
@@ -281,6 +256,8 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
   __shared__ int2 gtab[kGtabMax];          // (start, count) of the observations of this CTA's (frame slot, camera) pairs
   __shared__ unsigned char tri_lut[128];   // packed lower-triangle index -> (row << 4 | col)
   const double* scg = a.scale + nfp;
+  unsigned long long* ctlw = a.xbuf[a.rank] + kXchgCtlOff;  // [0] S exchanges, [1] C exchanges, [2] exit word
+  __shared__ unsigned long long exit_s;
 
   if (tid == 0) *ctl = *a.ctl;
   const bool use_gtab = nk * n_cams <= kGtabMax;
@@ -297,6 +274,10 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
   }
   __syncthreads();
   if (ctl->done) return;
+  if (bid == 0 && tid == 0 && !(ctlw[2] & 2ull)) {  // the stop bit of the previous launch; the abort bit is sticky
+    ctlw[2] = 0;
+    __threadfence();
+  }
   {
     const Blocks& b0 = a.blk[ctl->cur];
     double* C0 = Cacc + ctl->cur * NS;
@@ -308,14 +289,8 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     const int g = a.group_of[c * nf + bid + k * nb];
     return g < 0 ? make_int2(0, 0) : make_int2(a.grp_start[g], a.grp_count[g]);
   };
-  const bool multi = a.nranks > 1;
-  unsigned long long epS = 0, epC = 0;  // exchanges done so far (all CTAs of all ranks count alike)
-  if (multi) {
-    const unsigned long long* lf = reinterpret_cast<const unsigned long long*>(a.xbuf[a.rank] + kXchgFlagOff);
-    epS = lf[2 * kMaxRanks];
-    epC = lf[2 * kMaxRanks + 1];
-  }
-  bool comm_failed = false;
+  const bool sharded = a.nranks > 1;
+  unsigned epS = static_cast<unsigned>(ctlw[0]), epC = static_cast<unsigned>(ctlw[1]);  // same on every CTA of every rank
   unsigned long long t_prev = 0;
   const bool prof = a.prof != nullptr && bid == 0 && tid == 0;
   if (prof) t_prev = global_ns();
@@ -329,7 +304,9 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
 
   for (int it = 0; it < a.n_iters; ++it) {
     __syncthreads();
-    if (ctl->done) break;
+    // A CTA never leaves the loop on its own: it idles through phase S and leaves with everybody else right
+    // after the next grid barrier, on the word CTA 0 published (so a junk total can never split the grid).
+    const bool skip = ctl->done != 0;
     const int cur = ctl->cur;
     const Blocks& bc = a.blk[cur];
     const Blocks& bt = a.blk[1 - cur];
@@ -340,7 +317,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     double notpd = 0.0;
 
     // ------------------------------------------------------------ S: per-frame solves + Schur partial
-    {
+    if (!skip) {
       double* Sacc = Swork;
       for (int k = tid; k < NS; k += nthreads) Sacc[k] = 0.0;
       for (int base = 0; base < nk; base += nwarps) {
@@ -445,23 +422,28 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     }
     mark(kProfS);
     grid.sync();
+    if (tid == 0) exit_s = *reinterpret_cast<volatile unsigned long long*>(ctlw + 2);
+    __syncthreads();
+    if (exit_s) break;
     mark(kProfSync);
 
     // ------------------------------------------------------------ G: reduced system, every CTA the same
     {
       double* S = Swork;  // [G*G] lower triangle, then rhs [G]
-      const int parS = static_cast<int>((epS + 1) & 1);
-      if (multi) mega_xchg_publish(a.partS, PS, nb, PS, a, 0, parS, NS + kPNotPD, -1);
-      else mega_reduce_stage1(a.partS, PS, nb, PS, a.totS, NS + kPNotPD, -1);
-      mark(kProfG);
-      grid.sync();
-      if (multi) {
-        ++epS;
-        if (!mega_xchg_barrier(a, 0, epS, epS + epC)) { comm_failed = true; break; }
+      ++epS;
+      const int parS = static_cast<int>(epS & 1);
+      double* totS = reinterpret_cast<double*>(a.xbuf[a.rank]);  // single GPU: plain totals in the same buffer
+      if (sharded) {
+        mega_publish(a.partS, PS, nb, PS, a, 0, parS, epS, NS + kPNotPD, -1);
+      } else {
+        mega_reduce_stage1(a.partS, PS, nb, PS, totS, NS + kPNotPD, -1);
+        mark(kProfG);
+        grid.sync();
+        mark(kProfSync);
       }
-      mark(kProfSync);
       for (int e = tid; e < NS; e += nthreads) {
-        const double p = multi ? mega_xchg_total(a, 0, PS, parS, e, false) : __ldcg(a.totS + e);
+        if (e < G * G && e % G > e / G) continue;  // lower triangle only
+        const double p = sharded ? mega_total(a, 0, PS, parS, epS, e, false) : __ldcg(totS + e);
         if (e < G * G) {
           const int r = e / G, c = e - r * G;
           if (c > r) continue;
@@ -474,7 +456,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
         }
       }
       if (tid == 0) {
-        sc[kScNotPD] = multi ? mega_xchg_total(a, 0, PS, parS, NS + kPNotPD, true) : __ldcg(a.totS + NS + kPNotPD);
+        sc[kScNotPD] = sharded ? mega_total(a, 0, PS, parS, epS, NS + kPNotPD, true) : __ldcg(totS + NS + kPNotPD);
         bad = 0;
       }
       __syncthreads();
@@ -759,18 +741,19 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
     // ------------------------------------------------------------ D: global block of the trial point, decision
     {
       double* Ctrial = Cacc + (1 - cur) * NS;
-      const int parC = static_cast<int>((epC + 1) & 1);
-      if (multi) mega_xchg_publish(a.partC, PC, nb, PC, a, kXchgCOff, parC, NP + kPGfMax, NP + kPNotPD);
-      else mega_reduce_stage1(a.partC, PC, nb, PC, a.totC, NP + kPGfMax, NP + kPNotPD);
-      mark(kProfD);
-      grid.sync();
-      if (multi) {
-        ++epC;
-        if (!mega_xchg_barrier(a, kMaxRanks, epC, epS + epC)) { comm_failed = true; break; }
+      ++epC;
+      const int parC = static_cast<int>(epC & 1);
+      double* totC = reinterpret_cast<double*>(a.xbuf[a.rank] + kXchgCOff);
+      if (sharded) {
+        mega_publish(a.partC, PC, nb, PC, a, kXchgCOff, parC, epC, NP + kPGfMax, NP + kPNotPD);
+      } else {
+        mega_reduce_stage1(a.partC, PC, nb, PC, totC, NP + kPGfMax, NP + kPNotPD);
+        mark(kProfD);
+        grid.sync();
+        mark(kProfSync);
       }
-      mark(kProfSync);
       for (int e = tid; e < PC; e += nthreads)
-        totc[e] = multi ? mega_xchg_total(a, kXchgCOff, PC, parC, e, e == NP + kPGfMax || e == NP + kPNotPD) : __ldcg(a.totC + e);
+        totc[e] = sharded ? mega_total(a, kXchgCOff, PC, parC, epC, e, e == NP + kPGfMax || e == NP + kPNotPD) : __ldcg(totC + e);
       __syncthreads();
       for (int e = tid; e < NS; e += nthreads) {  // packed per-camera blocks -> dense C | gc
         const int r = e < G * G ? e / G : e - G * G;
@@ -819,6 +802,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
           sc[kScXnorm2] = v[5];
           decide_step(ctl, sc, 1);
           if (bid == 0) {
+            if (ctl->done) atomicOr(ctlw + 2, 1ull);
             *a.ctl = *ctl;
             for (int q = 0; q < 8; ++q) a.scalars[q] = sc[q];
             *bt.cost = v[0];
@@ -831,11 +815,10 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
   }
   // hand the accepted point's global block back to the multi-launch engine / inspection hooks
   __syncthreads();
-  if (multi && bid == 0 && tid == 0) {
-    unsigned long long* lf = reinterpret_cast<unsigned long long*>(a.xbuf[a.rank] + kXchgFlagOff);
-    lf[2 * kMaxRanks] = epS;
-    lf[2 * kMaxRanks + 1] = epC;
-    if (comm_failed) a.ctl->done = kMegaCommFailed;
+  if (bid == 0 && tid == 0) {
+    ctlw[0] = epS;
+    ctlw[1] = epC;
+    if (*reinterpret_cast<volatile unsigned long long*>(ctlw + 2) & 2ull) a.ctl->done = kMegaCommFailed;
   }
   if (bid == 0) {
     const Blocks& bf = a.blk[ctl->cur];

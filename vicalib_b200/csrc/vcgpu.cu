@@ -202,7 +202,7 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_blk_mem[0]); dev_free(&h->d_blk_mem[1]);
   dev_free(&h->d_scale); dev_free(&h->d_X); dev_free(&h->d_Spart); dev_free(&h->d_delta);
   dev_free(&h->d_red); dev_free(&h->d_scalars); dev_free(&h->d_Ssum); dev_free(&h->d_red_part); dev_free(&h->d_counter);
-  dev_free(&h->d_dl); dev_free(&h->d_dl_part); dev_free(&h->d_partS); dev_free(&h->d_partC); dev_free(&h->d_totS); dev_free(&h->d_totC); dev_free(&h->d_prof);
+  dev_free(&h->d_dl); dev_free(&h->d_dl_part); dev_free(&h->d_partS); dev_free(&h->d_partC); dev_free(&h->d_prof);
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
   dev_free(&h->d_mg); dev_free(&h->d_sep); dev_free(&h->d_dense);
@@ -433,15 +433,20 @@ static int mega_prepare(vcgpu_handle* h) {
   }
   const size_t PS = static_cast<size_t>(dp.G) * dp.G + dp.G + vc::kMegaPartExtra;
   const size_t PC = static_cast<size_t>(dp.n_cams) * vc::kCgStride + vc::kMegaPartExtra;
-  if (h->nranks > 1 && (2 * h->nranks * PS > static_cast<size_t>(vc::kXchgCOff) ||
-                        2 * h->nranks * PC > static_cast<size_t>(vc::kXchgFlagOff - vc::kXchgCOff)))
-    return VCGPU_OK;  // the totals do not fit the exchange buffer: NCCL multi-launch engine
+  if (4 * h->nranks * PS > static_cast<size_t>(vc::kXchgCOff) ||
+      4 * h->nranks * PC > static_cast<size_t>(vc::kXchgCtlOff - vc::kXchgCOff))
+    return VCGPU_OK;  // the totals do not fit the totals buffer: multi-launch engine
+  if (!h->xchg_local) {  // single GPU: the totals buffer is local only
+    void* p = nullptr;
+    CUDA_TRY(h, cudaMalloc(&p, vc::kXchgBytes));
+    CUDA_TRY(h, cudaMemset(p, 0, vc::kXchgBytes));
+    h->xchg_local = static_cast<double*>(p);
+    h->xchg_peer[0] = h->xchg_local;
+  }
   h->mega_grid = h->dev_sms;
   h->mega_warps = warps;
   VC_TRY(dev_alloc(h, &h->d_partS, h->mega_grid * PS));
   VC_TRY(dev_alloc(h, &h->d_partC, h->mega_grid * PC));
-  VC_TRY(dev_alloc(h, &h->d_totS, PS));
-  VC_TRY(dev_alloc(h, &h->d_totC, PC));
   CUDA_TRY(h, cudaMemsetAsync(h->d_partS, 0, h->mega_grid * PS * sizeof(double), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_partC, 0, h->mega_grid * PC * sizeof(double), h->stream));
   VC_TRY(dev_alloc(h, &h->d_prof, vc::kProfCount));
