@@ -8,11 +8,14 @@ arrow system, update the state, evaluate residuals + Jacobians at the trial poin
 block normal equations, accept/reject.  One JSON line is printed by rank 0.
 
 * value      — K iterations / device time (CUDA events on the library's launch stream, max over
-               ranks); inputs resident in HBM; L2 flushed before every iteration (working set of
-               config 2 is 102 MB < 126 MB L2) unless --no-flush.
+               ranks); inputs resident in HBM; L2 flushed before every iteration (config 2's inputs
+               are 12 MB, far below the 126 MB L2) unless --no-flush.  The single-/multi-GPU vision
+               solve runs in the persistent kernel: one launch per iteration in the flushed region,
+               one per solve otherwise (config.value_no_flush).
 * e2e        — the same metric through the C-ABI with HOST buffers: upload (set_* calls), K
                iterations, state read-back, all inside the timed region (wall clock).
-* roofline   — dominant kernel stage: algorithmic bytes per launch / its CUDA-event duration.
+* roofline   — dominant kernel: useful FP64 flops per launch / its duration against the FP64
+               throughput measured live (the path is FP64-pipe bound); HBM view beside it.
 * cpu_baseline — the CPU oracle (port of the reference's Ceres path) on a bounded sample.
 * --impl reference — the oracle port on all host threads (Ceres cannot be built here).
 """
@@ -92,12 +95,6 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def shard_problem(p, rank, world):
-    """Contiguous frame shard of a vision-only problem (weak scaling: every rank gets the full
-    BASELINE workload's worth of frames; frames are independent given the globals)."""
-    return p  # single-GPU until the sharded all-reduce path lands
 
 
 def algorithmic_bytes_per_obs(K):

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include <nccl.h>
 
@@ -254,16 +255,31 @@ extern "C" int vcgpu_set_frames(vcgpu_handle* h, int n, const double* T_wp, cons
   h->state_dirty = true;
   return VCGPU_OK;
 }
+// large host-to-pinned copies are split over a few threads (one core copies ~12 GB/s; the DMA that follows ~50 GB/s)
+template <class V, class T>
+static void assign_parallel(V* dst, const T* src, size_t n) {
+  dst->resize(n);
+  const size_t bytes = n * sizeof(T);
+  const int nt = bytes < (2u << 20) ? 1 : 4;
+  if (nt == 1) { if (n) std::memcpy(dst->data(), src, bytes); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t) {
+    const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    th.emplace_back([=]() { std::memcpy(dst->data() + lo, src + lo, (hi - lo) * sizeof(T)); });
+  }
+  for (auto& x : th) x.join();
+}
+
 extern "C" int vcgpu_set_observations(vcgpu_handle* h, int64_t n, const int32_t* frame_id, const int32_t* cam_id,
                                       const double* p_w, const double* p_c) {
   if (!h || n < 0 || (n > 0 && (!frame_id || !cam_id || !p_w || !p_c)))
     return h ? fail(h, VCGPU_ERR_INVALID, "set_observations: bad arguments") : VCGPU_ERR_INVALID;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // an earlier upload may still be reading the page-locked copies
   h->n_obs_all = n;
-  h->h_obs_frame.assign(frame_id, frame_id + n);
-  h->h_obs_cam.assign(cam_id, cam_id + n);
-  h->h_pw.assign(p_w, p_w + 3 * n);
-  h->h_pc.assign(p_c, p_c + 2 * n);
+  assign_parallel(&h->h_obs_frame, frame_id, static_cast<size_t>(n));
+  assign_parallel(&h->h_obs_cam, cam_id, static_cast<size_t>(n));
+  assign_parallel(&h->h_pw, p_w, 3 * static_cast<size_t>(n));
+  assign_parallel(&h->h_pc, p_c, 2 * static_cast<size_t>(n));
   h->h_active.assign(n, 1);
   h->dirty = true;
   return VCGPU_OK;
