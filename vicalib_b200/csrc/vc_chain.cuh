@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs
   __shared__ int bad;
   if (a.ctl->done) return;
   const ChainLevel& L = a.cur;
-  const int j = blockIdx.x, s = j * c, n = L.n, n_eff = L.n - L.ghost;
+  const int j = blockIdx.x, s = j * c, n_eff = L.n - L.ghost;
   const int nsep = (n_eff + c - 1) / c;
   const bool toGhost = L.ghost && !(s + c < n_eff);  // this chunk's right separator is the ghost node
   const bool hasR = s + c < n_eff || toGhost;

@@ -99,7 +99,7 @@ static int eval_reproj(vcgpu_handle* h, int which, bool jac, bool apply_loss, co
 // ------------------------------------------------------------------ evaluation pass
 // which = 0: the accepted point (buffers[cur]); which = 1: the trial point (buffers[1-cur]).
 // Residuals, Jacobians and block normal equations land in blk[buffer]; cost / gradient norms (and
-// the step reductions when with_step) land in d_scalars for decide_kernel.
+// the step reductions when with_step) land in d_scalars for decide_step.
 static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_mode, const double* D2x = nullptr) {
   const DevProblem& dp = h->dp;
   const bool visual = h->flags.visual && h->n_obs > 0;

@@ -225,33 +225,4 @@ __global__ void __launch_bounds__(128) imu_accumulate_kernel(ImuAccArgs a) {
   }
 }
 
-// level-1 partial of the IMU global block, folded into the same Cpart buffers the cameras use
-struct ImuReduceArgs {
-  DevProblem dp;
-  const double* Cg;
-  double* Cpart;
-  int ni;
-};
-__global__ void __launch_bounds__(256) imu_reduce_globals_kernel(ImuReduceArgs a) {
-  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G, io = a.dp.imu_goff;
-  const int lo = static_cast<int>(static_cast<int64_t>(a.ni) * blockIdx.x / gridDim.x);
-  const int hi = static_cast<int>(static_cast<int64_t>(a.ni) * (blockIdx.x + 1) / gridDim.x);
-  double* out = a.Cpart + static_cast<int64_t>(blockIdx.x) * NS;
-  for (int q = tid; q < 135; q += 256) {
-    double s = 0.0;
-    const double* p = a.Cg + static_cast<int64_t>(lo) * kImuCgStride + q;
-    for (int k = lo; k < hi; ++k, p += kImuCgStride) s += *p;
-    if (q < 120) {
-      int i = static_cast<int>((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
-      while ((i + 1) * (i + 2) / 2 <= q) ++i;
-      while (i * (i + 1) / 2 > q) --i;
-      const int j = q - i * (i + 1) / 2;
-      out[(io + i) * G + io + j] = s;
-      out[(io + j) * G + io + i] = s;
-    } else {
-      out[G * G + io + (q - 120)] = s;
-    }
-  }
-}
-
 }  // namespace vc

@@ -151,16 +151,6 @@ static int imu_accumulate(vcgpu_handle* h, int which) {
   CUDA_TRY(h, cudaGetLastError());
   return VCGPU_OK;
 }
-static int imu_reduce_globals(vcgpu_handle* h) {
-  vc::ImuDev* d = imu_dev(h);
-  ImuReduceArgs a;
-  a.dp = h->dp; a.Cg = d->Cg; a.Cpart = h->d_Cpart; a.ni = h->dp.n_frames - 1;
-  imu_reduce_globals_kernel<<<kReduceBlocks, 256, 0, h->stream>>>(a);
-  ++h->launches;
-  CUDA_TRY(h, cudaGetLastError());
-  return VCGPU_OK;
-}
-
 // forward elimination of the frame chain; the summed Schur partials land in Ssum
 static int imu_chain_eliminate(vcgpu_handle* h, const double* D2x) {
   vc::ImuDev* d = imu_dev(h);

@@ -7,9 +7,10 @@
 //   global_solve_kernel   dense Cholesky of the reduced (globals) system
 //   backsub_update_kernel back-substitution + x (+) delta into the trial state
 //   fused_build_kernel    residuals + Jacobians + block normal equations at the trial point
-//   reduce_globals_kernel / finalize_globals_kernel   global blocks, cost, gradient norms
-//   decide_kernel         accept / reject, trust-region radius, termination tests — on the device
-// Every kernel picks its double buffer through Ctl::cur, so the host only enqueues.
+//   reduce_finalize_kernel  global blocks, cost, gradient norms and — in the CTA that arrives last —
+//                         decide_step: accept / reject, trust-region radius, termination tests, on the device
+// Every kernel picks its double buffer through Ctl::cur, so the host only enqueues.  The single- and
+// multi-GPU vision solves run the same phases inside one persistent kernel instead (vc_mega.cuh).
 // The reference does all of this inside ceres::Solve (vicalibrator.h:956).
 #pragma once
 #include "vc_internal.h"
@@ -19,7 +20,7 @@ namespace vc {
 
 __device__ __forceinline__ int pick(const Ctl* c, int which) { return which ? 1 - c->cur : c->cur; }
 
-// scalars produced by the evaluation / step kernels for decide_kernel (indices into d_scalars)
+// scalars produced by the evaluation / step kernels for decide_step (indices into d_scalars)
 enum {
   kScCost = 0,      // robust cost of the evaluated point
   kScGmax = 1,      // gradient max norm
@@ -217,129 +218,6 @@ __global__ void __launch_bounds__(kBuildThreads) build_frames_kernel(BuildArgs a
   for (int k = tid; k < FD; k += kBuildThreads) out.gf[static_cast<int64_t>(f) * FD + k] = smg[k];
 }
 
-// ---------------------------------------------------------------- global blocks: level 1
-struct ReduceArgs {
-  DevProblem dp;
-  const double* Cg;
-  double* Cpart;  // [kReduceBlocks][G*G+G]
-};
-__global__ void __launch_bounds__(256) reduce_globals_kernel(ReduceArgs a) {
-  extern __shared__ double acc[];
-  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G;
-  for (int k = tid; k < NS; k += blockDim.x) acc[k] = 0.0;
-  __syncthreads();
-  for (int c = 0; c < a.dp.n_cams; ++c) {
-    const CamInfo& ci = a.dp.cams[c];
-    const int NG = 6 + ci.K, nsym = NG * (NG + 1) / 2;
-    const int lo = static_cast<int>(static_cast<int64_t>(ci.n_groups) * blockIdx.x / gridDim.x);
-    const int hi = static_cast<int>(static_cast<int64_t>(ci.n_groups) * (blockIdx.x + 1) / gridDim.x);
-    for (int e = tid; e < nsym + NG; e += blockDim.x) {
-      int src, dst, dst2 = -1;
-      if (e < nsym) {
-        int i = static_cast<int>((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        while (i * (i + 1) / 2 > e) --i;
-        const int j = e - i * (i + 1) / 2;
-        src = e;
-        dst = (ci.goff + i) * G + ci.goff + j;
-        if (i != j) dst2 = (ci.goff + j) * G + ci.goff + i;
-      } else {
-        src = 105 + (e - nsym);
-        dst = G * G + ci.goff + (e - nsym);
-      }
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      const double* p = a.Cg + static_cast<int64_t>(ci.group_start + lo) * kCgStride + src;
-      int g = lo;
-      for (; g + 3 < hi; g += 4, p += 4 * kCgStride) {
-        s0 += p[0];
-        s1 += p[kCgStride];
-        s2 += p[2 * kCgStride];
-        s3 += p[3 * kCgStride];
-      }
-      for (; g < hi; ++g, p += kCgStride) s0 += *p;
-      const double s = (s0 + s1) + (s2 + s3);
-      acc[dst] += s;
-      if (dst2 >= 0) acc[dst2] += s;
-    }
-    __syncthreads();
-  }
-  double* out = a.Cpart + static_cast<int64_t>(blockIdx.x) * NS;
-  for (int k = tid; k < NS; k += blockDim.x) out[k] = acc[k];
-}
-
-// ---------------------------------------------------------------- global blocks: level 2 + cost + norms
-struct FinalizeArgs {
-  DevProblem dp;
-  const Ctl* ctl;
-  int which;
-  const double* Cpart;
-  const double* cost_part;
-  int n_cost_part;
-  const double* imu_cost_part;
-  int n_imu_cost_part;
-  const double* step_part;  // [n_step_part][4] from backsub_update (may be null)
-  int n_step_part;
-  Blocks out[2];
-  double* scalars;
-};
-constexpr int kFinalizeThreads = 1024;
-__global__ void __launch_bounds__(kFinalizeThreads) finalize_globals_kernel(FinalizeArgs a) {
-  // 6 sums (cost, |g|^2, 4 step reductions) + 1 max (|g|_inf) reduced together; fixed order
-  __shared__ double sh[kFinalizeThreads / 32][8];
-  if (a.ctl->done) return;
-  const Blocks& out = a.out[pick(a.ctl, a.which)];
-  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G, lane = tid & 31, warp = tid >> 5;
-  double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // cost, g2, st0..3, gmax
-  for (int k = tid; k < NS; k += kFinalizeThreads) {
-    double s = 0.0;
-    for (int b = 0; b < kReduceBlocks; ++b) s += a.Cpart[static_cast<int64_t>(b) * NS + k];
-    if (k < G * G) {
-      out.C[k] = s;
-    } else {
-      out.gc[k - G * G] = s;
-      v[6] = fmax(v[6], fabs(s));
-      v[1] += s * s;
-    }
-  }
-  for (int k = tid; k < a.n_cost_part; k += kFinalizeThreads) v[0] += a.cost_part[k];
-  for (int k = tid; k < a.n_imu_cost_part; k += kFinalizeThreads) v[0] += a.imu_cost_part[k];
-  const int64_t nfp = static_cast<int64_t>(a.dp.n_frames) * a.dp.fd;
-  for (int64_t k = tid; k < nfp; k += kFinalizeThreads) {
-    const double g = out.gf[k];
-    v[6] = fmax(v[6], fabs(g));
-    v[1] += g * g;
-  }
-  if (a.step_part)
-    for (int k = tid; k < a.n_step_part; k += kFinalizeThreads)
-      for (int q = 0; q < 4; ++q) v[2 + q] += a.step_part[4 * k + q];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int q = 0; q < 6; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
-    v[6] = fmax(v[6], __shfl_down_sync(0xffffffffu, v[6], o));
-  }
-  if (lane == 0)
-    for (int q = 0; q < 7; ++q) sh[warp][q] = v[q];
-  __syncthreads();
-  if (tid == 0) {
-    double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int w = 0; w < kFinalizeThreads / 32; ++w) {
-      for (int q = 0; q < 6; ++q) t[q] += sh[w][q];
-      t[6] = fmax(t[6], sh[w][6]);
-    }
-    *out.cost = t[0];
-    a.scalars[kScCost] = t[0];
-    a.scalars[kScGmax] = t[6];
-    a.scalars[kScGnorm2] = t[1];
-    if (a.step_part) {
-      a.scalars[kScDotG] = t[2];
-      a.scalars[kScDotD] = t[3];
-      a.scalars[kScStep2] = t[4];
-      a.scalars[kScXnorm2] = t[5];
-    }
-  }
-}
-
 // ---------------------------------------------------------------- accept / reject on the device
 // mode 0: initial point (iteration 0): adopt cost / gradient norms
 // mode 1: one iteration of Ceres' TrustRegionMinimizer loop with the LM strategy's radius rules
@@ -409,10 +287,6 @@ __device__ inline void decide_step(Ctl* c, double* sc, int mode) {
     else if (!c->done) c->done = 1 + VCGPU_TERM_RADIUS;
   }
   if (!c->done && iter >= c->max_iters) c->done = 1 + VCGPU_TERM_NO_CONVERGENCE;
-}
-
-__global__ void decide_kernel(Ctl* c, double* sc, int mode) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) decide_step(c, sc, mode);
 }
 
 // ---------------------------------------------------------------- reduce + finalize + decide in one launch
