@@ -294,7 +294,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": roofline(g, top, stages, top_bytes, achieved, peaks, peak_src, p, K0, fused, local, args.workload,
                              persistent, dev_s / args.steps),
-        "cpu_baseline": cpu_baseline(p, args),
+        "cpu_baseline": cpu_baseline(p, args) if world == 1 else None,  # timed on rank 0 at N=1 only
     }
     _emit(out)
 

@@ -932,6 +932,7 @@ extern "C" int vcgpu_comm_init(vcgpu_handle* h, const uint8_t id[VCGPU_UNIQUE_ID
   if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return h ? fail(h, VCGPU_ERR_INVALID, "comm_init: bad arguments") : VCGPU_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
   xchg_release(h);
+  h->dirty = true;  // the totals buffer is gone: prepare() must set the persistent kernel up again
   if (h->comm) { ncclCommDestroy(static_cast<ncclComm_t>(h->comm)); h->comm = nullptr; }
   h->rank = rank;
   h->nranks = nranks;
