@@ -185,8 +185,7 @@ __device__ inline double mega_total(const MegaArgs& a, int off, int stride, int 
 // the solution overwrites the right-hand side.  The right-hand side is carried through the factorisation as an
 // extra row (so L y = rhs comes for free) and the pivots are kept as reciprocals.  Rows are spread over the
 // lanes, column updates batched by four.  (Register-resident variants — lane r owning row r, columns broadcast
-// with shuffles — were measured twice and were 1-2 us slower in this phase: the row array ends up in local memory.)  (A register-resident variant with shuffle broadcasts measured
-// slower on B200: +2 us in this phase and, through register pressure, +1 us in the others.)
+// with shuffles — were measured twice and were 1-2 us slower in this phase: the row array ends up in local memory.)
 __device__ inline void mega_chol_solve_smem(double* S, int G, int lane, double* invd, int* bad) {
   double* rhs = S + G * G;
   for (int j = 0; j < G; ++j) {
