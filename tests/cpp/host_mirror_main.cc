@@ -5,6 +5,8 @@
 #include <unistd.h>
 
 #include <cstdint>
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
@@ -79,6 +81,21 @@ int main(int argc, char** argv) {
   std::fprintf(o, "\nscale");
   for (double v : sf) std::fprintf(o, " %.17g", v);
   std::fprintf(o, "\n");
+  // cameras.xml round trip through the rig reader (calibu::ReadXmlRig stand-in): exact for %.17g output
+  double worst = 0.0;
+  const auto rig = ReadXmlRig(argv[3]);
+  if (static_cast<int>(rig.size()) != nc) worst = 1e300;
+  for (int c = 0; c < nc && worst < 1e300; ++c) {
+    const CameraInterface& w = *cal.GetCamera(c).camera;
+    if (rig[c]->Type() != w.Type() || rig[c]->Width() != w.Width() || rig[c]->GetParams().size() != w.GetParams().size()) { worst = 1e300; break; }
+    for (size_t k = 0; k < w.GetParams().size(); ++k) worst = std::max(worst, std::fabs(rig[c]->GetParams()[k] - w.GetParams()[k]));
+    double Ma[12], Mb[12];
+    rig[c]->Pose().matrix3x4(Ma);
+    w.Pose().matrix3x4(Mb);
+    for (int k = 0; k < 12; ++k) worst = std::max(worst, std::fabs(Ma[k] - Mb[k]));
+    for (int k = 0; k < 9; ++k) worst = std::max(worst, std::fabs(rig[c]->RDF()[k] - w.RDF()[k]));
+  }
+  std::fprintf(o, "xml_roundtrip %.3g\n", worst);
   fclose(o);
   return 0;
 }

@@ -46,6 +46,8 @@ def _run(tmp_path, p, has_guess=True, max_iters=200, dup=False):
             out[f"T_ck{c}"] = np.array(tok[i_t + 1:], dtype=float)
         else:
             out[tok[0]] = np.array(tok[1:], dtype=float)
+    # cameras.xml read back with the rig reader reproduces parameters / pose / RDF (17 significant digits written)
+    assert out["xml_roundtrip"][0] <= 1e-12
     return out, open(xml).read()
 
 

@@ -24,6 +24,7 @@
 #include <memory>
 #include <sstream>
 #include <stdexcept>
+#include <cctype>
 #include <string>
 #include <vector>
 
@@ -146,6 +147,88 @@ class CameraInterface {
   double rdf_[9];
   SE3d pose_;
 };
+
+// ---- calibu::ReadXmlRig stand-in: reads the rig files WriteCameraModels writes (and Calibu's own: same tags).
+// The reference uses it for `-model_files` warm starts and keeps only cameras_[0] of every file with an identity
+// pose (vicalib-engine.cc:188-196); pose and RDF are parsed as well.  Throws std::runtime_error on a malformed file.
+namespace xml_detail {
+inline std::string Between(const std::string& s, const std::string& open, const std::string& close, size_t from, size_t* end) {
+  const size_t a = s.find(open, from);
+  if (a == std::string::npos) { *end = std::string::npos; return std::string(); }
+  const size_t b = s.find(close, a + open.size());
+  if (b == std::string::npos) throw std::runtime_error("rig xml: missing " + close);
+  *end = b + close.size();
+  return s.substr(a + open.size(), b - a - open.size());
+}
+inline std::vector<double> Numbers(const std::string& text) {  // "[ a; b, c ]" -> {a, b, c}
+  std::vector<double> v;
+  std::string tok;
+  for (size_t i = 0; i <= text.size(); ++i) {
+    const char ch = i < text.size() ? text[i] : ' ';
+    if (std::isdigit(static_cast<unsigned char>(ch)) || ch == '-' || ch == '+' || ch == '.' || ch == 'e' || ch == 'E' ||
+        ch == 'n' || ch == 'a' || ch == 'i' || ch == 'f') {
+      tok.push_back(ch);
+    } else if (!tok.empty()) {
+      v.push_back(std::strtod(tok.c_str(), nullptr));
+      tok.clear();
+    }
+  }
+  return v;
+}
+inline std::string Attribute(const std::string& tag, const std::string& name) {
+  const size_t a = tag.find(name + "=\"");
+  if (a == std::string::npos) return std::string();
+  const size_t b = tag.find('"', a + name.size() + 2);
+  return tag.substr(a + name.size() + 2, b - a - name.size() - 2);
+}
+}  // namespace xml_detail
+
+inline std::vector<std::shared_ptr<CameraInterface>> ReadXmlRig(const std::string& filename) {
+  std::ifstream in(filename.c_str());
+  if (!in) throw std::runtime_error("rig xml: cannot open " + filename);
+  std::stringstream ss;
+  ss << in.rdbuf();
+  const std::string s = ss.str();
+  std::vector<std::shared_ptr<CameraInterface>> rig;
+  size_t pos = 0;
+  for (;;) {
+    size_t end = 0;
+    const std::string cam = xml_detail::Between(s, "<camera>", "</camera>", pos, &end);
+    if (end == std::string::npos) break;
+    pos = end;
+    const size_t m0 = cam.find("<camera_model");
+    if (m0 == std::string::npos) throw std::runtime_error("rig xml: <camera> without <camera_model>");
+    const std::string head = cam.substr(m0, cam.find('>', m0) - m0);
+    const std::string type = xml_detail::Attribute(head, "type");
+    size_t e = 0;
+    const std::vector<double> w = xml_detail::Numbers(xml_detail::Between(cam, "<width>", "</width>", 0, &e));
+    const std::vector<double> h = xml_detail::Numbers(xml_detail::Between(cam, "<height>", "</height>", 0, &e));
+    const std::vector<double> params = xml_detail::Numbers(xml_detail::Between(cam, "<params>", "</params>", 0, &e));
+    if (w.size() != 1 || h.size() != 1) throw std::runtime_error("rig xml: bad <width>/<height>");
+    std::shared_ptr<CameraInterface> c(new CameraInterface(type, static_cast<int>(w[0]), static_cast<int>(h[0]), params));
+    const std::string idx = xml_detail::Attribute(head, "index");
+    if (!idx.empty()) c->SetIndex(std::atoi(idx.c_str()));
+    const std::vector<double> r = xml_detail::Numbers(xml_detail::Between(cam, "<right>", "</right>", 0, &e));
+    const std::vector<double> d = xml_detail::Numbers(xml_detail::Between(cam, "<down>", "</down>", 0, &e));
+    const std::vector<double> f = xml_detail::Numbers(xml_detail::Between(cam, "<forward>", "</forward>", 0, &e));
+    if (r.size() == 3 && d.size() == 3 && f.size() == 3) {  // right / down / forward are the columns of the RDF matrix
+      const double R[9] = {r[0], d[0], f[0], r[1], d[1], f[1], r[2], d[2], f[2]};
+      c->SetRDF(R);
+    }
+    const std::vector<double> T = xml_detail::Numbers(xml_detail::Between(cam, "<T_wc>", "</T_wc>", 0, &e));
+    if (T.size() == 12) {
+      const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+      SE3d pose = SE3d::FromRotation(R);
+      pose.d[4] = T[3]; pose.d[5] = T[7]; pose.d[6] = T[11];
+      c->SetPose(pose);
+    } else if (!T.empty()) {
+      throw std::runtime_error("rig xml: <T_wc> is not 3x4");
+    }
+    rig.push_back(c);
+  }
+  if (rig.empty()) throw std::runtime_error("rig xml: no <camera> in " + filename);
+  return rig;
+}
 
 struct CameraAndPose {  // vicalibrator.h:65-73
   CameraAndPose(const std::shared_ptr<CameraInterface>& c, const SE3d& T) : camera(c), T_ck(T) {}
