@@ -389,7 +389,7 @@ static int enqueue_iteration(vcgpu_handle* h, bool weights) {
   if (mega_applies(h)) return mega_launch(h, 1);
   VC_TRY(solve_and_update(h, nullptr, false));
   VC_TRY(evaluate_into(h, 1, true, 1));
-  if (weights) VC_TRY(imu_update_weights(h));  // the reference's iteration callback (vicalibrator.h:691)
+  if (weights) VC_TRY(imu_update_weights(h, true));  // the reference's iteration callback (vicalibrator.h:691)
   return VCGPU_OK;
 }
 
@@ -477,6 +477,7 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
       if (h->h_ctl->done) break;
     }
   }
+  VC_TRY(wts_join(h));
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   VC_TRY(ctl_download(h));
   CUDA_TRY(h, cudaEventSynchronize(h->ev1));

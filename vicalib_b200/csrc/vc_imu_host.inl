@@ -121,7 +121,9 @@ static int imu_prepare(vcgpu_handle* h) {
   return VCGPU_OK;
 }
 
+static int wts_join(vcgpu_handle* h);
 static int imu_evaluate(vcgpu_handle* h, int which, bool apply_loss, int* n_cost, const double* mask_dev = nullptr) {
+  VC_TRY(wts_join(h));  // the residuals are weighted
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
   const int ni = dp.n_frames - 1;
@@ -245,18 +247,38 @@ static int imu_chain_backsub(vcgpu_handle* h, const double* D2x, bool explicit_u
 }
 
 // UpdateImuWeights (vicalibrator.h:723-799): active only when inertial && !rotation_only (:725)
-static int imu_update_weights(vcgpu_handle* h) {
+// the side-stream weight update (if any) must be complete before the main stream goes on
+static int wts_join(vcgpu_handle* h) {
+  if (h->wts_pending) {
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_wts, 0));
+    h->wts_pending = false;
+  }
+  return VCGPU_OK;
+}
+static int imu_update_weights(vcgpu_handle* h, bool side_stream = false) {
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
   if (!dp.inertial || dp.rotation_only) return VCGPU_OK;
+  VC_TRY(wts_join(h));
+  side_stream = side_stream && !h->profiling && !h->flush_l2 && h->stream2 != nullptr;  // timed per iteration: stay serial
+  cudaStream_t st_launch = h->stream;
+  if (side_stream) {  // everything enqueued so far (the decision included) happens before the update
+    CUDA_TRY(h, cudaEventRecord(h->ev_dec, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream2, h->ev_dec, 0));
+    st_launch = h->stream2;
+  }
   StageScope st(h, VCGPU_STAGE_IMU_WEIGHTS);
   vc::wts::WeightArgs a;
   a.dp = dp; a.buf = d->buf; a.ctl = h->d_ctl; a.states[0] = h->d_state[0]; a.states[1] = h->d_state[1];
   a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
   a.ni = dp.n_frames - 1; a.sigma_g = h->sigma_g; a.sigma_a = h->sigma_a;
-  vc::wts::imu_weights_kernel<<<(a.ni + vc::wts::kWtWarps - 1) / vc::wts::kWtWarps, 32 * vc::wts::kWtWarps, 0, h->stream>>>(a);
+  vc::wts::imu_weights_kernel<<<(a.ni + vc::wts::kWtWarps - 1) / vc::wts::kWtWarps, 32 * vc::wts::kWtWarps, 0, st_launch>>>(a);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
+  if (side_stream) {
+    CUDA_TRY(h, cudaEventRecord(h->ev_wts, h->stream2));
+    h->wts_pending = true;
+  }
   return VCGPU_OK;
 }
 

@@ -98,6 +98,11 @@ struct vcgpu_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // UpdateImuWeights of iteration k runs on a side stream next to the arrow solve of iteration k+1 (which only
+  // reads blocks built earlier); the IMU evaluation of k+1 joins it
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_dec = nullptr, ev_wts = nullptr;
+  bool wts_pending = false;
   long launches = 0, collectives = 0;
   std::unordered_map<void*, size_t> capacity;  // bytes held by each dev_alloc()ed pointer slot
   // measurement hooks

@@ -179,6 +179,9 @@ extern "C" int vcgpu_create(const vcgpu_config* cfg, vcgpu_handle** out) {
   if (dev < 0) cudaGetDevice(&dev);
   h->device = dev;
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_dec, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_wts, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), kScCount * sizeof(double)) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&h->h_ctl), sizeof(Ctl)) != cudaSuccess ||
@@ -220,6 +223,9 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   }
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
+  if (h->ev_dec) cudaEventDestroy(h->ev_dec);
+  if (h->ev_wts) cudaEventDestroy(h->ev_wts);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream);
   delete h;
   return VCGPU_OK;
