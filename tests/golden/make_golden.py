@@ -93,9 +93,16 @@ def project(model, p, k):
     r2 = u * u + v * v
     if model == LINEAR:
         f = 1
-    elif model == FOV:
-        rad = mp.sqrt(r2)
-        f = mp.atan(rad * 2 * mp.tan(k[4] / 2)) / (rad * k[4])
+    elif model == FOV:  # Calibu FovCamera::Factor: the two small-argument branches are part of the model
+        w = k[4]
+        if w * w > mp.mpf("1e-5"):
+            if r2 < mp.mpf("1e-5"):
+                f = 2 * mp.tan(w / 2) / w
+            else:
+                rad = mp.sqrt(r2)
+                f = mp.atan(rad * 2 * mp.tan(w / 2)) / (rad * w)
+        else:
+            f = mp.mpf(1)
     elif model == POLY2:
         f = 1 + k[4] * r2 + k[5] * r2 ** 2
     else:
@@ -109,20 +116,31 @@ def reproj(model, Rwk, twk, Rck, pck, intr, pw, z):
     return [pr[0] - z[0], pr[1] - z[1]]
 
 
-def reproj_kat(rng, model, n=12):
+def random_sample(rng, model, tgt=None, dist=None):
+    """(T_wk, T_ck, intrinsics, world point, measurement); tgt = the point's camera-frame coordinates."""
     K = NUM_INTR[model]
     from vicalib_b200.synth import TRUTH_DIST, quat_to_mat, so3_exp as np_exp
-    rows = []
-    for _ in range(n):
-        q = np_exp(rng.normal(0, 0.6, 3)); t = rng.normal(0, 0.2, 3) + np.array([0, 0, -0.6])
-        qc = np_exp(rng.normal(0, 0.3, 3)); pc = rng.normal(0, 0.05, 3)
-        intr = np.zeros(10)
-        intr[:4] = [300 + 30 * rng.random(), 310 + 30 * rng.random(), 320 + 5 * rng.random(), 240 + 5 * rng.random()]
-        intr[4:K] = np.array(TRUTH_DIST[model]) * (1 + 0.2 * rng.random(K - 4))
-        # a world point in front of the camera: p_w = R_wk (R_ck^T (pc_target - p_ck)) + t
+    q = np_exp(rng.normal(0, 0.6, 3)); t = rng.normal(0, 0.2, 3) + np.array([0, 0, -0.6])
+    qc = np_exp(rng.normal(0, 0.3, 3)); pc = rng.normal(0, 0.05, 3)
+    intr = np.zeros(10)
+    intr[:4] = [300 + 30 * rng.random(), 310 + 30 * rng.random(), 320 + 5 * rng.random(), 240 + 5 * rng.random()]
+    intr[4:K] = np.array(TRUTH_DIST[model]) * (1 + 0.2 * rng.random(K - 4))
+    if dist is not None:
+        intr[4:K] = dist
+    # a world point in front of the camera: p_w = R_wk (R_ck^T (pc_target - p_ck)) + t
+    if tgt is None:
         tgt = np.array([rng.uniform(-0.25, 0.25), rng.uniform(-0.2, 0.2), rng.uniform(0.4, 0.8)])
-        pw = quat_to_mat(q) @ (quat_to_mat(qc).T @ (tgt - pc)) + t
-        z = rng.uniform(100, 500, 2)
+    pw = quat_to_mat(q) @ (quat_to_mat(qc).T @ (np.asarray(tgt, float) - pc)) + t
+    z = rng.uniform(100, 500, 2)
+    return q, t, qc, pc, intr, pw, z
+
+
+def reproj_kat(rng, model, n=12, samples=None):
+    K = NUM_INTR[model]
+    rows = []
+    if samples is None:
+        samples = [random_sample(rng, model) for _ in range(n)]
+    for q, t, qc, pc, intr, pw, z in samples:
         Rwk, Rck = quat_R(q), quat_R(qc)
         a = (model, Rwk, V(t), Rck, V(pc), [mp.mpf(float(x)) for x in intr], V(pw), V(z))
         r = reproj(*a)
@@ -290,7 +308,35 @@ def imu_kat(rng):
                 W=W, r=np.array(out_r).reshape(2, nf - 1, 9), J=np.array(out_J).reshape(2, nf - 1, 9, 33))
 
 
+def edge_kat():
+    """Branch and boundary cases of the camera models (each model's own small-argument branches, the image
+    centre, the image border).  Written to reproj_edge_kat.npz with the keys of reproj_kat.npz."""
+    rng = np.random.default_rng(20260925)
+    out = {}
+    cases = {
+        "fov": [dict(tgt=[1e-4, -2e-4, 0.5]),                      # rad^2 < 1e-5:  2 tan(w/2) / w
+                dict(dist=[2e-3]),                                   # w^2 <= 1e-5:  factor 1
+                dict(tgt=[-3e-5, 1e-5, 0.7], dist=[1e-3]),          # both
+                dict(tgt=[0.45, -0.3, 0.4])],                        # wide angle (rad ~ 1.35)
+        "kb4": [dict(tgt=[1e-5, -2e-5, 0.5]), dict(tgt=[0.5, 0.35, 0.35])],
+        "poly3": [dict(tgt=[1e-6, 2e-6, 0.6]), dict(tgt=[0.35, 0.25, 0.4])],
+        "poly2": [dict(tgt=[0.0, 0.0, 0.5]), dict(tgt=[-0.35, 0.25, 0.4])],
+        "linear": [dict(tgt=[0.0, 0.0, 0.5]), dict(tgt=[0.4, -0.3, 0.4])],
+    }
+    ids = dict(linear=LINEAR, fov=FOV, poly2=POLY2, poly3=POLY3, kb4=KB4)
+    for name, specs in cases.items():
+        samples = [random_sample(rng, ids[name], **sp) for sp in specs]
+        kat = reproj_kat(rng, ids[name], samples=samples)
+        for k, v in kat.items():
+            out[f"{name}_{k}"] = v
+        print(name, "edge done", flush=True)
+    np.savez_compressed(os.path.join(HERE, "reproj_edge_kat.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--edge" in sys.argv:  # only the branch / boundary fixture (the others are unchanged)
+        edge_kat()
+        sys.exit(0)
     rng = np.random.default_rng(20260924)
     out = {}
     for name, m in (("linear", LINEAR), ("fov", FOV), ("poly2", POLY2), ("poly3", POLY3), ("kb4", KB4)):

@@ -30,9 +30,11 @@ def _oracle_for_reproj(model, d, i):
     return o, K
 
 
+# reproj_edge_kat.npz: each model's small-argument branches (FOV: rad^2 < 1e-5, w^2 <= 1e-5), image centre, border
+@pytest.mark.parametrize("fixture", ["reproj_kat.npz", "reproj_edge_kat.npz"])
 @pytest.mark.parametrize("name", ["linear", "fov", "poly2", "poly3", "kb4"])
-def test_reprojection_kat(name):
-    z = np.load(os.path.join(GOLD, "reproj_kat.npz"))
+def test_reprojection_kat(name, fixture):
+    z = np.load(os.path.join(GOLD, fixture))
     model = synth.MODEL_IDS[name]
     d = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "_")}
     for i in range(d["r"].shape[0]):

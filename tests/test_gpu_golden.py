@@ -10,11 +10,12 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+@pytest.mark.parametrize("fixture", ["reproj_kat.npz", "reproj_edge_kat.npz"])  # edge: model branches, centre, border
 @pytest.mark.parametrize("name", ["linear", "fov", "poly2", "poly3", "kb4"])
-def test_reprojection_kernel_vs_kat(name):
+def test_reprojection_kernel_vs_kat(name, fixture):
     from vicalib_b200.capi import Calibrator
 
-    z = np.load(os.path.join(GOLD, "reproj_kat.npz"))
+    z = np.load(os.path.join(GOLD, fixture))
     model = synth.MODEL_IDS[name]
     K = synth.NUM_INTR[model]
     d = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "_")}
