@@ -60,3 +60,23 @@ def test_imu_kat(switch):
     r, J = o.eval_imu()
     assert np.abs(r - z["r"][switch]).max() <= 1e-9 * np.abs(z["r"][switch]).max()
     assert np.abs(J - z["J"][switch]).max() <= 1e-9 * np.abs(z["J"][switch]).max()
+
+
+def test_imu_weights_kat():
+    """UpdateImuWeights against an independent computation: tests/golden/make_weights_golden.py propagates the
+    covariance with exact (mpmath, central-difference) Jacobians of the integrator and of the residual map — none
+    of the reference's hand-derived derivative formulas — with unit scale factors, where those formulas are exact
+    up to the truncated series of d exp(w)/dw.  Measured agreement 7e-11; tolerance 1e-8 relative."""
+    from oracle.binding import Oracle
+
+    z = np.load(os.path.join(GOLD, "imu_weights_kat.npz"))
+    p = synth.make_problem(models=("linear",), n_frames=2, inertial=True, seed=1)
+    p.T_wp, p.v_w, p.ftime = z["T_wp"].copy(), z["v_w"].copy(), z["ftime"].copy()
+    p.imu_t, p.imu_w, p.imu_a = z["imu_t"].copy(), z["imu_w"].copy(), z["imu_a"].copy()
+    p.g, p.b, p.sf, p.ts = z["g"].copy(), z["b"].copy(), z["sf"].copy(), float(z["ts"])
+    assert synth.GYRO_SIGMA == float(z["sigma_g"]) and synth.ACCEL_SIGMA == float(z["sigma_a"])
+    o = Oracle(p, inertial=1, bias_active=1, scale_active=1, optimize_ts=1)
+    o.update_imu_weights()
+    W = o.imu_weights()[0]
+    assert np.abs(W - z["W"]).max() <= 1e-8 * np.abs(z["W"]).max()
+    assert np.abs(W @ W - z["info"]).max() <= 1e-8 * np.abs(z["info"]).max()

@@ -49,3 +49,20 @@ def test_imu_kernel_vs_kat(switch):
     r, J = g.eval_imu()
     assert np.abs(r - z["r"][switch]).max() <= 1e-9 * np.abs(z["r"][switch]).max()
     assert np.abs(J - z["J"][switch]).max() <= 1e-9 * np.abs(z["J"][switch]).max()
+
+
+def test_imu_weights_kernel_vs_kat():
+    """imu_weights_kernel against the independent mpmath covariance propagation (see test_cpu_oracle_golden.py)."""
+    from vicalib_b200.capi import Calibrator
+
+    z = np.load(os.path.join(GOLD, "imu_weights_kat.npz"))
+    g = Calibrator()
+    g.set_cameras([0], np.array([[300, 300, 320, 240, 0, 0, 0, 0, 0, 0.0]]), np.array([[0, 0, 0, 1.0]]), np.zeros((1, 3)))
+    g.set_frames(z["T_wp"], z["v_w"], z["ftime"])
+    g.set_observations(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3)), np.zeros((0, 2)))
+    g.set_imu(z["imu_t"], z["imu_w"], z["imu_a"], float(z["sigma_g"]), float(z["sigma_a"]))
+    g.set_imu_params(z["g"], z["b"], z["sf"], float(z["ts"]))
+    g.set_flags(inertial=1, bias_active=1, scale_active=1, optimize_ts=1)
+    g.update_imu_weights()
+    W = g.imu_weights()[0]
+    assert np.abs(W - z["W"]).max() <= 1e-8 * np.abs(z["W"]).max()
