@@ -131,3 +131,33 @@ def test_evaluate_order_and_outliers():
     assert np.array_equal(o.obs_active(), g.obs_active())
     assert set(np.flatnonzero(g.obs_active() == 0)) >= set(bad.tolist())
     assert abs(g.cost() - o.cost()) <= 1e-10 * o.cost()
+
+
+def test_bad_ids_are_reported_and_order_does_not_matter():
+    """prepare(): ids are validated (the reference CHECKs, vicalibrator.h:396), and sorted / unsorted / reversed
+    caller orders give the same normal equations (fast sorted pass, counting sort otherwise)."""
+    from vicalib_b200.capi import Calibrator, VcgpuError
+
+    p = synth.make_problem(models=("poly3", "fov"), n_frames=9, grid=(14, 10), seed=3)
+    ref = None
+    for order in (np.arange(p.n_obs), np.arange(p.n_obs)[::-1], np.random.default_rng(0).permutation(p.n_obs)):
+        g = Calibrator()
+        g.set_cameras(p.models, p.intr, p.q_ck, p.p_ck)
+        g.set_frames(p.T_wp, p.v_w, p.ftime)
+        g.set_observations(p.obs_frame[order], p.obs_cam[order], p.p_w[order], p.p_c[order])
+        ne = g.normal_equations()
+        if ref is None:
+            ref = ne
+        for k in ("B", "E", "gf", "C", "gc"):
+            assert np.abs(ne[k] - ref[k]).max() <= 1e-9 * max(np.abs(ref[k]).max(), 1e-300), k
+        g.close()
+    for bad_frame, bad_cam in ((p.n_frames, 0), (-1, 0), (0, 2), (0, -3)):
+        g = Calibrator()
+        g.set_cameras(p.models, p.intr, p.q_ck, p.p_ck)
+        g.set_frames(p.T_wp, p.v_w, p.ftime)
+        fr, cm = p.obs_frame.copy(), p.obs_cam.copy()
+        fr[p.n_obs // 2], cm[p.n_obs // 2] = bad_frame if bad_frame != 0 else fr[p.n_obs // 2], bad_cam if bad_cam != 0 else cm[p.n_obs // 2]
+        g.set_observations(fr, cm, p.p_w, p.p_c)
+        with pytest.raises(VcgpuError, match="unknown"):
+            g.normal_equations()
+        g.close()

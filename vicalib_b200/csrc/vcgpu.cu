@@ -485,20 +485,53 @@ static int prepare(vcgpu_handle* h) {
       CUDA_TRY(h, cudaMemcpyAsync(h->d_obs_frame, h->h_obs_frame.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
       uploaded = true;
     }
-    // one pass: validate ids, count per (camera, frame), detect an already-sorted caller order
+    // Validate ids, count per (camera, frame), detect an already-sorted caller order.  Fast pass first: with every
+    // observation active (`uploaded`), one branch-light sweep checks bounds and order and records the run boundaries;
+    // the per-group counts of a sorted input are just the run lengths.
     std::vector<int64_t> count(static_cast<size_t>(nc) * nf + 1, 0);
-    bool sorted = true;
-    int64_t prev_key = -1, n_act = 0;
-    for (int64_t i = 0; i < h->n_obs_all; ++i) {
-      const int32_t c = h->h_obs_cam[i], f = h->h_obs_frame[i];
-      if (c < 0 || c >= nc) return fail(h, VCGPU_ERR_INVALID, "observation with unknown camera id");  // vicalibrator.h:396
-      if (f < 0 || f >= nf) return fail(h, VCGPU_ERR_INVALID, "observation with unknown frame id");
-      if (!h->h_active[i]) continue;
-      const int64_t key = static_cast<int64_t>(c) * nf + f;
-      sorted &= key >= prev_key;
-      prev_key = key;
-      ++count[key + 1];
-      ++n_act;
+    bool sorted = false;
+    int64_t n_act = 0;
+    if (uploaded) {
+      const int32_t* cam = h->h_obs_cam.data();
+      const int32_t* frm = h->h_obs_frame.data();
+      const int64_t n = h->n_obs_all;
+      bool in_range = true, ordered = true;
+      int64_t prev_key = -1, run_start = 0;
+      for (int64_t i = 0; i < n; ++i) {
+        const int32_t c = cam[i], f = frm[i];
+        in_range &= static_cast<uint32_t>(c) < static_cast<uint32_t>(nc) && static_cast<uint32_t>(f) < static_cast<uint32_t>(nf);
+        const int64_t key = static_cast<int64_t>(c) * nf + f;
+        if (key != prev_key) {
+          if (in_range && prev_key >= 0) count[prev_key + 1] = i - run_start;
+          ordered &= key > prev_key;
+          if (!ordered || !in_range) break;  // the general pass below reports / sorts
+          prev_key = key;
+          run_start = i;
+        }
+      }
+      if (in_range && ordered) {
+        if (prev_key >= 0) count[prev_key + 1] = n - run_start;
+        sorted = true;
+        n_act = n;
+      } else {
+        std::fill(count.begin(), count.end(), 0);
+      }
+    }
+    if (!sorted) {
+      bool ordered = true;
+      int64_t prev_key = -1;
+      for (int64_t i = 0; i < h->n_obs_all; ++i) {
+        const int32_t c = h->h_obs_cam[i], f = h->h_obs_frame[i];
+        if (c < 0 || c >= nc) return fail(h, VCGPU_ERR_INVALID, "observation with unknown camera id");  // vicalibrator.h:396
+        if (f < 0 || f >= nf) return fail(h, VCGPU_ERR_INVALID, "observation with unknown frame id");
+        if (!h->h_active[i]) continue;
+        const int64_t key = static_cast<int64_t>(c) * nf + f;
+        ordered &= key >= prev_key;
+        prev_key = key;
+        ++count[key + 1];
+        ++n_act;
+      }
+      sorted = ordered;
     }
     for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
     h->n_obs = n_act;
