@@ -312,7 +312,7 @@ struct WeightArgs {
 };
 constexpr int kWtWarps = 2;
 
-__global__ void __launch_bounds__(32 * kWtWarps) imu_weights_kernel(WeightArgs a) {
+__global__ void __launch_bounds__(32 * kWtWarps, 8) imu_weights_kernel(WeightArgs a) {
   __shared__ Work work[kWtWarps];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int kk = blockIdx.x * kWtWarps + wid;
