@@ -71,7 +71,7 @@ struct ElimArgs {
 };
 
 template <int FD>
-__global__ void __launch_bounds__(kChainThreads) chain_eliminate_kernel(ElimArgs a) {
+__global__ void __launch_bounds__(kChainThreads, 4) chain_eliminate_kernel(ElimArgs a) {
   extern __shared__ double sm[];
   const int G = a.G, c = a.c, tid = threadIdx.x, NS = G * G + G;
   const int w = 2 * FD + G + 1, VW = FD + w;
