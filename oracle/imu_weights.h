@@ -396,10 +396,15 @@ inline bool Inverse(const Mat<N, N>& a, Mat<N, N>* out) {
   return true;
 }
 
-// principal square root of a symmetric PSD matrix by cyclic Jacobi eigen-decomposition
-// (Eigen MatrixFunctions `.sqrt()` at vicalibrator.h:796; equal to it for SPD input)
+// principal square root of a symmetric PSD matrix by Jacobi eigen-decomposition
+// (Eigen MatrixFunctions `.sqrt()` at vicalibrator.h:796; equal to it for SPD input).
+// Rotation order: round-robin tournament — round r holds the disjoint pairs {i, j}, i + j = r (mod N), i < j —
+// with all rotations of a round computed from the same matrix and applied together (columns, then rows).
+// Rotations on disjoint index pairs commute, so this is the classical cyclic method in another sweep order; it is
+// the order the CUDA kernel runs four pairs at a time (vc_imu_weights.cuh).
 template <int N>
 inline Mat<N, N> SqrtSym(const Mat<N, N>& a_in) {
+  static_assert(N % 2 == 1, "round-robin schedule written for odd N");
   Mat<N, N> a;
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) a(i, j) = 0.5 * (a_in(i, j) + a_in(j, i));
@@ -411,28 +416,38 @@ inline Mat<N, N> SqrtSym(const Mat<N, N>& a_in) {
       for (int j = i + 1; j < N; ++j) off += a(i, j) * a(i, j);
     }
     if (off <= 1e-30 * diag) break;
-    for (int p = 0; p < N; ++p)
-      for (int q = p + 1; q < N; ++q) {
-        if (a(p, q) == 0.0) continue;
-        const double tau = (a(q, q) - a(p, p)) / (2.0 * a(p, q));
-        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
-        const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
-        for (int k = 0; k < N; ++k) {
-          const double akp = a(k, p), akq = a(k, q);
-          a(k, p) = c * akp - s * akq;
-          a(k, q) = s * akp + c * akq;
+    for (int r = 0; r < N; ++r) {
+      int P[N / 2], Q[N / 2], np = 0;
+      double C[N / 2], S[N / 2];
+      for (int i = 0; i < N; ++i) {
+        const int j = ((r - i) % N + N) % N;
+        if (i >= j) continue;
+        const double apq = a(i, j);
+        double c = 1.0, sn = 0.0;
+        if (apq != 0.0) {
+          const double tau = (a(j, j) - a(i, i)) / (2.0 * apq);
+          const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+          c = 1.0 / std::sqrt(1.0 + t * t);
+          sn = t * c;
         }
-        for (int k = 0; k < N; ++k) {
-          const double apk = a(p, k), aqk = a(q, k);
-          a(p, k) = c * apk - s * aqk;
-          a(q, k) = s * apk + c * aqk;
-        }
-        for (int k = 0; k < N; ++k) {
-          const double vkp = V(k, p), vkq = V(k, q);
-          V(k, p) = c * vkp - s * vkq;
-          V(k, q) = s * vkp + c * vkq;
-        }
+        P[np] = i; Q[np] = j; C[np] = c; S[np] = sn; ++np;
       }
+      for (int t = 0; t < np; ++t)
+        for (int k = 0; k < N; ++k) {
+          const double akp = a(k, P[t]), akq = a(k, Q[t]);
+          a(k, P[t]) = C[t] * akp - S[t] * akq;
+          a(k, Q[t]) = S[t] * akp + C[t] * akq;
+          const double vkp = V(k, P[t]), vkq = V(k, Q[t]);
+          V(k, P[t]) = C[t] * vkp - S[t] * vkq;
+          V(k, Q[t]) = S[t] * vkp + C[t] * vkq;
+        }
+      for (int t = 0; t < np; ++t)
+        for (int k = 0; k < N; ++k) {
+          const double apk = a(P[t], k), aqk = a(Q[t], k);
+          a(P[t], k) = C[t] * apk - S[t] * aqk;
+          a(Q[t], k) = S[t] * apk + C[t] * aqk;
+        }
+    }
   }
   Mat<N, N> r;
   for (int k = 0; k < N; ++k) {

@@ -174,6 +174,8 @@ __device__ inline void dLog_dSE3(Quat<double> q, Vec<double> tr, double dlog[42]
 // per-warp shared workspace (doubles)
 struct Work {
   double C[100], A[100], Gm[60], t1[100], t2[100], t3[100];
+  double rot[8];  // (c, s) of the four rotations of a Jacobi round
+  int rpq[8];     // their index pairs
 };
 
 // Jacobian pieces of one RK4 stage (types.h:380-425), computed redundantly by every lane
@@ -418,30 +420,51 @@ __global__ void __launch_bounds__(32 * kWtWarps, 8) imu_weights_kernel(WeightArg
       for (int j = i + 1; j < 9; ++j) off += A[i * 9 + j] * A[i * 9 + j];
     }
     if (off <= 1e-30 * dg) break;
-    for (int p = 0; p < 9; ++p)
-      for (int q = p + 1; q < 9; ++q) {
-        const double apq = A[p * 9 + q];
-        if (apq == 0.0) continue;  // uniform across the warp
-        const double tau = (A[q * 9 + q] - A[p * 9 + p]) / (2.0 * apq);
-        const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
-        __syncwarp();
-        if (lane < 9) {  // columns p,q of A and V
-          const double akp = A[lane * 9 + p], akq = A[lane * 9 + q];
-          A[lane * 9 + p] = c * akp - s * akq;
-          A[lane * 9 + q] = s * akp + c * akq;
-          const double vkp = V[lane * 9 + p], vkq = V[lane * 9 + q];
-          V[lane * 9 + p] = c * vkp - s * vkq;
-          V[lane * 9 + q] = s * vkp + c * vkq;
+    // round-robin order: round r holds the four disjoint pairs {i, j}, i + j = r (mod 9), i < j; their rotations
+    // are computed from the same matrix by four lanes and applied together (columns of A and V, then rows of A) —
+    // the order of oracle/imu_weights.h:SqrtSym, nine serial steps per sweep instead of thirty-six
+    for (int r = 0; r < 9; ++r) {
+      if (lane < 4) {
+        int cnt = 0, pi = 0, qi = 0;
+        for (int i = 0; i < 9; ++i) {
+          const int j = (r - i + 9) % 9;
+          if (i < j) {
+            if (cnt == lane) { pi = i; qi = j; }
+            ++cnt;
+          }
         }
-        __syncwarp();
-        if (lane < 9) {  // rows p,q of A
-          const double apk = A[p * 9 + lane], aqk = A[q * 9 + lane];
-          A[p * 9 + lane] = c * apk - s * aqk;
-          A[q * 9 + lane] = s * apk + c * aqk;
+        const double apq = A[pi * 9 + qi];
+        double c = 1.0, sn = 0.0;
+        if (apq != 0.0) {
+          const double tau = (A[qi * 9 + qi] - A[pi * 9 + pi]) / (2.0 * apq);
+          const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          sn = t * c;
         }
-        __syncwarp();
+        W->rot[2 * lane] = c; W->rot[2 * lane + 1] = sn;
+        W->rpq[2 * lane] = pi; W->rpq[2 * lane + 1] = qi;
       }
+      __syncwarp();
+      for (int e = lane; e < 36; e += 32) {  // columns p, q of A and V: row k, rotation t
+        const int k = e >> 2, t = e & 3, p = W->rpq[2 * t], q = W->rpq[2 * t + 1];
+        const double c = W->rot[2 * t], sn = W->rot[2 * t + 1];
+        const double akp = A[k * 9 + p], akq = A[k * 9 + q];
+        A[k * 9 + p] = c * akp - sn * akq;
+        A[k * 9 + q] = sn * akp + c * akq;
+        const double vkp = V[k * 9 + p], vkq = V[k * 9 + q];
+        V[k * 9 + p] = c * vkp - sn * vkq;
+        V[k * 9 + q] = sn * vkp + c * vkq;
+      }
+      __syncwarp();
+      for (int e = lane; e < 36; e += 32) {  // rows p, q of A: column k, rotation t
+        const int k = e >> 2, t = e & 3, p = W->rpq[2 * t], q = W->rpq[2 * t + 1];
+        const double c = W->rot[2 * t], sn = W->rot[2 * t + 1];
+        const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
+        A[p * 9 + k] = c * apk - sn * aqk;
+        A[q * 9 + k] = sn * apk + c * aqk;
+      }
+      __syncwarp();
+    }
   }
   double* out = a.wsqrt + static_cast<int64_t>(kk) * 81;
   for (int e = lane; e < 81; e += 32) {
