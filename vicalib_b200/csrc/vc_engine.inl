@@ -1,14 +1,17 @@
 // The iteration engine (included by vcgpu.cu): kernel launch helpers, the evaluation pass, the
 // damped arrow solve and the trust-region loop.  All trust-region state lives in a device-resident
-// Ctl block, so an iteration is a fixed sequence of launches the host enqueues without waiting:
+// Ctl block.  Vision solves (one GPU or frame shards) run in the persistent kernel (mega_launch,
+// vc_mega.cuh): one launch per solve.  Everything else — inertial solves, DOGLEG, the inspection hooks,
+// profiling — is a fixed sequence of launches the host enqueues without waiting:
 //
 //   frame_solve -> sum_partials -> global_solve -> backsub_update        (vision)
 //   chain_init -> chain_eliminate x levels -> sum_partials -> dense_solve -> chain_backsub x levels
 //              -> backsub_update                                         (inertial)
-//   fused_build [-> imu_eval -> imu_accumulate] -> reduce_globals -> finalize -> decide [-> imu_weights]
+//   fused_build [-> imu_eval -> imu_accumulate] -> reduce_finalize (+ decide_step) [-> imu_weights, side stream]
 //
-// Multi-GPU: all_reduce_dense() after the partial sums and all_reduce_eval() before decide are the
-// only cross-rank points (frames are sharded; every rank then solves the same small dense system).
+// Multi-GPU on this path: an NCCL all-reduce of the reduced system after the partial sums and one of the
+// global blocks / scalars before the decision are the only cross-rank points (frames are sharded; every
+// rank then solves the same small dense system).
 
 // Measured on B200 (config 2): summing the Schur partials inside the single-CTA dense solve is
 // latency-bound (+18 us); it stays a separate, fully parallel launch.

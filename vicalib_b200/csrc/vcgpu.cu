@@ -3,9 +3,9 @@
 // Replaces, for ViCalibrator, what ceres::Problem + ceres::Solve + Problem::Evaluate do
 // (vicalibrator.h:152, 548-679, 859-916, 956-971).  The trust-region loop below is the Ceres
 // loop (TrustRegionMinimizer + LevenbergMarquardtStrategy) driven from the host
-// with every arithmetic step on the device; the candidate point is evaluated *with* its Jacobian
-// blocks (speculatively) so an accepted step needs no second pass and a multi-GPU run needs one
-// all-reduce per iteration.
+// with every arithmetic step — the accept/reject decision included — on the device; the candidate
+// point is evaluated *with* its Jacobian blocks (speculatively) so an accepted step needs no second
+// pass.  Engines: vc_mega.cuh (persistent kernel, vision solves) and vc_engine.inl (multi-launch).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
