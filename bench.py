@@ -338,7 +338,10 @@ def run_reference(args):
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"{args.workload}: " + _describe(p),
                       "note": "Ceres/Calibu/Sophus/Eigen are not in the image: the reference arm is the CPU port "
-                              "(oracle/) of the reference's Ceres path on the host cores"},
+                              "(oracle/) of the reference's Ceres path on the host cores",
+                      "multi_gpu": None if int(os.environ.get("WORLD_SIZE", "1")) == 1 else
+                      "the GPU arm counts block-iterations of an N-block joint problem; the CPU arm times one block: on the "
+                      "same cores an N-block problem takes N times longer per iteration, i.e. the same block-iterations/s"},
            "cpu_baseline": cb,
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(out)
