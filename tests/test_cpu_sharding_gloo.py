@@ -40,6 +40,60 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_inertial(rank, world, port, q):
+    """Inertial shards: every rank but the last carries the next rank's first frame as a ghost and owns the IMU factor
+    that reaches it.  Summed over the ranks, the global blocks, the cost and — ghost block of rank p added to the first
+    block of rank p+1 — the separator frames' blocks are those of the whole problem."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.binding import Oracle
+    from vicalib_b200 import synth
+
+    flags = dict(inertial=1, bias_active=1, scale_active=1, optimize_ts=1)
+    p = synth.make_problem(models=("poly3",), n_frames=13, inertial=True, seed=4)
+    ps = synth.shard(p, rank, world)
+    f0, f1 = synth.shard_frames(p.n_frames, rank, world)
+    assert ps.n_frames == (f1 - f0) + (1 if rank < world - 1 else 0)
+    ne = Oracle(ps, **flags).normal_equations()
+    G = ne["C"].shape[0]
+    fd = ne["B"].shape[1]
+    # ghost block of this rank (zeros on the last rank) travels to the next rank's separator
+    ghost = np.concatenate([ne["B"][-1].ravel(), ne["gf"][-1]]) if rank < world - 1 else np.zeros(fd * fd + fd)
+    buf = torch.from_numpy(np.concatenate([ne["C"].ravel(), ne["gc"], [ne["cost"]], ghost]))
+    dist.all_reduce(buf)
+    if rank == world - 1:
+        full = Oracle(p, **flags).normal_equations()
+        red = buf.numpy()
+        scale = np.abs(full["C"]).max()
+        ok = (np.abs(red[: G * G].reshape(G, G) - full["C"]).max() <= 1e-11 * scale
+              and np.abs(red[G * G: G * G + G] - full["gc"]).max() <= 1e-11 * max(np.abs(full["gc"]).max(), 1.0)
+              and abs(red[G * G + G] - full["cost"]) <= 1e-12 * full["cost"])
+        # this rank's first frame is a separator: its block = local part + the previous rank's ghost part
+        gB = red[G * G + G + 1: G * G + G + 1 + fd * fd].reshape(fd, fd)
+        gg = red[G * G + G + 1 + fd * fd:]
+        ok = ok and np.abs(ne["B"][0] + gB - full["B"][f0]).max() <= 1e-11 * np.abs(full["B"][f0]).max()
+        ok = ok and np.abs(ne["gf"][0] + gg - full["gf"][f0]).max() <= 1e-9 * max(np.abs(full["gf"][f0]).max(), 1.0)
+        # interior frames and the coupling blocks U = H[f-1, f] are local
+        ok = ok and np.allclose(ne["B"][1:], full["B"][f0 + 1:f1], rtol=1e-12, atol=1e-6)
+        ok = ok and np.allclose(ne["U"][1:], full["U"][f0 + 1:f1], rtol=1e-12, atol=1e-6)
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_inertial_blocks_with_ghost_frames_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_inertial, args=(r, 2, 29733, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(180)
+        assert pr.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def test_shard_frames_partition():
     sys.path.insert(0, ROOT)
     from vicalib_b200 import synth
