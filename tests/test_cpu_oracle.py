@@ -146,3 +146,20 @@ def test_imu_weights_are_sqrt_information():
     o2 = Oracle(p, inertial=1, rotation_only=1)
     o2.update_imu_weights()
     assert np.array_equal(o2.imu_weights()[0], 500 * np.eye(9))
+
+
+def test_extrinsic_columns_are_a_constant_map_of_the_pose_columns():
+    """The identity behind the reduced Gram formulation of the CUDA build phase: for one camera the six
+    T_ck columns of the reprojection Jacobian are  J_pose * A  with  A = [[0, -R_ck^T], [-I, 0]]  for every corner,
+    because both perturbations are right perturbations acting on the same point.  Checked on the oracle's dual-number
+    Jacobians (independent of the kernels), all five models."""
+    for models in (("linear",), ("fov",), ("poly2",), ("poly3",), ("kb4",)):
+        p = synth.make_problem(models=models, n_frames=5, grid=(14, 10), seed=8)
+        o = Oracle(p)
+        _, J = o.eval_reproj()          # [n_obs, 2, 12 + K]: pose (t, w), extrinsics (w_ck, p_ck), intrinsics
+        R = synth.quat_to_mat(p.q_ck[0])
+        A = np.zeros((6, 6))
+        A[0:3, 3:6] = -R.T
+        A[3:6, 0:3] = -np.eye(3)
+        Jp, Je = J[:, :, 0:6], J[:, :, 6:12]
+        assert np.abs(Jp @ A - Je).max() <= 1e-12 * np.abs(J).max(), models
