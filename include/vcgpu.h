@@ -192,7 +192,9 @@ enum {
   VCGPU_STAGE_FINALIZE = 7,     /* level 2 + cost + gradient norms */
   VCGPU_STAGE_IMU_EVAL = 8,     /* IMU residual + Jacobian */
   VCGPU_STAGE_IMU_WEIGHTS = 9,  /* UpdateImuWeights */
-  VCGPU_STAGE_GRID_SYNC = 10,   /* persistent kernel: the two grid barriers of an iteration */
+  VCGPU_STAGE_GRID_SYNC = 10,   /* persistent vision kernel: the two grid barriers of an iteration */
+  VCGPU_STAGE_EVAL_TASKS = 11,  /* persistent inertial kernels: IMU residual/Jacobian + reprojection evaluate/build (one task queue) */
+  VCGPU_STAGE_IMU_ACCUM = 12,   /* persistent inertial kernels: J^T J of the IMU factors into the frame blocks */
   VCGPU_STAGE_COUNT = 16
 };
 /* Measured FP64 throughput of `device` in TFLOP/s (FMA = 2 flop): independent DFMA chains and independent

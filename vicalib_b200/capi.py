@@ -272,7 +272,7 @@ class Calibrator:
         return x
 
     STAGES = ["diag", "frame_solve", "global_solve", "backsub", "eval_reproj", "build_frames", "reduce_globals",
-              "finalize", "imu_eval", "imu_weights", "grid_sync"]
+              "finalize", "imu_eval", "imu_weights", "grid_sync", "eval_tasks", "imu_accumulate"]
 
     def set_profiling(self, profile=True, flush_l2=False):
         self._chk(self.L.vcgpu_set_profiling(self.h, C.c_int(int(profile)), C.c_int(int(flush_l2))))

@@ -99,12 +99,114 @@ static int eval_reproj(vcgpu_handle* h, int which, bool jac, bool apply_loss, co
   return VCGPU_OK;
 }
 
+// ------------------------------------------------------------------ persistent inertial kernels (one GPU)
+// chain_solve_kernel + eval_mega_kernel (vc_imu_mega.cuh, vc_imu_eval_mega.cuh): two cooperative launches per iteration
+static bool imu_mega_applies(const vcgpu_handle* h) {
+  return h->imu_mega_ok && h->dp.inertial && h->nranks == 1 && !h->materialize && !h->multi_launch;
+}
+static int imu_mega_prepare(vcgpu_handle* h) {
+  const DevProblem& dp = h->dp;
+  h->imu_mega_ok = false;
+  if (!dp.inertial || h->nranks > 1) return VCGPU_OK;
+  if (h->dev_sms == 0) {
+    int coop = 0, smem_optin = 0, sms = 0;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    h->dev_sms = sms;
+    h->dev_smem_optin = coop ? smem_optin : 0;
+  }
+  const size_t sm_solve = chain_solve_smem_doubles(dp.G) * sizeof(double);
+  const size_t sm_eval = eval_mega_smem_doubles(dp.G) * sizeof(double);
+  vc::ImuDev* d = imu_dev(h);
+  if (h->dev_smem_optin == 0 || sm_solve > static_cast<size_t>(h->dev_smem_optin) || sm_eval > static_cast<size_t>(h->dev_smem_optin) ||
+      d->levels.size() > static_cast<size_t>(kMaxChainLevels))
+    return VCGPU_OK;  // does not fit: the multi-launch engine runs the solve
+  CUDA_TRY(h, cudaFuncSetAttribute(chain_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_solve)));
+  CUDA_TRY(h, cudaFuncSetAttribute(eval_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_eval)));
+  int per_sm = 0;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_solve_kernel, kCsThreads, sm_solve));
+  if (per_sm < 1) return VCGPU_OK;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eval_mega_kernel, kEvThreads, sm_eval));
+  if (per_sm < 1) return VCGPU_OK;
+  const int grid = h->dev_sms;
+  const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
+  VC_TRY(dev_alloc(h, &h->d_Spart, std::max<size_t>(static_cast<size_t>(grid) * kCsGroups, std::max(h->n_solve_blocks, d->n_part)) * NS));
+  VC_TRY(dev_alloc(h, &h->d_Cpart, std::max<size_t>(grid, kReduceBlocks) * NS));
+  VC_TRY(dev_alloc(h, &h->d_red_part, 8 * std::max<size_t>(grid, kReduceBlocks)));
+  VC_TRY(dev_alloc(h, &h->d_red, 4 * (std::max<size_t>(dp.n_frames, grid) + 2)));
+  VC_TRY(dev_alloc(h, &h->d_prof2, 16));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_prof2, 0, 16 * sizeof(unsigned long long), h->stream));
+  h->imu_mega_grid = grid;
+  h->imu_mega_ok = true;
+  return VCGPU_OK;
+}
+static int imu_mega_solve(vcgpu_handle* h, const double* D2x, bool do_update) {
+  vc::ImuDev* d = imu_dev(h);
+  const DevProblem& dp = h->dp;
+  ChainSolveArgs ca;
+  ca.dp = dp; ca.b[0] = h->blk[0]; ca.b[1] = h->blk[1]; ca.ctl = h->d_ctl; ca.scale = h->d_scale; ca.D2x = D2x;
+  ca.n_levels = static_cast<int>(d->levels.size());
+  for (int l = 0; l < ca.n_levels; ++l) ca.lev[l] = d->levels[l];
+  ca.Spart = h->d_Spart; ca.Ssum = d->Ssum; ca.delta = h->d_delta; ca.scalars = h->d_scalars;
+  ca.state[0] = h->d_state[0]; ca.state[1] = h->d_state[1]; ca.step_part = h->d_red; ca.do_update = do_update ? 1 : 0;
+  ca.prof = (h->phase_clocks || h->profiling) ? h->d_prof2 : nullptr;
+  void* args[] = {&ca};
+  CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chain_solve_kernel), dim3(h->imu_mega_grid), dim3(kCsThreads), args,
+                                          chain_solve_smem_doubles(dp.G) * sizeof(double), h->stream));
+  ++h->launches;
+  if (do_update) h->n_step_part = h->imu_mega_grid + 1;
+  return VCGPU_OK;
+}
+static int wts_join(vcgpu_handle* h);
+static int imu_mega_eval(vcgpu_handle* h, int which, bool with_step, int decide_mode, bool weights) {
+  VC_TRY(wts_join(h));
+  vc::ImuDev* d = imu_dev(h);
+  const DevProblem& dp = h->dp;
+  const bool visual = h->flags.visual && h->n_obs > 0;
+  EvalMegaArgs ea;
+  ea.dp = dp;
+  if (!visual) ea.dp.n_cams = 0;
+  ea.ctl = h->d_ctl; ea.which = which; ea.decide_mode = decide_mode; ea.do_weights = weights ? 1 : 0;
+  ea.state[0] = h->d_state[0]; ea.state[1] = h->d_state[1]; ea.blk[0] = h->blk[0]; ea.blk[1] = h->blk[1];
+  ea.grp_start = h->d_grp_start; ea.grp_count = h->d_grp_count; ea.group_of = h->d_group_of;
+  ea.pw = h->d_pw; ea.pc = h->d_pc; ea.mask = h->d_mask; ea.Cg = h->d_Cg; ea.cost_part = h->d_cost_part;
+  ea.buf = d->buf; ea.ftime = d->ftime; ea.wsqrt = h->d_wsqrt; ea.imu_r = h->d_imu_r; ea.imu_J = h->d_imu_J;
+  ea.imu_cost = d->cost; ea.imuCg = d->Cg; ea.sigma_g = h->sigma_g; ea.sigma_a = h->sigma_a;
+  ea.Cpart = h->d_Cpart; ea.red_part = h->d_red_part;
+  ea.step_part = with_step ? h->d_red : nullptr; ea.n_step_part = h->n_step_part;
+  ea.scalars = h->d_scalars; ea.counter = h->d_counter + 2;
+  ea.prof = (h->phase_clocks || h->profiling) ? h->d_prof2 + 8 : nullptr;
+  void* args[] = {&ea};
+  CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(eval_mega_kernel), dim3(h->imu_mega_grid), dim3(kEvThreads), args,
+                                          eval_mega_smem_doubles(dp.G) * sizeof(double), h->stream));
+  ++h->launches;
+  return VCGPU_OK;
+}
+// fold the persistent inertial kernels' phase clocks into the stage times (call after a stream synchronise)
+static int imu_mega_collect_clocks(vcgpu_handle* h, int iters) {
+  if (!(h->phase_clocks || h->profiling) || !h->d_prof2 || !h->imu_mega_ok) return VCGPU_OK;
+  unsigned long long ns[16];
+  CUDA_TRY(h, cudaMemcpy(ns, h->d_prof2, sizeof ns, cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemset(h->d_prof2, 0, sizeof ns));
+  const int map_s[kCsProfCount] = {VCGPU_STAGE_FRAME_SOLVE, VCGPU_STAGE_FRAME_SOLVE, VCGPU_STAGE_GLOBAL_SOLVE, VCGPU_STAGE_GLOBAL_SOLVE,
+                                   VCGPU_STAGE_BACKSUB, VCGPU_STAGE_BACKSUB};
+  const int map_e[kEvProfCount] = {VCGPU_STAGE_EVAL_TASKS, VCGPU_STAGE_IMU_ACCUM, VCGPU_STAGE_REDUCE, VCGPU_STAGE_FINALIZE,
+                                   VCGPU_STAGE_IMU_WEIGHTS};
+  bool seen[VCGPU_STAGE_COUNT] = {};
+  for (int k = 0; k < kCsProfCount; ++k) { h->st_ms[map_s[k]] += ns[k] * 1e-6; seen[map_s[k]] = true; }
+  for (int k = 0; k < kEvProfCount; ++k) { h->st_ms[map_e[k]] += ns[8 + k] * 1e-6; seen[map_e[k]] = true; }
+  for (int s = 0; s < VCGPU_STAGE_COUNT; ++s) if (seen[s]) h->st_n[s] += iters;
+  return VCGPU_OK;
+}
+
 // ------------------------------------------------------------------ evaluation pass
 // which = 0: the accepted point (buffers[cur]); which = 1: the trial point (buffers[1-cur]).
 // Residuals, Jacobians and block normal equations land in blk[buffer]; cost / gradient norms (and
 // the step reductions when with_step) land in d_scalars for decide_step.
 static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_mode, const double* D2x = nullptr) {
   const DevProblem& dp = h->dp;
+  if (imu_mega_applies(h)) return imu_mega_eval(h, which, with_step, decide_mode, false);
   const bool visual = h->flags.visual && h->n_obs > 0;
   const bool fused = !h->materialize;
   if (visual && !fused) {
@@ -168,7 +270,7 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     ra.imu_cost_part = imu_cost_part(h); ra.n_imu_cost_part = n_imu_cost;
     ra.step_part = with_step ? h->d_red : nullptr;
     // the last step_part slot is the globals' share: counted once (rank 0) in a sharded run
-    ra.n_step_part = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps + (h->rank == 0 ? 1 : 0);
+    ra.n_step_part = h->n_step_part - (h->rank == 0 ? 0 : 1);
     ra.n_frames_fd = dp.n_frames * dp.fd;
     ra.out[0] = h->blk[0]; ra.out[1] = h->blk[1]; ra.scalars = h->d_scalars; ra.counter = h->d_counter;
     reduce_finalize_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
@@ -207,7 +309,9 @@ static int read_scalars(vcgpu_handle* h) {
 static int solve_and_update(vcgpu_handle* h, const double* D2x, bool with_update_in_eval) {
   const DevProblem& dp = h->dp;
   const size_t NS = static_cast<size_t>(dp.G) * dp.G + dp.G;
-  if (dp.inertial) {
+  if (dp.inertial && imu_mega_applies(h)) {
+    VC_TRY(imu_mega_solve(h, D2x, true));
+  } else if (dp.inertial) {
     {
       StageScope st(h, VCGPU_STAGE_FRAME_SOLVE);
       VC_TRY(imu_chain_eliminate(h, D2x));
@@ -258,6 +362,7 @@ static int solve_and_update(vcgpu_handle* h, const double* D2x, bool with_update
       const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
       backsub_update_kernel<6><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
       ++h->launches;
+      h->n_step_part = nb + 1;
     }
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -377,6 +482,7 @@ static int enqueue_dogleg_iteration(vcgpu_handle* h, bool weights) {
     if (dp.fd == 6) backsub_update_kernel<6><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
     else backsub_update_kernel<9><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
     ++h->launches;
+    h->n_step_part = nb + 1;
   }
   VC_TRY(evaluate_into(h, 1, true, -1));
   dl_decide_kernel<<<1, 32, 0, h->stream>>>(h->d_ctl, h->d_scalars);
@@ -390,6 +496,10 @@ static int enqueue_dogleg_iteration(vcgpu_handle* h, bool weights) {
 static int enqueue_iteration(vcgpu_handle* h, bool weights) {
   if (h->opts.strategy == 1) return enqueue_dogleg_iteration(h, weights);
   if (mega_applies(h)) return mega_launch(h, 1);
+  if (imu_mega_applies(h)) {  // two cooperative launches: solve + update, evaluate + decide + UpdateImuWeights
+    VC_TRY(imu_mega_solve(h, nullptr, true));
+    return imu_mega_eval(h, 1, true, 1, weights);
+  }
   VC_TRY(solve_and_update(h, nullptr, false));
   VC_TRY(evaluate_into(h, 1, true, 1));
   if (weights) VC_TRY(imu_update_weights(h, true));  // the reference's iteration callback (vicalibrator.h:691)
@@ -499,6 +609,7 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
   sum.device_seconds = (h->flush_l2 ? flushed_ms : ms) * 1e-3;
   sum.kernel_launches = static_cast<int>(h->launches - launches0);
   VC_TRY(mega_collect_clocks(h, c.iter));
+  VC_TRY(imu_mega_collect_clocks(h, c.iter));
   h->blocks_valid = true;
   VC_TRY(download_state(h));
   write_mirrors(h);

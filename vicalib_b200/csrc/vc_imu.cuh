@@ -50,12 +50,9 @@ __device__ __forceinline__ void se3_local_column(const double* x, int col, doubl
 
 constexpr int kImuWarps = 4;
 
-__global__ void __launch_bounds__(32 * kImuWarps) imu_eval_kernel(ImuEvalArgs a) {
+// residual (9) and tangent Jacobian (9 x 33) of interval k by one warp: lane -> Jacobian column
+__device__ __forceinline__ void imu_eval_interval(const ImuEvalArgs& a, int k, int lane, const double* state) {
   using imu::D1;
-  const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * kImuWarps + (threadIdx.x >> 5);
-  if (k >= a.ni || a.ctl->done) return;
-  const double* state = a.states[a.which ? 1 - a.ctl->cur : a.ctl->cur];
   // lane -> Jacobian column: pose2 0-5 | pose1 6-11 | (v2 12-14 analytic) | v1 15-17 | g 18-19 | b 20-25 | sf 26-31 | ts 32
   const int col = lane < 12 ? lane : lane + 3;
   const double* X2 = state + 7 * static_cast<int64_t>(k + 1);
@@ -143,6 +140,13 @@ __global__ void __launch_bounds__(32 * kImuWarps) imu_eval_kernel(ImuEvalArgs a)
   }
 }
 
+__global__ void __launch_bounds__(32 * kImuWarps) imu_eval_kernel(ImuEvalArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kImuWarps + (threadIdx.x >> 5);
+  if (k >= a.ni || a.ctl->done) return;
+  imu_eval_interval(a, k, lane, a.states[a.which ? 1 - a.ctl->cur : a.ctl->cur]);
+}
+
 // ---------------------------------------------------------------- IMU -> frame blocks
 struct ImuAccArgs {
   DevProblem dp;
@@ -157,12 +161,12 @@ struct ImuAccArgs {
 __device__ __forceinline__ int imu_local_col(int c) {
   return c < 6 ? 6 + c : c < 9 ? 15 + (c - 6) : c < 15 ? (c - 9) : c < 18 ? 12 + (c - 15) : c;
 }
-__global__ void __launch_bounds__(128) imu_accumulate_kernel(ImuAccArgs a) {
-  // one CTA per frame f: interval f-1 (f is its second frame) and interval f (f is its first frame)
-  __shared__ double Jl[2][9][34];  // [which][row][local col 0..32, 33 = residual]
-  if (a.ctl->done) return;
-  const Blocks& out = a.outs[a.which ? 1 - a.ctl->cur : a.ctl->cur];
-  const int f = blockIdx.x, tid = threadIdx.x, G = a.dp.G, nf = a.dp.n_frames, io = a.dp.imu_goff;
+// frame f by a group of 128 threads: interval f-1 (f is its second frame) and interval f (f is its first frame).
+// Jl: the group's [2][9][34] staging area ([which][row][local col 0..32, 33 = residual]); SYNC: the group's barrier
+template <class SYNC>
+__device__ __forceinline__ void imu_accumulate_frame(const ImuAccArgs& a, const Blocks& out, int f, int tid, double (*Jl)[9][34],
+                                                     SYNC sync) {
+  const int G = a.dp.G, nf = a.dp.n_frames, io = a.dp.imu_goff;
   const bool hasP = f > 0, hasN = f < nf - 1;
   for (int e = tid; e < 2 * 9 * 34; e += 128) {
     const int which = e / (9 * 34), row = (e / 34) % 9, c = e % 34;
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(128) imu_accumulate_kernel(ImuAccArgs a) {
     if (k >= 0 && k < a.ni) v = c < 33 ? a.J[static_cast<int64_t>(k) * 297 + row * 33 + imu_local_col(c)] : a.r[static_cast<int64_t>(k) * 9 + row];
     Jl[which][row][c] = v;
   }
-  __syncthreads();
+  sync();
   const double m = a.dp.imu_mult;
   double* Bf = out.B + static_cast<int64_t>(f) * 81;
   double* Uf = out.U + static_cast<int64_t>(f) * 81;
@@ -223,6 +227,11 @@ __global__ void __launch_bounds__(128) imu_accumulate_kernel(ImuAccArgs a) {
       a.Cg[static_cast<int64_t>(f) * kImuCgStride + q] = s * m;
     }
   }
+}
+__global__ void __launch_bounds__(128) imu_accumulate_kernel(ImuAccArgs a) {
+  __shared__ double Jl[2][9][34];
+  if (a.ctl->done) return;
+  imu_accumulate_frame(a, a.outs[a.which ? 1 - a.ctl->cur : a.ctl->cur], blockIdx.x, threadIdx.x, Jl, [] { __syncthreads(); });
 }
 
 }  // namespace vc

@@ -241,6 +241,7 @@ static int imu_chain_backsub(vcgpu_handle* h, const double* D2x, bool explicit_u
     const int nb = (dp.n_frames + kUpdateWarps - 1) / kUpdateWarps;
     backsub_update_kernel<9><<<nb, 32 * kUpdateWarps, 0, h->stream>>>(ua);
     ++h->launches;
+    h->n_step_part = nb + 1;
   }
   CUDA_TRY(h, cudaGetLastError());
   return VCGPU_OK;
@@ -272,7 +273,7 @@ static int imu_update_weights(vcgpu_handle* h, bool side_stream = false) {
   a.dp = dp; a.buf = d->buf; a.ctl = h->d_ctl; a.states[0] = h->d_state[0]; a.states[1] = h->d_state[1];
   a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
   a.ni = dp.n_frames - 1; a.sigma_g = h->sigma_g; a.sigma_a = h->sigma_a;
-  vc::wts::imu_weights_kernel<<<(a.ni + vc::wts::kWtWarps - 1) / vc::wts::kWtWarps, 32 * vc::wts::kWtWarps, 0, st_launch>>>(a);
+  vc::wts::imu_weights_kernel<<<(a.ni + vc::wts::kWtTeams - 1) / vc::wts::kWtTeams, 32 * vc::wts::kWtWarps, 0, st_launch>>>(a);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
   if (side_stream) {

@@ -1,0 +1,592 @@
+// Persistent (cooperative) kernels of the inertial trust-region iteration — one GPU.
+//
+// An inertial LM iteration used to be ~21 launches (chain_init, one chain_eliminate per level, sum_partials,
+// dense_solve, one chain_backsub per level, backsub_update, fused_build, imu_eval, imu_accumulate, reduce_finalize,
+// imu_weights).  Here it is TWO cooperative launches of one CTA per SM, with grid barriers where a launch boundary
+// used to be:
+//
+//   chain_solve_kernel   damped, Jacobi-scaled block-tridiagonal + arrow system (frame chain + dense globals):
+//                        level-0 blocks -> partitioned elimination level by level (every 4th node a separator;
+//                        a chunk = 3 interior nodes is swept by a GROUP of 128 threads, two groups per CTA, each
+//                        keeping its share of the Schur complement of the globals in shared memory across all
+//                        levels) -> distributed fixed-order sum of the groups' Schur partials -> dense Cholesky of
+//                        [globals | top nodes] by every CTA -> back-substitution level by level -> x (+) step into
+//                        the trial state + step statistics
+//   eval_kernel          (vc_imu_eval_mega.cuh) residuals + Jacobians + block normal equations at the trial point,
+//                        reduction, accept/reject, UpdateImuWeights
+//
+// Replaces what ceres::Solve does per iteration for the inertial stages (vicalibrator.h:956; SPARSE_NORMAL_CHOLESKY
+// on the block-tridiagonal + arrow J^T J).  Same arithmetic as vc_chain.cuh's kernels (which remain
+// the engine of frame-sharded runs, where an NCCL all-reduce sits between assembling and factoring the dense system).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "vc_chain.cuh"
+#include "vc_kernels.cuh"
+#include "vc_mega.cuh"
+
+namespace vc {
+
+constexpr int kMaxChainLevels = 10;
+constexpr int kCsThreads = 256;              // threads per CTA
+constexpr int kCsGroup = 128;                // threads per elimination group
+constexpr int kCsGroups = kCsThreads / kCsGroup;
+constexpr int kCsChunk = 4;                  // every 4th node of a level is a separator
+enum { kCsProfInit = 0, kCsProfElim, kCsProfReduce, kCsProfDense, kCsProfBacksub, kCsProfUpdate, kCsProfCount };
+
+struct ChainSolveArgs {
+  DevProblem dp;
+  Blocks b[2];
+  Ctl* ctl;
+  const double* scale;
+  const double* D2x;            // explicit damping (inspection hook / dogleg) or null: LM rule
+  ChainLevel lev[kMaxChainLevels];
+  int n_levels;
+  double* Spart;                // [grid * kCsGroups][G*G+G]
+  double* Ssum;                 // [G*G+G]
+  double* delta;                // scaled step [nf*9 + G]
+  double* scalars;
+  double* state[2];
+  double* step_part;            // [grid + 1][4]
+  int do_update;                // 1: trial state + step statistics
+  unsigned long long* prof;     // [kCsProfCount] ns per phase (CTA 0) or null
+};
+
+__host__ __device__ inline size_t chain_group_doubles(int G) {
+  constexpr int FD = 9;
+  const size_t NS = static_cast<size_t>(G) * G + G, VW = FD + 2 * FD + G + 1;
+  return NS + 3 * FD * FD + FD * G + FD + (kCsChunk - 1) * FD * VW + (kCsChunk - 1) * FD * G;
+}
+__host__ __device__ inline size_t chain_solve_smem_doubles(int G) {
+  const size_t grp = kCsGroups * chain_group_doubles(G);
+  const size_t N = static_cast<size_t>(G) + kCsChunk * 9;
+  const size_t dense = N * N + N;
+  return (grp > dense ? grp : dense) + 16;
+}
+
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(kCsGroup) : "memory");
+}
+
+// Forward + backward sweep of one chunk (separator s = j*c, interior nodes s+1..s+m) by one group of 128 threads.
+// Same algorithm as chain_eliminate_kernel (vc_chain.cuh); the group's Schur accumulator Sacc lives on across calls.
+template <int FD>
+__device__ inline void chain_eliminate_chunk(const ChainLevel& L, const ChainLevel& nxt, int G, int j, double* sm, int tid,
+                                             int grp, int* bad) {
+  constexpr int c = kCsChunk, NT = kCsGroup;
+  const int NS = G * G + G;
+  const int w = 2 * FD + G + 1, VW = FD + w;
+  const int oL = FD, oR = 2 * FD, oE = 3 * FD, og = 3 * FD + G;  // column offsets inside a V row
+  double* Sacc = sm;                       // [NS]
+  double* Al = Sacc + NS;                  // [FD*FD]
+  double* El = Al + FD * FD;               // [FD*G]
+  double* gl = El + FD * G;                // [FD]
+  double* Ap = gl + FD;                    // [FD*FD] pivot
+  double* Uc = Ap + FD * FD;               // [FD*FD] U[p]
+  double* V = Uc + FD * FD;                // [(c-1)][FD][VW]
+  double* Eo = V + (c - 1) * FD * VW;      // [(c-1)][FD*G] the interior nodes' own global coupling
+  const int s = j * c, n_eff = L.n - L.ghost;
+  const int nsep = (n_eff + c - 1) / c;
+  const bool toGhost = L.ghost && !(s + c < n_eff);
+  const bool hasR = s + c < n_eff || toGhost;
+  const int m = min(c - 1, n_eff - 1 - s);
+  const int rIdx = s + m + 1;
+  const int jr = toGhost ? nsep : j + 1;
+  const bool add = L.addA != nullptr;
+  group_sync(grp);  // the previous chunk of this group is done with the workspace
+  for (int e = tid; e < FD * FD; e += NT)
+    Al[e] = L.A[static_cast<int64_t>(s) * FD * FD + e] + (add ? L.addA[static_cast<int64_t>(s) * FD * FD + e] : 0.0);
+  for (int e = tid; e < FD * G; e += NT)
+    El[e] = L.E[static_cast<int64_t>(s) * FD * G + e] + (add ? L.addE[static_cast<int64_t>(s) * FD * G + e] : 0.0);
+  for (int e = tid; e < FD; e += NT)
+    gl[e] = L.g[static_cast<int64_t>(s) * FD + e] + (add ? L.addg[static_cast<int64_t>(s) * FD + e] : 0.0);
+  // all interior nodes' right-hand sides at once (one round of global loads instead of one per node)
+  for (int i = 0; i < m; ++i) {
+    const int64_t p = s + 1 + i;
+    double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+    const bool lastI = i == m - 1;
+    for (int e = tid; e < FD * FD; e += NT) {
+      const int r = e / FD, q = e - r * FD;
+      const double unext = (!lastI || hasR) ? L.U[(p + 1) * FD * FD + e] : 0.0;  // H[p, p+1]
+      Vi[r * VW + q] = lastI ? 0.0 : unext;
+      Vi[r * VW + oR + q] = (lastI && hasR) ? unext : 0.0;
+      Vi[r * VW + oL + q] = i == 0 ? L.U[p * FD * FD + q * FD + r] : 0.0;  // H[p0, s] = U[p0]^T
+    }
+    for (int e = tid; e < FD * G; e += NT) {
+      const int r = e / G, q = e - r * G;
+      const double v = L.E[p * FD * G + e] + (add ? L.addE[p * FD * G + e] : 0.0);
+      Vi[r * VW + oE + q] = v;
+      Eo[i * FD * G + e] = v;
+    }
+    for (int e = tid; e < FD; e += NT) Vi[e * VW + og] = L.g[p * FD + e] + (add ? L.addg[p * FD + e] : 0.0);
+  }
+  // ---- forward sweep
+  for (int i = 0; i < m; ++i) {
+    const int64_t p = s + 1 + i;
+    double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+    for (int e = tid; e < FD * FD; e += NT) {
+      Ap[e] = L.A[p * FD * FD + e] + (add ? L.addA[p * FD * FD + e] : 0.0);
+      Uc[e] = L.U[p * FD * FD + e];
+    }
+    group_sync(grp);
+    if (i > 0) {
+      const double* Vp = V + static_cast<int64_t>(i - 1) * FD * VW;
+      // A'_i = A_i - U^T V_U(i-1);  R'_i = R_i - U^T V_R(i-1)
+      for (int e = tid; e < FD * VW; e += NT) {
+        const int r = e / VW, q = e - r * VW;
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < FD; ++k) sum += Uc[k * FD + r] * Vp[k * VW + q];
+        if (q < FD) Ap[r * FD + q] -= sum;
+        else Vi[r * VW + q] -= sum;
+      }
+      group_sync(grp);
+    }
+    if (tid < VW) {
+      // every column-solving thread factors the FD x FD pivot in registers (no serial section, no barrier)
+      double Lr[FD][FD], iL[FD];
+#pragma unroll
+      for (int ii = 0; ii < FD; ++ii)
+#pragma unroll
+        for (int k = 0; k <= ii; ++k) Lr[ii][k] = Ap[ii * FD + k];
+      bool ok = true;
+#pragma unroll
+      for (int jj = 0; jj < FD; ++jj) {
+        double d = Lr[jj][jj];
+#pragma unroll
+        for (int k = 0; k < jj; ++k) d -= Lr[jj][k] * Lr[jj][k];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        d = sqrt(d);
+        Lr[jj][jj] = d;
+        const double inv = 1.0 / d;
+        iL[jj] = inv;
+#pragma unroll
+        for (int ii = jj + 1; ii < FD; ++ii) {
+          double t = Lr[ii][jj];
+#pragma unroll
+          for (int k = 0; k < jj; ++k) t -= Lr[ii][k] * Lr[jj][k];
+          Lr[ii][jj] = t * inv;
+        }
+      }
+      if (!ok && tid == 0) *bad = 1;
+      for (int q = tid; q < VW; q += NT) {
+        double x[FD];
+#pragma unroll
+        for (int ii = 0; ii < FD; ++ii) {
+          double t = Vi[ii * VW + q];
+#pragma unroll
+          for (int k = 0; k < ii; ++k) t -= Lr[ii][k] * x[k];
+          x[ii] = t * iL[ii];
+        }
+#pragma unroll
+        for (int ii = FD - 1; ii >= 0; --ii) {
+          double t = x[ii];
+#pragma unroll
+          for (int k = ii + 1; k < FD; ++k) t -= Lr[k][ii] * x[k];
+          x[ii] = t * iL[ii];
+        }
+#pragma unroll
+        for (int ii = 0; ii < FD; ++ii) Vi[ii * VW + q] = x[ii];
+      }
+    }
+    group_sync(grp);
+  }
+  // ---- backward sweep: X_i = V_R(i) - V_U(i) X_{i+1}
+  for (int i = m - 2; i >= 0; --i) {
+    double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+    const double* Vn = V + static_cast<int64_t>(i + 1) * FD * VW;
+    for (int e = tid; e < FD * w; e += NT) {
+      const int r = e / w, q = FD + (e - r * w);
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < FD; ++k) sum += Vi[r * VW + k] * Vn[k * VW + q];
+      Vi[r * VW + q] -= sum;
+    }
+    group_sync(grp);
+  }
+  // ---- store Z, accumulate the Schur terms: S += E_i^T X_i[E], rhs += E_i^T X_i[g]
+  for (int i = 0; i < m; ++i) {
+    const int64_t p = s + 1 + i;
+    const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+    for (int e = tid; e < FD * w; e += NT) {
+      const int r = e / w, q = e - r * w;
+      L.Z[(p * FD + r) * w + q] = Vi[r * VW + FD + q];
+    }
+  }
+  for (int e = tid; e < NS; e += NT) {
+    const int ra = e < G * G ? e / G : e - G * G;
+    const int cb = e < G * G ? oE + (e - ra * G) : og;
+    double sum = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+      const double* Ei = Eo + i * FD * G;
+#pragma unroll
+      for (int k = 0; k < FD; ++k) sum += Ei[k * G + ra] * Vi[k * VW + cb];
+    }
+    Sacc[e] += sum;
+  }
+  if (m > 0) {
+    const double* X0 = V;                                          // node s+1
+    const double* Xl = V + static_cast<int64_t>(m - 1) * FD * VW;  // last interior node
+    const double* U0 = L.U + static_cast<int64_t>(s + 1) * FD * FD;  // H[s, s+1]
+    const double* Ur = hasR ? L.U + static_cast<int64_t>(rIdx) * FD * FD : nullptr;  // H[rIdx-1, rIdx]
+    for (int e = tid; e < FD * w; e += NT) {
+      const int r = e / w, q = e - r * w;  // q indexes [L | R | E | g]
+      double sl = 0.0, sr = 0.0;
+#pragma unroll
+      for (int k = 0; k < FD; ++k) {
+        sl += U0[r * FD + k] * X0[k * VW + FD + q];
+        if (hasR) sr += Ur[k * FD + r] * Xl[k * VW + FD + q];
+      }
+      if (q < FD) {
+        Al[r * FD + q] -= sl;                                        // A_s -= H[s,p0] Z_L
+      } else if (q < 2 * FD) {
+        if (hasR) {
+          nxt.U[static_cast<int64_t>(jr) * FD * FD + r * FD + (q - FD)] = -sl;     // fill H[s, rIdx]
+          nxt.addA[static_cast<int64_t>(jr) * FD * FD + r * FD + (q - FD)] = -sr;  // A_r -= H[r,pl] Z_R
+        }
+      } else if (q < 2 * FD + G) {
+        El[r * G + (q - 2 * FD)] -= sl;
+        if (hasR) nxt.addE[static_cast<int64_t>(jr) * FD * G + r * G + (q - 2 * FD)] = -sr;
+      } else {
+        gl[r] -= sl;
+        if (hasR) nxt.addg[static_cast<int64_t>(jr) * FD + r] = -sr;
+      }
+    }
+  } else if (hasR) {
+    // no interior node between this separator and the ghost: the coupling passes through unchanged
+    for (int e = tid; e < FD * FD; e += NT) {
+      nxt.U[static_cast<int64_t>(jr) * FD * FD + e] = L.U[static_cast<int64_t>(rIdx) * FD * FD + e];
+      nxt.addA[static_cast<int64_t>(jr) * FD * FD + e] = 0.0;
+    }
+    for (int e = tid; e < FD * G; e += NT) nxt.addE[static_cast<int64_t>(jr) * FD * G + e] = 0.0;
+    for (int e = tid; e < FD; e += NT) nxt.addg[static_cast<int64_t>(jr) * FD + e] = 0.0;
+  }
+  if (toGhost) {  // carry the ghost node itself to the next level (its Schur updates went to nxt.add*)
+    for (int e = tid; e < FD * FD; e += NT)
+      nxt.A[static_cast<int64_t>(jr) * FD * FD + e] = L.A[static_cast<int64_t>(rIdx) * FD * FD + e] + (add ? L.addA[static_cast<int64_t>(rIdx) * FD * FD + e] : 0.0);
+    for (int e = tid; e < FD * G; e += NT)
+      nxt.E[static_cast<int64_t>(jr) * FD * G + e] = L.E[static_cast<int64_t>(rIdx) * FD * G + e] + (add ? L.addE[static_cast<int64_t>(rIdx) * FD * G + e] : 0.0);
+    for (int e = tid; e < FD; e += NT)
+      nxt.g[static_cast<int64_t>(jr) * FD + e] = L.g[static_cast<int64_t>(rIdx) * FD + e] + (add ? L.addg[static_cast<int64_t>(rIdx) * FD + e] : 0.0);
+    if (tid == 0) nxt.orig[jr] = L.orig[rIdx];
+  }
+  group_sync(grp);
+  for (int e = tid; e < FD * FD; e += NT) {
+    nxt.A[static_cast<int64_t>(j) * FD * FD + e] = Al[e];
+    if (j == 0) { nxt.U[e] = 0.0; nxt.addA[e] = 0.0; }
+  }
+  for (int e = tid; e < FD * G; e += NT) {
+    nxt.E[static_cast<int64_t>(j) * FD * G + e] = El[e];
+    if (j == 0) nxt.addE[e] = 0.0;
+  }
+  for (int e = tid; e < FD; e += NT) {
+    nxt.g[static_cast<int64_t>(j) * FD + e] = gl[e];
+    if (j == 0) nxt.addg[e] = 0.0;
+  }
+  if (tid == 0) nxt.orig[j] = L.orig[s];
+}
+
+// One damped solve of the frame-chain + globals system and (optionally) the state update, all in one launch.
+__global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveArgs a) {
+  extern __shared__ double smem[];
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  constexpr int FD = 9;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid / kCsGroup, gtid = tid - grp * kCsGroup;
+  const int nb = gridDim.x, bid = blockIdx.x;
+  const int n_groups = nb * kCsGroups, gid = bid * kCsGroups + grp;
+  const int G = a.dp.G, NS = G * G + G, nf = a.dp.n_frames;
+  const int64_t nfp = static_cast<int64_t>(nf) * FD;
+  __shared__ int bad_s[kCsGroups];
+  __shared__ int bad_dense;
+  if (a.ctl->done) return;  // uniform over the grid: written before this launch
+  const Blocks& b = a.b[a.ctl->cur];
+  const double rinv = 1.0 / a.ctl->radius;
+  unsigned long long t_prev = 0;
+  const bool prof = a.prof != nullptr && bid == 0 && tid == 0;
+  if (prof) t_prev = global_ns();
+  auto mark = [&](int slot) {
+    if (prof) {
+      const unsigned long long t = global_ns();
+      a.prof[slot] += t - t_prev;
+      t_prev = t;
+    }
+  };
+  double* gsm = smem + static_cast<size_t>(grp) * chain_group_doubles(G);
+  if (gtid == 0) bad_s[grp] = 0;
+  for (int e = gtid; e < NS; e += kCsGroup) gsm[e] = 0.0;  // the group's Schur accumulator
+
+  // ------------------------------------------------------------ level 0: scaled + damped blocks
+  {
+    const ChainLevel& L = a.lev[0];
+    const double* sc = a.scale + nfp;
+    for (int f = gid; f < nf; f += n_groups) {
+      const double* sf = a.scale + static_cast<int64_t>(f) * FD;
+      for (int e = gtid; e < FD * FD; e += kCsGroup) {
+        const int r = e / FD, c = e - r * FD;
+        const double bij = b.B[static_cast<int64_t>(f) * FD * FD + e];
+        double v = bij * sf[r] * sf[c];
+        if (r == c) v += a.D2x ? a.D2x[static_cast<int64_t>(f) * FD + r] : lm_damp(bij, sf[r], rinv);
+        L.A[static_cast<int64_t>(f) * FD * FD + e] = v;
+        double u = 0.0;
+        if (f > 0) u = b.U[static_cast<int64_t>(f) * FD * FD + e] * a.scale[static_cast<int64_t>(f - 1) * FD + r] * sf[c];
+        L.U[static_cast<int64_t>(f) * FD * FD + e] = u;
+      }
+      for (int e = gtid; e < FD * G; e += kCsGroup) {
+        const int r = e / G, c = e - r * G;
+        L.E[static_cast<int64_t>(f) * FD * G + e] = b.E[static_cast<int64_t>(f) * FD * G + e] * sf[r] * sc[c];
+      }
+      for (int e = gtid; e < FD; e += kCsGroup) L.g[static_cast<int64_t>(f) * FD + e] = b.gf[static_cast<int64_t>(f) * FD + e] * sf[e];
+      if (gtid == 0) L.orig[f] = f;
+    }
+  }
+  mark(kCsProfInit);
+  grid.sync();
+  // ------------------------------------------------------------ elimination, level by level
+  for (int l = 0; l + 1 < a.n_levels; ++l) {
+    const ChainLevel& L = a.lev[l];
+    const int nsep = a.lev[l + 1].n - a.dp.ghost;
+    for (int j = gid; j < nsep; j += n_groups) chain_eliminate_chunk<FD>(L, a.lev[l + 1], G, j, gsm, gtid, grp, &bad_s[grp]);
+    if (l + 2 == a.n_levels) {  // last level: publish this group's Schur partial
+      group_sync(grp);
+      double* out = a.Spart + static_cast<int64_t>(gid) * NS;
+      for (int e = gtid; e < NS; e += kCsGroup) out[e] = gsm[e];
+      if (gtid == 0 && bad_s[grp]) a.scalars[kScNotPD] = 1.0;
+    }
+    grid.sync();
+  }
+  if (a.n_levels == 1) {  // nothing to eliminate: zero partials
+    double* out = a.Spart + static_cast<int64_t>(gid) * NS;
+    for (int e = gtid; e < NS; e += kCsGroup) out[e] = 0.0;
+    grid.sync();
+  }
+  mark(kCsProfElim);
+  // ------------------------------------------------------------ Schur partials -> total (fixed order), distributed
+  mega_reduce_stage1(a.Spart, NS, n_groups, NS, a.Ssum, -1, -1);
+  mark(kCsProfReduce);
+  grid.sync();
+  // ------------------------------------------------------------ dense solve of [globals | top nodes], every CTA
+  {
+    const ChainLevel& top = a.lev[a.n_levels - 1];
+    const int nt = top.n, N = G + nt * FD;
+    double* S = smem;
+    double* rhs = S + N * N;
+    const double* sc = a.scale + nfp;
+    if (tid == 0) bad_dense = 0;
+    for (int e = tid; e < N * N + N; e += kCsThreads) S[e] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < NS; e += kCsThreads) {
+      const double p = __ldcg(a.Ssum + e);
+      if (e < G * G) {
+        const int r = e / G, c = e - r * G;
+        double v = b.C[e] * sc[r] * sc[c] - p;
+        if (r == c) v += a.D2x ? a.D2x[nfp + r] : lm_damp(b.C[e], sc[r], rinv);
+        S[r * N + c] = v;
+      } else {
+        const int r = e - G * G;
+        rhs[r] = -b.gc[r] * sc[r] + p;
+      }
+    }
+    const bool add = top.addA != nullptr;
+    for (int t = 0; t < nt; ++t) {
+      const int o = G + t * FD;
+      for (int e = tid; e < FD * FD; e += kCsThreads) {
+        const int r = e / FD, c = e - r * FD;
+        S[(o + r) * N + o + c] = __ldcg(top.A + static_cast<int64_t>(t) * FD * FD + e) + (add ? __ldcg(top.addA + static_cast<int64_t>(t) * FD * FD + e) : 0.0);
+        if (t > 0) {
+          const int op = o - FD;
+          const double u = __ldcg(top.U + static_cast<int64_t>(t) * FD * FD + e);  // H[t-1, t]
+          S[(op + r) * N + o + c] = u;
+          S[(o + c) * N + op + r] = u;
+        }
+      }
+      for (int e = tid; e < FD * G; e += kCsThreads) {
+        const int r = e / G, c = e - r * G;
+        const double v = __ldcg(top.E + static_cast<int64_t>(t) * FD * G + e) + (add ? __ldcg(top.addE + static_cast<int64_t>(t) * FD * G + e) : 0.0);
+        S[(o + r) * N + c] = v;
+        S[c * N + o + r] = v;
+      }
+      for (int e = tid; e < FD; e += kCsThreads)
+        rhs[o + e] = -(__ldcg(top.g + static_cast<int64_t>(t) * FD + e) + (add ? __ldcg(top.addg + static_cast<int64_t>(t) * FD + e) : 0.0));
+    }
+    __syncthreads();
+    // right-looking Cholesky, lower triangle; the right-hand side rides along as row N
+    for (int j = 0; j < N; ++j) {
+      const double d0 = S[j * N + j];
+      const bool okp = d0 > 0.0;
+      const double inv = rsqrt(okp ? d0 : 1.0);
+      __syncthreads();
+      if (tid == 0) {
+        S[j * N + j] = (okp ? d0 : 1.0) * inv;
+        if (!okp) bad_dense = 1;
+      }
+      for (int i = j + 1 + tid; i <= N; i += kCsThreads) {
+        double* row = i < N ? S + i * N : rhs;
+        row[j] *= inv;
+      }
+      __syncthreads();
+      const int rem = N - j;  // rows j+1..N (N = rhs)
+      for (int e = tid; e < rem * (rem - 1); e += kCsThreads) {
+        const int ri = e / (rem - 1), ci = e - ri * (rem - 1);
+        const int i = j + 1 + ri, k = j + 1 + ci;
+        if (k > i || k >= N) continue;
+        double* row = i < N ? S + i * N : rhs;
+        row[k] -= row[j] * S[k * N + j];
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {  // L^T x = y (y = rhs after the forward elimination above)
+      for (int i = N - 1; i >= 0; --i) {
+        const double xi = rhs[i] / S[i * N + i];
+        __syncwarp();
+        if (lane == 0) rhs[i] = xi;
+        for (int k = lane; k < i; k += 32) rhs[k] -= S[i * N + k] * xi;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (bid == 0) {
+      const int bd = bad_dense;
+      for (int i = tid; i < G; i += kCsThreads) a.delta[nfp + i] = bd ? 0.0 : rhs[i];
+      for (int e = tid; e < nt * FD; e += kCsThreads) {
+        const int t = e / FD, r = e - t * FD;
+        a.delta[static_cast<int64_t>(top.orig[t]) * FD + r] = bd ? 0.0 : rhs[G + t * FD + r];
+      }
+      if (tid == 0 && bd) a.scalars[kScNotPD] = 1.0;
+    }
+  }
+  mark(kCsProfDense);
+  grid.sync();
+  // ------------------------------------------------------------ back-substitution, top-down
+  {
+    const int w = 2 * FD + G + 1, c = kCsChunk;
+    const int gw = bid * (kCsThreads / 32) + warp, nw = nb * (kCsThreads / 32);
+    const double* dc = a.delta + nfp;
+    for (int l = a.n_levels - 2; l >= 0; --l) {
+      const ChainLevel& cur = a.lev[l];
+      const int n_eff = cur.n - cur.ghost;
+      for (int p = gw; p < n_eff; p += nw) {
+        if (p % c == 0) continue;  // separators were solved at the level above
+        const int s = (p / c) * c;
+        const int r = s + c < n_eff ? s + c : (cur.ghost ? cur.n - 1 : cur.n);
+        const double* xl = a.delta + static_cast<int64_t>(cur.orig[s]) * FD;
+        const double* xr = r < cur.n ? a.delta + static_cast<int64_t>(cur.orig[r]) * FD : nullptr;
+        const double* Z = cur.Z + static_cast<int64_t>(p) * FD * w;
+        double* out = a.delta + static_cast<int64_t>(cur.orig[p]) * FD;
+#pragma unroll
+        for (int rr = 0; rr < FD; ++rr) {
+          const double* z = Z + rr * w;
+          double sum = 0.0;
+          for (int q = lane; q < w - 1; q += 32) {
+            const double x = q < FD ? __ldcg(xl + q) : q < 2 * FD ? (xr ? __ldcg(xr + q - FD) : 0.0) : __ldcg(dc + q - 2 * FD);
+            sum += __ldcg(z + q) * x;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) out[rr] = -__ldcg(z + w - 1) - sum;
+        }
+      }
+      grid.sync();
+    }
+  }
+  mark(kCsProfBacksub);
+  if (!a.do_update) return;
+  // ------------------------------------------------------------ x (+) step into the trial state, step statistics
+  {
+    const int cur = a.ctl->cur;
+    const double* x_cur = a.state[cur];
+    double* x_new = a.state[1 - cur];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int f = bid * kCsThreads + tid; f < nf; f += nb * kCsThreads) {
+      double du[FD];
+#pragma unroll
+      for (int r = 0; r < FD; ++r) {
+        const int64_t k = static_cast<int64_t>(f) * FD + r;
+        const double d = __ldcg(a.delta + k), sc = a.scale[k];
+        const double d2 = a.D2x ? a.D2x[k] : lm_damp(b.B[k * FD + r], sc, rinv);
+        acc[0] += d * b.gf[k] * sc;
+        acc[1] += d * d * d2;
+        du[r] = d * sc;
+      }
+      const double* x = x_cur + 7 * static_cast<int64_t>(f);
+      double xo[7];
+      se3_plus(x, du, xo);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        x_new[7 * static_cast<int64_t>(f) + k] = xo[k];
+        acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+        acc[3] += xo[k] * xo[k];
+      }
+      const double* v = x_cur + a.dp.off_v + 3 * static_cast<int64_t>(f);
+      double* vo = x_new + a.dp.off_v + 3 * static_cast<int64_t>(f);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double nv = v[k] + du[6 + k];
+        vo[k] = nv;
+        acc[2] += (nv - v[k]) * (nv - v[k]);
+        acc[3] += nv * nv;
+      }
+    }
+    __shared__ double part[kCsThreads / 32][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    if (lane == 0)
+      for (int q = 0; q < 4; ++q) part[warp][q] = acc[q];
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 0; q < 4; ++q) {
+        double s = 0.0;
+        for (int w = 0; w < kCsThreads / 32; ++w) s += part[w][q];
+        a.step_part[4 * static_cast<int64_t>(bid) + q] = s;
+      }
+    }
+    // globals: cameras + IMU parameters (one thread of the last CTA)
+    if (bid == nb - 1 && tid == kCsThreads - 1) {
+      double g4[4] = {0.0, 0.0, 0.0, 0.0};
+      const double* sc = a.scale + nfp;
+      const double* dc = a.delta + nfp;
+      for (int c = 0; c < a.dp.n_cams; ++c) {
+        const CamInfo& ci = a.dp.cams[c];
+        const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
+        double* xo = x_new + a.dp.off_cam + kCamStateStride * c;
+        double du[3];
+        for (int k = 0; k < 3; ++k) du[k] = __ldcg(dc + ci.goff + k) * sc[ci.goff + k];
+        double qo[4];
+        so3_plus(x, du, qo);
+        for (int k = 0; k < 4; ++k) xo[k] = qo[k];
+        for (int k = 0; k < 3; ++k) xo[4 + k] = x[4 + k] + __ldcg(dc + ci.goff + 3 + k) * sc[ci.goff + 3 + k];
+        for (int k = 0; k < 10; ++k)
+          xo[7 + k] = x[7 + k] + (k < ci.K ? __ldcg(dc + ci.goff + 6 + k) * sc[ci.goff + 6 + k] : 0.0);
+        for (int k = 0; k < 7 + ci.K; ++k) {
+          g4[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+          g4[3] += xo[k] * xo[k];
+        }
+      }
+      {
+        const double* x = x_cur + a.dp.off_imu;
+        double* xo = x_new + a.dp.off_imu;
+        for (int k = 0; k < kImuStateSize; ++k) {
+          const double dd = __ldcg(dc + a.dp.imu_goff + k) * sc[a.dp.imu_goff + k];
+          xo[k] = x[k] + dd;
+          g4[2] += dd * dd;
+          g4[3] += xo[k] * xo[k];
+        }
+      }
+      for (int k = 0; k < G; ++k) {
+        const double d2 = a.D2x ? a.D2x[nfp + k] : lm_damp(b.C[k * G + k], sc[k], rinv);
+        const double d = __ldcg(dc + k);
+        g4[0] += d * b.gc[k] * sc[k];
+        g4[1] += d * d * d2;
+      }
+      for (int q = 0; q < 4; ++q) a.step_part[4 * static_cast<int64_t>(nb) + q] = g4[q];
+    }
+  }
+  mark(kCsProfUpdate);
+}
+
+}  // namespace vc

@@ -1,5 +1,5 @@
-// UpdateImuWeights on the device: one warp per frame interval, small dense matrices in shared
-// memory, products shared across the lanes.
+// UpdateImuWeights on the device: a team of 16 lanes per frame interval (two teams per warp), small dense
+// matrices in shared memory, products shared across the lanes of the team.
 //
 // Reference being reproduced (formulas AS WRITTEN, approximations included):
 //   ViCalibrator::UpdateImuWeights                        vicalibrator.h:723-799
@@ -9,8 +9,9 @@
 //                                                         vicalibrator-utils.h:106-154,187-202,214-230,234-274,307-434
 // Only values that reach an output are computed: per IMU step
 //   C <- A C A^T + G R G^T,  A = d y/d y0 (10x10), G = d y/d b (10x6) of the full RK4 step,
-// then info = (Jt C Jt^T)^-1 and W = sqrtm(info) (principal root by cyclic Jacobi, equal to
-// Eigen's MatrixFunctions sqrt for the symmetric positive definite info matrix).
+// then info = (Jt C Jt^T)^-1 and W = sqrtm(info): with P = Jt C Jt^T = V L V^T (cyclic Jacobi), W = V L^-1/2 V^T —
+// the principal root Eigen's MatrixFunctions sqrt returns for the symmetric positive definite info matrix, without
+// forming the inverse.
 #pragma once
 #include "vc_imu_math.cuh"
 #include "vc_internal.h"
@@ -22,30 +23,6 @@ using imu::Meas;
 using imu::Pose;
 using imu::Quat;
 using imu::Vec;
-
-// out[R x C] = alpha * A[R x K] * op(B) (+ out if acc); transB: B is stored [C x K]
-__device__ __forceinline__ void wmm(double* out, const double* A, const double* B, int R, int K, int C, int lane,
-                                    bool transB = false, bool acc = false, double alpha = 1.0) {
-  for (int e = lane; e < R * C; e += 32) {
-    const int r = e / C, c = e - r * C;
-    double s = 0.0;
-    for (int k = 0; k < K; ++k) s += A[r * K + k] * (transB ? B[c * K + k] : B[k * C + c]);
-    out[e] = acc ? out[e] + alpha * s : alpha * s;
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void wzero(double* m, int n, int lane) {
-  for (int e = lane; e < n; e += 32) m[e] = 0.0;
-  __syncwarp();
-}
-__device__ __forceinline__ void wcopy(double* dst, const double* src, int n, int lane) {
-  for (int e = lane; e < n; e += 32) dst[e] = src[e];
-  __syncwarp();
-}
-__device__ __forceinline__ void waxpy(double* y, const double* x, double a, int n, int lane) {
-  for (int e = lane; e < n; e += 32) y[e] += a * x[e];
-  __syncwarp();
-}
 
 __device__ inline double powi(double x, int y) {  // vicalibrator-utils.h:69-82
   double r = x;
@@ -171,21 +148,37 @@ __device__ inline void dLog_dSE3(Quat<double> q, Vec<double> tr, double dlog[42]
     }
 }
 
-// per-warp shared workspace (doubles)
+// ---- team layout --------------------------------------------------------------------------------------------
+// One interval is worked on by a TEAM of 16 lanes (the RK4 Jacobian [dy/dy0 (10) | dy/db (6)] has 16 columns: one
+// per lane); a warp carries two teams.  Every small dense product is spread over the 16 lanes of the team through
+// the team's shared-memory workspace; nothing runs on a single lane except the scalar formula tables of dLog_dSE3,
+// which lane 0 of the team writes straight into shared memory (no local-memory arrays, no stack frame).
+constexpr int kTeam = 16;
 struct Work {
-  double C[100], A[100], Gm[60], t1[100], t2[100], t3[100];
+  double C[100], A[100], Gm[60], t1[100], t2[100];
   double rot[8];  // (c, s) of the four rotations of a Jacobi round
   int rpq[8];     // their index pairs
 };
 
-// Jacobian pieces of one RK4 stage (types.h:380-425), computed redundantly by every lane
+// out[R x C] = A[R x K] * op(B); transB: B is stored [C x K].  Caller synchronises.
+__device__ __forceinline__ void tmm(double* out, const double* A, const double* B, int R, int K, int C, int tl,
+                                    bool transB = false) {
+  for (int e = tl; e < R * C; e += kTeam) {
+    const int r = e / C, c = e - r * C;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += A[r * K + k] * (transB ? B[c * K + k] : B[k * C + c]);
+    out[e] = s;
+  }
+}
+
+// Jacobian pieces of one RK4 stage (types.h:380-425), computed by every lane (all lanes need all of them)
 struct StageJac {
   double R[9];    // dw/dbg = da/dba = R(q)
   double Dw[12];  // dw/dq = dqx_dq(q, zg) + dqx_dq(q, bg)   (unscaled measurements, as the reference)
   double Da[12];  // da/dq = dqx_dq(q, za) + dqx_dq(q, ba)
 };
-__device__ inline void stage_jac(const Pose<double>& y, const Meas<double>& z0, const Meas<double>& z1, Vec<double> bg,
-                                 Vec<double> ba, double dt, StageJac* J) {
+__device__ __forceinline__ void stage_jac(const Pose<double>& y, const Meas<double>& z0, const Meas<double>& z1, Vec<double> bg,
+                                          Vec<double> ba, double dt, StageJac* J) {
   const double alpha = (z1.time - (z0.time + dt)) / (z1.time - z0.time);
   const Vec<double> zg = imu::scale(z0.w, alpha) + imu::scale(z1.w, 1.0 - alpha);
   const Vec<double> za = imu::scale(z0.a, alpha) + imu::scale(z1.a, 1.0 - alpha);
@@ -202,30 +195,37 @@ __device__ __forceinline__ void stage_T(const double col[10], int j, const Stage
     T[3 + i] = J.Dw[i * 4] * col[3] + J.Dw[i * 4 + 1] * col[4] + J.Dw[i * 4 + 2] * col[5] + J.Dw[i * 4 + 3] * col[6];
     T[6 + i] = J.Da[i * 4] * col[3] + J.Da[i * 4 + 1] * col[4] + J.Da[i * 4 + 2] * col[5] + J.Da[i * 4 + 3] * col[6];
   }
-  if (j >= 10) {
-    const int bcol = j - 10;
+  // bias columns: dk_db = [0; R 0; 0 R]  (types.h:410-411)
+  const double sel_g = (j >= 10 && j < 13) ? 1.0 : 0.0, sel_a = j >= 13 ? 1.0 : 0.0;
+  const int bc = j >= 13 ? j - 13 : (j >= 10 ? j - 10 : 0);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      if (bcol < 3) T[3 + i] += J.R[i * 3 + bcol];
-      else T[6 + i] += J.R[i * 3 + bcol - 3];
-    }
+  for (int i = 0; i < 3; ++i) {
+    const double rv = bc == 0 ? J.R[i * 3] : (bc == 1 ? J.R[i * 3 + 1] : J.R[i * 3 + 2]);
+    T[3 + i] += sel_g * rv;
+    T[6 + i] += sel_a * rv;
   }
 }
 // IntegratePose(y0, k, h) with its Jacobians folded into column j:
 //   col_j <- dy_dy[:, j] (direct dependence on y0; zero for the bias columns) + dy_dk * T_j   (types.h:330-378)
-__device__ inline Pose<double> integrate_push(const Pose<double>& y0, const double k[9], double h, const double T[9], int j,
-                                              double col[10]) {
+__device__ __forceinline__ Pose<double> integrate_push(const Pose<double>& y0, const double k[9], double h, const double T[9], int j,
+                                                       double col[10]) {
   const Vec<double> wdt{k[3] * h, k[4] * h, k[5] * h};
   const Quat<double> r = imu::so3_exp<double>(wdt);
-  double a[16], e[12], Qq[16];
+  double a[16], e[12];
   dq1q2_dq1(y0.q, a, 4);
   dqExp_dw(wdt, e);
-  dq1q2_dq2(r, Qq, 4);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     col[i] = h * T[i] + (j == i ? 1.0 : 0.0);
     col[7 + i] = h * T[6 + i] + (j == 7 + i ? 1.0 : 0.0);
   }
+  // dq1q2_dq2(r)[:, j-3] for the quaternion columns of y0 (vicalibrator-utils.h:214-220)
+  const int jq = j - 3;
+  const double Qc[4] = {jq == 0 ? r.w : jq == 1 ? -r.z : jq == 2 ? r.y : r.x,
+                        jq == 0 ? r.z : jq == 1 ? r.w : jq == 2 ? -r.x : r.y,
+                        jq == 0 ? -r.y : jq == 1 ? r.x : jq == 2 ? r.w : r.z,
+                        jq == 0 ? -r.x : jq == 1 ? -r.y : jq == 2 ? -r.z : r.w};
+  const bool isq = j >= 3 && j < 7;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     double s = 0.0;
@@ -236,68 +236,73 @@ __device__ inline Pose<double> integrate_push(const Pose<double>& y0, const doub
       for (int m = 0; m < 4; ++m) q += a[i * 4 + m] * e[m * 3 + c];
       s += q * h * T[3 + c];
     }
-    if (j >= 3 && j < 7) s += Qq[i * 4 + (j - 3)];
-    col[3 + i] = s;
+    col[3 + i] = s + (isq ? Qc[i] : 0.0);
   }
   return imu::integrate_pose<double>(y0, k, h);
 }
 
 // IntegrateImu, Jacobian + covariance branch (types.h:427-595): C <- A C A^T + G R G^T.
-// Lane j < 16 carries column j of [dy/dy0 (10) | dy/db (6)] in registers through the four RK stages.
-__device__ inline Pose<double> integrate_imu_cov(const Pose<double>& pose, const Meas<double>& z0, const Meas<double>& z1,
-                                                 Vec<double> bg, Vec<double> ba, const double sf[6], Vec<double> g,
-                                                 double sg2, double sa2, Work* W, int lane) {
+// Team lane j carries column j of [dy/dy0 (10) | dy/db (6)] in registers through the four RK stages.  `on` is
+// team-uniform: a team whose interval is finished (or empty) idles through the barriers of its warp mate.
+__device__ __forceinline__ Pose<double> integrate_imu_cov(const Pose<double>& pose, const Meas<double>& z0, const Meas<double>& z1,
+                                                          Vec<double> bg, Vec<double> ba, const double sf[6], Vec<double> g,
+                                                          double sg2, double sa2, Work* W, int j, bool on) {
   const double dt = z1.time - z0.time;
-  if (dt == 0) return pose;  // degenerate step: identity map (the reference leaves its outputs untouched)
-  const int j = lane < 16 ? lane : 15;
-  double col[10], tot[9], T[9], k1[9], k2[9], k3[9], k4[9], k[9];
+  on = on && dt != 0;  // degenerate step: identity map (the reference leaves its outputs untouched)
+  Pose<double> res = pose;
+  if (on) {
+    double col[10], tot[9], T[9], k1[9], k2[9], k3[9], k4[9];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) col[i] = (j == i) ? 1.0 : 0.0;  // dy_dy0 = I, dy_db = 0
-  StageJac J;
-  imu::pose_derivative<double>(pose, g, z0, z1, bg, ba, sf, 0.0, k1);
-  stage_jac(pose, z0, z1, bg, ba, 0.0, &J);
-  stage_T(col, j, J, T);
+    for (int i = 0; i < 10; ++i) col[i] = (j == i) ? 1.0 : 0.0;  // dy_dy0 = I, dy_db = 0
+    StageJac J;
+    imu::pose_derivative<double>(pose, g, z0, z1, bg, ba, sf, 0.0, k1);
+    stage_jac(pose, z0, z1, bg, ba, 0.0, &J);
+    stage_T(col, j, J, T);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) tot[i] = T[i];
-  const Pose<double> y1 = integrate_push(pose, k1, dt * 0.5, T, j, col);
-  imu::pose_derivative<double>(y1, g, z0, z1, bg, ba, sf, dt / 2, k2);
-  stage_jac(y1, z0, z1, bg, ba, dt / 2, &J);
-  stage_T(col, j, J, T);
+    for (int i = 0; i < 9; ++i) tot[i] = T[i];
+    const Pose<double> y1 = integrate_push(pose, k1, dt * 0.5, T, j, col);
+    imu::pose_derivative<double>(y1, g, z0, z1, bg, ba, sf, dt / 2, k2);
+    stage_jac(y1, z0, z1, bg, ba, dt / 2, &J);
+    stage_T(col, j, J, T);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) tot[i] += 2.0 * T[i];
-  const Pose<double> y2 = integrate_push(pose, k2, dt * 0.5, T, j, col);
-  imu::pose_derivative<double>(y2, g, z0, z1, bg, ba, sf, dt / 2, k3);
-  stage_jac(y2, z0, z1, bg, ba, dt / 2, &J);
-  stage_T(col, j, J, T);
+    for (int i = 0; i < 9; ++i) tot[i] += 2.0 * T[i];
+    const Pose<double> y2 = integrate_push(pose, k2, dt * 0.5, T, j, col);
+    imu::pose_derivative<double>(y2, g, z0, z1, bg, ba, sf, dt / 2, k3);
+    stage_jac(y2, z0, z1, bg, ba, dt / 2, &J);
+    stage_T(col, j, J, T);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) tot[i] += 2.0 * T[i];
-  const Pose<double> y3 = integrate_push(pose, k3, dt, T, j, col);
-  imu::pose_derivative<double>(y3, g, z0, z1, bg, ba, sf, dt, k4);
-  stage_jac(y3, z0, z1, bg, ba, dt, &J);
-  stage_T(col, j, J, T);
+    for (int i = 0; i < 9; ++i) tot[i] += 2.0 * T[i];
+    const Pose<double> y3 = integrate_push(pose, k3, dt, T, j, col);
+    imu::pose_derivative<double>(y3, g, z0, z1, bg, ba, sf, dt, k4);
+    stage_jac(y3, z0, z1, bg, ba, dt, &J);
+    stage_T(col, j, J, T);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    tot[i] += T[i];
-    k[i] = k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i];
-  }
-  const Pose<double> res = integrate_push(pose, k, dt / 6.0, tot, j, col);
-  // C = A C A^T + G R G^T
-  if (lane < 10) {
+    for (int i = 0; i < 9; ++i) {
+      tot[i] += T[i];
+      k1[i] = k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i];
+    }
+    res = integrate_push(pose, k1, dt / 6.0, tot, j, col);
+    if (j < 10) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) W->A[i * 10 + lane] = col[i];
-  } else if (lane < 16) {
+      for (int i = 0; i < 10; ++i) W->A[i * 10 + j] = col[i];
+    } else {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) W->Gm[i * 6 + (lane - 10)] = col[i];
+      for (int i = 0; i < 10; ++i) W->Gm[i * 6 + (j - 10)] = col[i];
+    }
   }
   __syncwarp();
-  wmm(W->t1, W->A, W->C, 10, 10, 10, lane);
-  wmm(W->t2, W->t1, W->A, 10, 10, 10, lane, true);
-  for (int e = lane; e < 100; e += 32) {
-    const int r = e / 10, c = e - r * 10;
-    double s = 0.0;
-    for (int q = 0; q < 6; ++q) s += W->Gm[r * 6 + q] * (q < 3 ? sg2 : sa2) * W->Gm[c * 6 + q];
-    W->C[e] = W->t2[e] + s;
-  }
+  if (on) tmm(W->t1, W->A, W->C, 10, 10, 10, j);
+  __syncwarp();
+  if (on) tmm(W->t2, W->t1, W->A, 10, 10, 10, j, true);
+  __syncwarp();
+  if (on)
+    for (int e = j; e < 100; e += kTeam) {
+      const int r = e / 10, c = e - r * 10;
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s += W->Gm[r * 6 + q] * (q < 3 ? sg2 : sa2) * W->Gm[c * 6 + q];
+      W->C[e] = W->t2[e] + s;
+    }
   __syncwarp();
   return res;
 }
@@ -312,40 +317,12 @@ struct WeightArgs {
   int ni;
   double sigma_g, sigma_a;
 };
-constexpr int kWtWarps = 2;
+constexpr int kWtWarps = 4;                              // warps per CTA
+constexpr int kWtTeams = kWtWarps * (32 / kTeam);        // intervals per CTA
 
-__global__ void __launch_bounds__(32 * kWtWarps, 8) imu_weights_kernel(WeightArgs a) {
-  __shared__ Work work[kWtWarps];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int kk = blockIdx.x * kWtWarps + wid;
-  if (kk >= a.ni || a.ctl->done) return;
-  // a rejected step leaves the accepted state — hence the weights — unchanged
-  if (a.ctl->iter > 0 && !a.ctl->last_accepted) return;
-  Work* W = &work[wid];
-  const double* state = a.states[a.ctl->cur];
-  const double* X1 = state + 7 * static_cast<int64_t>(kk);
-  const double* X2 = state + 7 * static_cast<int64_t>(kk + 1);
-  const double* V1 = state + a.dp.off_v + 3 * static_cast<int64_t>(kk);
-  const double* P = state + a.dp.off_imu;
-  const double ts = P[14];
-  const double t_start = a.ftime[kk], t_end = a.ftime[kk + 1];
-  // measurements.size() == 0 -> continue (vicalibrator.h:731-733)
-  if (!(t_start >= a.buf.start_time + ts && t_start <= a.buf.end_time + ts) || a.buf.n == 0) return;
-  const Vec<double> g = imu::gravity_vector<double>(P[0], P[1]);
-  const Vec<double> bg{P[2], P[3], P[4]}, ba{P[5], P[6], P[7]};
-  double sf[6];
-  for (int i = 0; i < 6; ++i) sf[i] = P[8 + i];
-  Pose<double> y{{X1[4], X1[5], X1[6]}, {X1[0], X1[1], X1[2], X1[3]}, {V1[0], V1[1], V1[2]}};
-  wzero(W->C, 100, lane);
-  const double sg2 = a.sigma_g * a.sigma_g, sa2 = a.sigma_a * a.sigma_a;
-  int idx;
-  Meas<double> prev = imu::get_element<double>(a.buf, t_start, ts, &idx), cur;
-  bool more = true;
-  while (more) {
-    more = imu::get_next<double>(a.buf, t_end, ts, &idx, &cur);
-    y = integrate_imu_cov(y, prev, cur, bg, ba, sf, g, sg2, sa2, W, lane);
-    prev = cur;
-  }
+// The weights of one interval: everything after the covariance chain (vicalibrator.h:755-796).  Team-collective;
+// `on` team-uniform.  Writes the 9x9 weight_sqrt_ to `out` (left untouched when the information matrix is singular).
+__device__ __forceinline__ void weight_from_cov(const Pose<double>& y, const double* X2, Work* W, int tl, bool on, double* out) {
   // t12 = T_end * T_2w, T_2w = T_w2^-1
   const Quat<double> q2i = imu::qconj(Quat<double>{X2[0], X2[1], X2[2], X2[3]});
   const Vec<double> t2 = imu::qrot(q2i, Vec<double>{X2[4], X2[5], X2[6]});
@@ -353,83 +330,73 @@ __global__ void __launch_bounds__(32 * kWtWarps, 8) imu_weights_kernel(WeightArg
   const Quat<double> q12 = imu::qmul(y.q, q2i);
   const Vec<double> t12 = y.p + imu::qrot(y.q, t2i);
   // Jt (9x10) = [dLog_dSE3(t12) * dt1t2_dt1(T_end, T_2w), 0; 0, I3]   (vicalibrator.h:763-781)
-  double* Jt = W->t1;   // 90
-  double* tmp = W->t2;  // 100
-  if (lane == 0) {
-    double dlog[42], dmul[49];
-    dLog_dSE3(q12, t12, dlog);
-    for (int i = 0; i < 49; ++i) dmul[i] = 0.0;
-    for (int i = 0; i < 3; ++i) dmul[i * 7 + i] = 1.0;
+  double* dlog = W->t1;        // 42
+  double* dmul = W->t1 + 42;   // 49
+  double* Jt = W->t2;          // 90
+  if (on) {
+    for (int e = tl; e < 49; e += kTeam) dmul[e] = (e % 8 == 0 && e < 3 * 8) ? 1.0 : 0.0;  // identity in the 3x3 corner
+    for (int e = tl; e < 90; e += kTeam) Jt[e] = (e == 67 || e == 78 || e == 89) ? 1.0 : 0.0;  // rows 6-8: [0 | I3]
+  }
+  __syncwarp();
+  if (on && tl == 0) dLog_dSE3(q12, t12, dlog);
+  if (on && tl == 1) {
     dqx_dq(y.q, t2i, dmul + 3, 7);          // block(0,3) = dqx_dq(t1.q, t2.translation)
     dq1q2_dq1(q2i, dmul + 3 * 7 + 3, 7);    // block(3,3) = dq1q2_dq1(t2.q)
-    for (int i = 0; i < 90; ++i) Jt[i] = 0.0;
-    for (int i = 0; i < 6; ++i)
-      for (int j = 0; j < 7; ++j) {
-        double s = 0;
-        for (int q = 0; q < 7; ++q) s += dlog[i * 7 + q] * dmul[q * 7 + j];
-        Jt[i * 10 + j] = s;
-      }
-    for (int i = 0; i < 3; ++i) Jt[(6 + i) * 10 + 7 + i] = 1.0;
   }
   __syncwarp();
-  // P = Jt C Jt^T  (9x9) -> T_dy[0..80]
-  wmm(tmp, Jt, W->C, 9, 10, 10, lane);
-  double* Pm = W->t3;
-  wmm(Pm, tmp, Jt, 9, 10, 9, lane, true);
-  // inverse by Gauss-Jordan with partial pivoting (Eigen .inverse()), lane 0
-  double* inv = W->A;  // 81
-  __shared__ int singular[kWtWarps];
-  if (lane == 0) {
-    double M[9][18];
-    for (int i = 0; i < 9; ++i)
-      for (int j = 0; j < 9; ++j) { M[i][j] = Pm[i * 9 + j]; M[i][9 + j] = i == j ? 1.0 : 0.0; }
-    int bad = 0;
-    for (int c = 0; c < 9 && !bad; ++c) {
-      int p = c;
-      for (int r = c + 1; r < 9; ++r) if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
-      if (M[p][c] == 0.0) { bad = 1; break; }
-      if (p != c) for (int j = 0; j < 18; ++j) { const double t = M[p][j]; M[p][j] = M[c][j]; M[c][j] = t; }
-      const double iv = 1.0 / M[c][c];
-      for (int j = 0; j < 18; ++j) M[c][j] *= iv;
-      for (int r = 0; r < 9; ++r) {
-        if (r == c) continue;
-        const double f = M[r][c];
-        if (f == 0.0) continue;
-        for (int j = 0; j < 18; ++j) M[r][j] -= f * M[c][j];
-      }
+  if (on)
+    for (int e = tl; e < 42; e += kTeam) {
+      const int i = e / 7, jj = e - i * 7;
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) s += dlog[i * 7 + q] * dmul[q * 7 + jj];
+      Jt[i * 10 + jj] = s;
     }
-    for (int i = 0; i < 9; ++i)
-      for (int j = 0; j < 9; ++j) inv[i * 9 + j] = M[i][9 + j];
-    singular[wid] = bad;
-  }
   __syncwarp();
-  if (singular[wid]) return;
-  // principal square root: cyclic Jacobi on the symmetrised matrix; A in t1, V in t2
-  double* A = W->t1;
-  double* V = W->t2;
-  for (int e = lane; e < 81; e += 32) {
-    const int r = e / 9, c = e - r * 9;
-    A[e] = 0.5 * (inv[r * 9 + c] + inv[c * 9 + r]);
-    V[e] = r == c ? 1.0 : 0.0;
-  }
+  // P = Jt C Jt^T (9x9): tmp = Jt C in t1, P in A
+  if (on) tmm(W->t1, Jt, W->C, 9, 10, 10, tl);
   __syncwarp();
-  for (int sweep = 0; sweep < 60; ++sweep) {
+  double* A = W->A;   // 81: P, then its eigenvalues on the diagonal
+  double* V = W->C;   // 81: eigenvectors (the covariance chain is done with C)
+  if (on) tmm(A, W->t1, Jt, 9, 10, 9, tl, true);
+  __syncwarp();
+  // info = P^-1, weight_sqrt = sqrtm(info) (vicalibrator.h:783-796) = V diag(lambda^-1/2) V^T with P = V diag(lambda) V^T:
+  // one cyclic Jacobi eigen-decomposition of the symmetrised P (no explicit inverse).  Round r of a sweep holds the
+  // four disjoint pairs {i, j}, i + j = r (mod 9), i < j; their rotations are computed from the same matrix by four
+  // lanes and applied together (columns of A and V, then rows of A).
+  if (on)
+    for (int e = tl; e < 81; e += kTeam) {
+      const int r = e / 9, c = e - r * 9;
+      if (c >= r) {
+        const double v = 0.5 * (A[r * 9 + c] + A[c * 9 + r]);
+        W->t2[r * 9 + c] = v;
+        W->t2[c * 9 + r] = v;
+      }
+      V[e] = r == c ? 1.0 : 0.0;
+    }
+  __syncwarp();
+  A = W->t2;
+  for (int sweep = 0; sweep < 40; ++sweep) {
     double off = 0.0, dg = 0.0;
-    for (int i = 0; i < 9; ++i) {
-      dg += A[i * 9 + i] * A[i * 9 + i];
-      for (int j = i + 1; j < 9; ++j) off += A[i * 9 + j] * A[i * 9 + j];
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        dg += A[i * 9 + i] * A[i * 9 + i];
+#pragma unroll
+        for (int jj = i + 1; jj < 9; ++jj) off += A[i * 9 + jj] * A[i * 9 + jj];
+      }
     }
-    if (off <= 1e-30 * dg) break;
-    // round-robin order: round r holds the four disjoint pairs {i, j}, i + j = r (mod 9), i < j; their rotations
-    // are computed from the same matrix by four lanes and applied together (columns of A and V, then rows of A) —
-    // the order of oracle/imu_weights.h:SqrtSym, nine serial steps per sweep instead of thirty-six
+    const bool conv = !on || off <= 1e-30 * dg;
+    if (__all_sync(0xffffffffu, conv)) break;
     for (int r = 0; r < 9; ++r) {
-      if (lane < 4) {
+      if (on && !conv && tl < 4) {
+        // pair number tl of round r: i runs over the residues with i < (r - i) mod 9
         int cnt = 0, pi = 0, qi = 0;
+#pragma unroll
         for (int i = 0; i < 9; ++i) {
-          const int j = (r - i + 9) % 9;
-          if (i < j) {
-            if (cnt == lane) { pi = i; qi = j; }
+          const int jj = (r - i + 9) % 9;
+          if (i < jj) {
+            if (cnt == tl) { pi = i; qi = jj; }
             ++cnt;
           }
         }
@@ -438,44 +405,95 @@ __global__ void __launch_bounds__(32 * kWtWarps, 8) imu_weights_kernel(WeightArg
         if (apq != 0.0) {
           const double tau = (A[qi * 9 + qi] - A[pi * 9 + pi]) / (2.0 * apq);
           const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + t * t);
+          c = rsqrt(1.0 + t * t);
           sn = t * c;
         }
-        W->rot[2 * lane] = c; W->rot[2 * lane + 1] = sn;
-        W->rpq[2 * lane] = pi; W->rpq[2 * lane + 1] = qi;
+        W->rot[2 * tl] = c; W->rot[2 * tl + 1] = sn;
+        W->rpq[2 * tl] = pi; W->rpq[2 * tl + 1] = qi;
       }
       __syncwarp();
-      for (int e = lane; e < 36; e += 32) {  // columns p, q of A and V: row k, rotation t
-        const int k = e >> 2, t = e & 3, p = W->rpq[2 * t], q = W->rpq[2 * t + 1];
-        const double c = W->rot[2 * t], sn = W->rot[2 * t + 1];
-        const double akp = A[k * 9 + p], akq = A[k * 9 + q];
-        A[k * 9 + p] = c * akp - sn * akq;
-        A[k * 9 + q] = sn * akp + c * akq;
-        const double vkp = V[k * 9 + p], vkq = V[k * 9 + q];
-        V[k * 9 + p] = c * vkp - sn * vkq;
-        V[k * 9 + q] = sn * vkp + c * vkq;
-      }
+      if (on && !conv)
+        for (int e = tl; e < 36; e += kTeam) {  // columns p, q of A and V: row k, rotation t
+          const int k = e >> 2, t = e & 3, p = W->rpq[2 * t], q = W->rpq[2 * t + 1];
+          const double c = W->rot[2 * t], sn = W->rot[2 * t + 1];
+          const double akp = A[k * 9 + p], akq = A[k * 9 + q];
+          A[k * 9 + p] = c * akp - sn * akq;
+          A[k * 9 + q] = sn * akp + c * akq;
+          const double vkp = V[k * 9 + p], vkq = V[k * 9 + q];
+          V[k * 9 + p] = c * vkp - sn * vkq;
+          V[k * 9 + q] = sn * vkp + c * vkq;
+        }
       __syncwarp();
-      for (int e = lane; e < 36; e += 32) {  // rows p, q of A: column k, rotation t
-        const int k = e >> 2, t = e & 3, p = W->rpq[2 * t], q = W->rpq[2 * t + 1];
-        const double c = W->rot[2 * t], sn = W->rot[2 * t + 1];
-        const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
-        A[p * 9 + k] = c * apk - sn * aqk;
-        A[q * 9 + k] = sn * apk + c * aqk;
-      }
+      if (on && !conv)
+        for (int e = tl; e < 36; e += kTeam) {  // rows p, q of A: column k, rotation t
+          const int k = e >> 2, t = e & 3, p = W->rpq[2 * t], q = W->rpq[2 * t + 1];
+          const double c = W->rot[2 * t], sn = W->rot[2 * t + 1];
+          const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
+          A[p * 9 + k] = c * apk - sn * aqk;
+          A[q * 9 + k] = sn * apk + c * aqk;
+        }
       __syncwarp();
     }
   }
-  double* out = a.wsqrt + static_cast<int64_t>(kk) * 81;
-  for (int e = lane; e < 81; e += 32) {
+  if (!on) return;
+  bool singular = false;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) singular = singular || !(A[k * 9 + k] > 0.0);
+  if (singular) return;
+  if (tl < 9) W->t1[tl] = 1.0 / sqrt(A[tl * 9 + tl]);  // lambda^-1/2
+  __syncwarp(0xffffu << (threadIdx.x & 16));  // this team only: the other one may have left
+  for (int e = tl; e < 81; e += kTeam) {
     const int r = e / 9, c = e - r * 9;
     double s = 0.0;
-    for (int k = 0; k < 9; ++k) {
-      const double l = A[k * 9 + k] > 0 ? sqrt(A[k * 9 + k]) : 0.0;
-      s += V[r * 9 + k] * l * V[c * 9 + k];
-    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s += V[r * 9 + k] * W->t1[k] * V[c * 9 + k];
     out[e] = s;
   }
+}
+
+// UpdateImuWeights for interval kk by the team of 16 lanes `tl` belongs to (kk >= ni: the team idles along)
+__device__ __forceinline__ void imu_weights_team(const WeightArgs& a, const double* state, int kk, Work* W, int tl) {
+  const int ki = min(kk, a.ni - 1);  // an odd tail team shadows the last interval (never written)
+  const double* X1 = state + 7 * static_cast<int64_t>(ki);
+  const double* X2 = state + 7 * static_cast<int64_t>(ki + 1);
+  const double* V1 = state + a.dp.off_v + 3 * static_cast<int64_t>(ki);
+  const double* P = state + a.dp.off_imu;
+  const double ts = P[14];
+  const double t_start = a.ftime[ki], t_end = a.ftime[ki + 1];
+  // measurements.size() == 0 -> continue (vicalibrator.h:731-733)
+  bool on = kk < a.ni && (t_start >= a.buf.start_time + ts && t_start <= a.buf.end_time + ts) && a.buf.n > 0;
+  const Vec<double> g = imu::gravity_vector<double>(P[0], P[1]);
+  const Vec<double> bg{P[2], P[3], P[4]}, ba{P[5], P[6], P[7]};
+  double sf[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) sf[i] = P[8 + i];
+  Pose<double> y{{X1[4], X1[5], X1[6]}, {X1[0], X1[1], X1[2], X1[3]}, {V1[0], V1[1], V1[2]}};
+  __syncwarp();  // the team's previous interval is done with the workspace
+  for (int e = tl; e < 100; e += kTeam) W->C[e] = 0.0;
+  __syncwarp();
+  const double sg2 = a.sigma_g * a.sigma_g, sa2 = a.sigma_a * a.sigma_a;
+  int idx = 0;
+  Meas<double> prev{}, cur{};
+  if (on) prev = imu::get_element<double>(a.buf, t_start, ts, &idx);
+  bool more = on;
+  while (__any_sync(0xffffffffu, more)) {
+    const bool step = more;
+    if (step) more = imu::get_next<double>(a.buf, t_end, ts, &idx, &cur);
+    y = integrate_imu_cov(y, prev, cur, bg, ba, sf, g, sg2, sa2, W, tl, step);
+    if (step) prev = cur;
+  }
+  weight_from_cov(y, X2, W, tl, on, a.wsqrt + static_cast<int64_t>(ki) * 81);
+}
+
+__global__ void __launch_bounds__(32 * kWtWarps, 2) imu_weights_kernel(WeightArgs a) {
+  __shared__ Work work[kWtTeams];
+  const int tl = threadIdx.x & (kTeam - 1);
+  const int team = threadIdx.x / kTeam;
+  if (a.ctl->done) return;
+  // a rejected step leaves the accepted state — hence the weights — unchanged
+  if (a.ctl->iter > 0 && !a.ctl->last_accepted) return;
+  if (blockIdx.x * kWtTeams + (threadIdx.x >> 5) * (32 / kTeam) >= a.ni) return;  // whole warp past the end
+  imu_weights_team(a, a.states[a.ctl->cur], blockIdx.x * kWtTeams + team, &work[team], tl);
 }
 
 }  // namespace wts

@@ -176,6 +176,11 @@ struct vcgpu_handle {
   int dev_sms = 0, dev_smem_optin = 0;
   size_t mega_smem_set = 0;
   int mega_grid = 0, mega_warps = 0;  // 0 warps: does not fit / not supported, use the multi-launch engine
+  // persistent inertial kernels (vc_imu_mega.cuh, vc_imu_eval_mega.cuh)
+  bool imu_mega_ok = false;
+  int imu_mega_grid = 0;
+  unsigned long long* d_prof2 = nullptr;  // [16] phase clocks: chain_solve [0,8), eval [8,16)
+  int n_step_part = 0;            // entries of d_red written by the last state update
   double* d_dl = nullptr;         // dogleg work vectors [6][nf*fd+G] + matvec partials
   double* d_dl_part = nullptr;    // [kDlBlocks][4]
   double* d_scalars = nullptr;    // device scalars (see vcgpu.cu)

@@ -318,15 +318,10 @@ struct RedFinArgs {
   double* scalars;
   unsigned* counter;
 };
-__global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
-  extern __shared__ double acc[];
-  __shared__ double shr[8][8];
-  __shared__ double sh4[4][64];
-  __shared__ int is_last;
-  if (a.ctl->done) return;
-  const Blocks& out = a.out[pick(a.ctl, a.which)];
+// Level 1 of the reduction for slice `bid` of `nb` (256 threads): the slice's share of the per-group global blocks
+// -> Cpart[bid], of the cost / gradient-norm / step partials -> red_part[bid].  acc: NS doubles of shared memory.
+__device__ __forceinline__ void reduce_level1(const RedFinArgs& a, const Blocks& out, double* acc, double (*shr)[8], int bid, int nb) {
   const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G, lane = tid & 31, warp = tid >> 5;
-  const int nb = gridDim.x, bid = blockIdx.x;
   for (int k = tid; k < NS; k += 256) acc[k] = 0.0;
   __syncthreads();
   for (int c = 0; c < a.dp.n_cams; ++c) {
@@ -423,6 +418,20 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
       t[6] = fmax(t[6], shr[w][6]);
     }
     for (int q = 0; q < 7; ++q) a.red_part[8 * bid + q] = t[q];
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
+  extern __shared__ double acc[];
+  __shared__ double shr[8][8];
+  __shared__ double sh4[4][64];
+  __shared__ int is_last;
+  if (a.ctl->done) return;
+  const Blocks& out = a.out[pick(a.ctl, a.which)];
+  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G, lane = tid & 31, warp = tid >> 5;
+  const int nb = gridDim.x, bid = blockIdx.x;
+  reduce_level1(a, out, acc, shr, bid, nb);
+  if (tid == 0) {
     if (a.level1_only) { is_last = 0; }
     __threadfence();
     if (!a.level1_only) {

@@ -23,6 +23,8 @@
 #include "vc_mega.cuh"
 #include "vc_dogleg.cuh"
 #include "vc_imu_weights.cuh"
+#include "vc_imu_mega.cuh"
+#include "vc_imu_eval_mega.cuh"
 
 using namespace vc;
 
@@ -91,6 +93,7 @@ static void stage_collect(vcgpu_handle* h) {  // call after a stream synchronise
     }
 }
 static void xchg_release(vcgpu_handle* h);
+static int imu_mega_prepare(vcgpu_handle* h);
 #include "vc_imu_host.inl"
 
 extern "C" int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2) {
@@ -205,7 +208,7 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_blk_mem[0]); dev_free(&h->d_blk_mem[1]);
   dev_free(&h->d_scale); dev_free(&h->d_X); dev_free(&h->d_Spart); dev_free(&h->d_delta);
   dev_free(&h->d_red); dev_free(&h->d_scalars); dev_free(&h->d_Ssum); dev_free(&h->d_red_part); dev_free(&h->d_counter);
-  dev_free(&h->d_dl); dev_free(&h->d_dl_part); dev_free(&h->d_partS); dev_free(&h->d_partC); dev_free(&h->d_prof);
+  dev_free(&h->d_dl); dev_free(&h->d_dl_part); dev_free(&h->d_partS); dev_free(&h->d_partC); dev_free(&h->d_prof); dev_free(&h->d_prof2);
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
   dev_free(&h->d_mg); dev_free(&h->d_sep); dev_free(&h->d_dense);
@@ -655,12 +658,13 @@ static int prepare(vcgpu_handle* h) {
       const size_t N = static_cast<size_t>(G) + 9 * h->nranks;
       VC_TRY(dev_alloc(h, &h->d_dense, N * N + N));
     }
-    VC_TRY(dev_alloc(h, &h->d_counter, 4));
-    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned), h->stream));
+    VC_TRY(dev_alloc(h, &h->d_counter, 8));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, 8 * sizeof(unsigned), h->stream));
     VC_TRY(dev_alloc(h, &h->d_scalars, kScCount));
     CUDA_TRY(h, cudaMemsetAsync(h->d_scalars, 0, kScCount * sizeof(double), h->stream));
     VC_TRY(mega_prepare(h));
     VC_TRY(imu_prepare(h));
+    VC_TRY(imu_mega_prepare(h));
     h->cur = 0;
     h->dirty = false;
     h->state_dirty = true;
