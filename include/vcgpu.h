@@ -202,6 +202,10 @@ enum {
 int vcgpu_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
 int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2);
 int vcgpu_get_stage_times(vcgpu_handle* h, double ms_total[VCGPU_STAGE_COUNT], int64_t launches[VCGPU_STAGE_COUNT]);
+/* raw device phase clocks (ns, summed over the iterations since vcgpu_set_profiling) of the persistent inertial kernels:
+ * chain_solve_kernel: elimination level l at [l], Schur reduce [10], dense solve [11], back-substitution level at [12 + k],
+ * step statistics [22]; eval_mega_kernel: tasks [32], IMU accumulate [33], reduce [34], decide [35], weights [36] */
+int vcgpu_get_phase_clocks(vcgpu_handle* h, uint64_t ns[64]);
 
 /* ---- multi-GPU: one process per GPU, frames sharded contiguously, one NCCL all-reduce of the
  * reduced normal equations per iteration ---------------------------------------------------- */

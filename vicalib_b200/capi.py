@@ -24,7 +24,7 @@ EXPORTS = [
     "vcgpu_get_obs_active", "vcgpu_update_imu_weights", "vcgpu_get_imu_weights", "vcgpu_set_imu_weights",
     "vcgpu_get_state", "vcgpu_num_residuals", "vcgpu_frame_dim", "vcgpu_num_globals", "vcgpu_eval_reproj",
     "vcgpu_eval_imu", "vcgpu_normal_equations", "vcgpu_solve_arrow", "vcgpu_comm_unique_id", "vcgpu_comm_init",
-    "vcgpu_set_profiling", "vcgpu_get_stage_times", "vcgpu_fp64_peak",
+    "vcgpu_set_profiling", "vcgpu_get_stage_times", "vcgpu_fp64_peak", "vcgpu_get_phase_clocks",
 ]
 
 
@@ -288,6 +288,12 @@ class Calibrator:
         n = np.zeros(16, dtype=np.int64)
         self._chk(self.L.vcgpu_get_stage_times(self.h, _p(ms), _p(n)))
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.STAGES)}
+
+    def phase_clocks(self):
+        """raw phase clocks (ns) of the persistent inertial kernels, see vcgpu_get_phase_clocks"""
+        ns = np.zeros(64, dtype=np.uint64)
+        self._chk(self.L.vcgpu_get_phase_clocks(self.h, _p(ns)))
+        return ns
 
     def update_imu_weights(self):
         self._chk(self.L.vcgpu_update_imu_weights(self.h))

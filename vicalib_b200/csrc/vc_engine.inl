@@ -120,7 +120,7 @@ static int imu_mega_prepare(vcgpu_handle* h) {
   const size_t sm_eval = eval_mega_smem_doubles(dp.G) * sizeof(double);
   vc::ImuDev* d = imu_dev(h);
   if (h->dev_smem_optin == 0 || sm_solve > static_cast<size_t>(h->dev_smem_optin) || sm_eval > static_cast<size_t>(h->dev_smem_optin) ||
-      d->levels.size() > static_cast<size_t>(kMaxChainLevels))
+      d->levels.size() > static_cast<size_t>(kMaxChainLevels) || 3 * 9 + dp.G + 1 > kCsGroup)
     return VCGPU_OK;  // does not fit: the multi-launch engine runs the solve
   CUDA_TRY(h, cudaFuncSetAttribute(chain_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_solve)));
   CUDA_TRY(h, cudaFuncSetAttribute(eval_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_eval)));
@@ -135,8 +135,11 @@ static int imu_mega_prepare(vcgpu_handle* h) {
   VC_TRY(dev_alloc(h, &h->d_Cpart, std::max<size_t>(grid, kReduceBlocks) * NS));
   VC_TRY(dev_alloc(h, &h->d_red_part, 8 * std::max<size_t>(grid, kReduceBlocks)));
   VC_TRY(dev_alloc(h, &h->d_red, 4 * (std::max<size_t>(dp.n_frames, grid) + 2)));
-  VC_TRY(dev_alloc(h, &h->d_prof2, 16));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_prof2, 0, 16 * sizeof(unsigned long long), h->stream));
+  VC_TRY(dev_alloc(h, &h->d_prof2, kImuProfSlots));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_prof2, 0, kImuProfSlots * sizeof(unsigned long long), h->stream));
+  VC_TRY(dev_alloc(h, &d->d_levels, d->levels.size()));
+  CUDA_TRY(h, cudaMemcpyAsync(d->d_levels, d->levels.data(), d->levels.size() * sizeof(vc::ChainLevel), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->imu_mega_grid = grid;
   h->imu_mega_ok = true;
   return VCGPU_OK;
@@ -147,7 +150,7 @@ static int imu_mega_solve(vcgpu_handle* h, const double* D2x, bool do_update) {
   ChainSolveArgs ca;
   ca.dp = dp; ca.b[0] = h->blk[0]; ca.b[1] = h->blk[1]; ca.ctl = h->d_ctl; ca.scale = h->d_scale; ca.D2x = D2x;
   ca.n_levels = static_cast<int>(d->levels.size());
-  for (int l = 0; l < ca.n_levels; ++l) ca.lev[l] = d->levels[l];
+  ca.lev = d->d_levels;
   ca.Spart = h->d_Spart; ca.Ssum = d->Ssum; ca.delta = h->d_delta; ca.scalars = h->d_scalars;
   ca.state[0] = h->d_state[0]; ca.state[1] = h->d_state[1]; ca.step_part = h->d_red; ca.do_update = do_update ? 1 : 0;
   ca.prof = (h->phase_clocks || h->profiling) ? h->d_prof2 : nullptr;
@@ -176,7 +179,7 @@ static int imu_mega_eval(vcgpu_handle* h, int which, bool with_step, int decide_
   ea.Cpart = h->d_Cpart; ea.red_part = h->d_red_part;
   ea.step_part = with_step ? h->d_red : nullptr; ea.n_step_part = h->n_step_part;
   ea.scalars = h->d_scalars; ea.counter = h->d_counter + 2;
-  ea.prof = (h->phase_clocks || h->profiling) ? h->d_prof2 + 8 : nullptr;
+  ea.prof = (h->phase_clocks || h->profiling) ? h->d_prof2 + 32 : nullptr;
   void* args[] = {&ea};
   CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(eval_mega_kernel), dim3(h->imu_mega_grid), dim3(kEvThreads), args,
                                           eval_mega_smem_doubles(dp.G) * sizeof(double), h->stream));
@@ -186,16 +189,17 @@ static int imu_mega_eval(vcgpu_handle* h, int which, bool with_step, int decide_
 // fold the persistent inertial kernels' phase clocks into the stage times (call after a stream synchronise)
 static int imu_mega_collect_clocks(vcgpu_handle* h, int iters) {
   if (!(h->phase_clocks || h->profiling) || !h->d_prof2 || !h->imu_mega_ok) return VCGPU_OK;
-  unsigned long long ns[16];
+  unsigned long long ns[kImuProfSlots];
   CUDA_TRY(h, cudaMemcpy(ns, h->d_prof2, sizeof ns, cudaMemcpyDeviceToHost));
   CUDA_TRY(h, cudaMemset(h->d_prof2, 0, sizeof ns));
-  const int map_s[kCsProfCount] = {VCGPU_STAGE_FRAME_SOLVE, VCGPU_STAGE_FRAME_SOLVE, VCGPU_STAGE_GLOBAL_SOLVE, VCGPU_STAGE_GLOBAL_SOLVE,
-                                   VCGPU_STAGE_BACKSUB, VCGPU_STAGE_BACKSUB};
+  for (int k = 0; k < kImuProfSlots; ++k) h->phase_ns[k] += ns[k];
+  bool seen[VCGPU_STAGE_COUNT] = {};
+  auto add = [&](int stage, unsigned long long v) { h->st_ms[stage] += v * 1e-6; seen[stage] = true; };
+  for (int k = 0; k < kCsProfCount; ++k)
+    add(k < kCsProfReduce ? VCGPU_STAGE_FRAME_SOLVE : k <= kCsProfDense ? VCGPU_STAGE_GLOBAL_SOLVE : VCGPU_STAGE_BACKSUB, ns[k]);
   const int map_e[kEvProfCount] = {VCGPU_STAGE_EVAL_TASKS, VCGPU_STAGE_IMU_ACCUM, VCGPU_STAGE_REDUCE, VCGPU_STAGE_FINALIZE,
                                    VCGPU_STAGE_IMU_WEIGHTS};
-  bool seen[VCGPU_STAGE_COUNT] = {};
-  for (int k = 0; k < kCsProfCount; ++k) { h->st_ms[map_s[k]] += ns[k] * 1e-6; seen[map_s[k]] = true; }
-  for (int k = 0; k < kEvProfCount; ++k) { h->st_ms[map_e[k]] += ns[8 + k] * 1e-6; seen[map_e[k]] = true; }
+  for (int k = 0; k < kEvProfCount; ++k) add(map_e[k], ns[32 + k]);
   for (int s = 0; s < VCGPU_STAGE_COUNT; ++s) if (seen[s]) h->st_n[s] += iters;
   return VCGPU_OK;
 }

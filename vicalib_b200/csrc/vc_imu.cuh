@@ -161,14 +161,14 @@ struct ImuAccArgs {
 __device__ __forceinline__ int imu_local_col(int c) {
   return c < 6 ? 6 + c : c < 9 ? 15 + (c - 6) : c < 15 ? (c - 9) : c < 18 ? 12 + (c - 15) : c;
 }
-// frame f by a group of 128 threads: interval f-1 (f is its second frame) and interval f (f is its first frame).
+// frame f by a group of NT threads: interval f-1 (f is its second frame) and interval f (f is its first frame).
 // Jl: the group's [2][9][34] staging area ([which][row][local col 0..32, 33 = residual]); SYNC: the group's barrier
-template <class SYNC>
+template <int NT, class SYNC>
 __device__ __forceinline__ void imu_accumulate_frame(const ImuAccArgs& a, const Blocks& out, int f, int tid, double (*Jl)[9][34],
                                                      SYNC sync) {
   const int G = a.dp.G, nf = a.dp.n_frames, io = a.dp.imu_goff;
   const bool hasP = f > 0, hasN = f < nf - 1;
-  for (int e = tid; e < 2 * 9 * 34; e += 128) {
+  for (int e = tid; e < 2 * 9 * 34; e += NT) {
     const int which = e / (9 * 34), row = (e / 34) % 9, c = e % 34;
     const int k = which == 0 ? f - 1 : f;
     double v = 0.0;
@@ -182,7 +182,7 @@ __device__ __forceinline__ void imu_accumulate_frame(const ImuAccArgs& a, const 
   double* Ef = out.E + static_cast<int64_t>(f) * 9 * G;
   double* gf = out.gf + static_cast<int64_t>(f) * 9;
   // B (81) | U (81) | E imu columns (9*15) | g (9) | Cg of interval f (120 + 15)
-  for (int e = tid; e < 81 + 81 + 135 + 9 + 135; e += 128) {
+  for (int e = tid; e < 81 + 81 + 135 + 9 + 135; e += NT) {
     if (e < 81) {
       const int i = e / 9, j = e % 9;
       double s = 0.0;
@@ -231,7 +231,7 @@ __device__ __forceinline__ void imu_accumulate_frame(const ImuAccArgs& a, const 
 __global__ void __launch_bounds__(128) imu_accumulate_kernel(ImuAccArgs a) {
   __shared__ double Jl[2][9][34];
   if (a.ctl->done) return;
-  imu_accumulate_frame(a, a.outs[a.which ? 1 - a.ctl->cur : a.ctl->cur], blockIdx.x, threadIdx.x, Jl, [] { __syncthreads(); });
+  imu_accumulate_frame<128>(a, a.outs[a.which ? 1 - a.ctl->cur : a.ctl->cur], blockIdx.x, threadIdx.x, Jl, [] { __syncthreads(); });
 }
 
 }  // namespace vc

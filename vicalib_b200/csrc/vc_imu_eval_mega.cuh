@@ -6,7 +6,7 @@
 //      warp's shared-memory slab and FP64 DMMA, vc_mega.cuh's phase B): frame block, E, gradient, per-(frame,
 //      camera) packed global block
 //   -- grid barrier
-//   A  per frame (group of 128 threads): J^T J of the two intervals touching the frame into B, U, E, gradient, and
+//   A  per frame (one warp): J^T J of the two intervals touching the frame into B, U, E, gradient, and
 //      the interval's packed 15x15 IMU global block
 //   -- grid barrier
 //   R1 slice b of the per-group global blocks / cost / gradient-norm / step partials by CTA b (fixed order)
@@ -280,11 +280,10 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
     ImuAccArgs aa;
     aa.dp = a.dp; aa.ctl = a.ctl; aa.which = a.which; aa.r = a.imu_r; aa.J = a.imu_J;
     aa.outs[0] = a.blk[0]; aa.outs[1] = a.blk[1]; aa.Cg = a.imuCg; aa.ni = ni;
-    const int grp = tid / kCsGroup, gtid = tid - grp * kCsGroup;
-    double (*Jl)[9][34] = reinterpret_cast<double (*)[9][34]>(smem + static_cast<size_t>(grp) * 2 * 9 * 34);
-    for (int f = bid * kCsGroups + grp; f < nf; f += nb * kCsGroups) {
-      group_sync(grp);  // the group's previous frame is done with the staging area
-      imu_accumulate_frame(aa, bt, f, gtid, Jl, [grp] { group_sync(grp); });
+    double (*Jl)[9][34] = reinterpret_cast<double (*)[9][34]>(smem + static_cast<size_t>(warp) * 2 * 9 * 34);
+    for (int f = bid * kEvWarps + warp; f < nf; f += nb * kEvWarps) {
+      __syncwarp();  // the warp's previous frame is done with the staging area
+      imu_accumulate_frame<32>(aa, bt, f, lane, Jl, [] { __syncwarp(); });
     }
   }
   mark(kEvProfAccum);

@@ -6,6 +6,7 @@ struct ImuDevHost {
   double* ftime = nullptr;  // [nf]
   vc::imu::ImuBuf buf{};
   std::vector<vc::ChainLevel> levels;
+  vc::ChainLevel* d_levels = nullptr;  // device copy for the persistent kernel
   double* pool = nullptr;
   int32_t* ipool = nullptr;
   double* Ssum = nullptr;
@@ -22,7 +23,7 @@ static void imu_free(vcgpu_handle* h) {
   vc::ImuDev* d = imu_dev(h);
   if (!d) return;
   dev_free(&d->cost); dev_free(&d->Cg); dev_free(&d->ftime); dev_free(&d->pool); dev_free(&d->ipool);
-  dev_free(&d->Ssum);
+  dev_free(&d->Ssum); dev_free(&d->d_levels);
   delete d;
   h->imu = nullptr;
 }

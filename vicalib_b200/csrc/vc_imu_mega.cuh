@@ -32,7 +32,8 @@ constexpr int kCsThreads = 256;              // threads per CTA
 constexpr int kCsGroup = 128;                // threads per elimination group
 constexpr int kCsGroups = kCsThreads / kCsGroup;
 constexpr int kCsChunk = 4;                  // every 4th node of a level is a separator
-enum { kCsProfInit = 0, kCsProfElim, kCsProfReduce, kCsProfDense, kCsProfBacksub, kCsProfUpdate, kCsProfCount };
+// phase clock slots: elimination levels [0, 10), reduce 10, dense 11, back-substitution levels [12, 22), update 22
+enum { kCsProfElim = 0, kCsProfReduce = kMaxChainLevels, kCsProfDense, kCsProfBacksub, kCsProfUpdate = kCsProfBacksub + kMaxChainLevels, kCsProfCount };
 
 struct ChainSolveArgs {
   DevProblem dp;
@@ -40,7 +41,7 @@ struct ChainSolveArgs {
   Ctl* ctl;
   const double* scale;
   const double* D2x;            // explicit damping (inspection hook / dogleg) or null: LM rule
-  ChainLevel lev[kMaxChainLevels];
+  const ChainLevel* lev;        // [n_levels] level descriptors (device memory)
   int n_levels;
   double* Spart;                // [grid * kCsGroups][G*G+G]
   double* Ssum;                 // [G*G+G]
@@ -55,12 +56,12 @@ struct ChainSolveArgs {
 __host__ __device__ inline size_t chain_group_doubles(int G) {
   constexpr int FD = 9;
   const size_t NS = static_cast<size_t>(G) * G + G, VW = FD + 2 * FD + G + 1;
-  return NS + 3 * FD * FD + FD * G + FD + (kCsChunk - 1) * FD * VW + (kCsChunk - 1) * FD * G;
+  return NS + FD * FD + FD * G + FD + (2 * (kCsChunk - 1) + 1) * FD * FD + (kCsChunk - 1) * FD * VW + (kCsChunk - 1) * FD * G;
 }
 __host__ __device__ inline size_t chain_solve_smem_doubles(int G) {
   const size_t grp = kCsGroups * chain_group_doubles(G);
   const size_t N = static_cast<size_t>(G) + kCsChunk * 9;
-  const size_t dense = N * N + N;
+  const size_t dense = N * N + 2 * N;
   return (grp > dense ? grp : dense) + 16;
 }
 
@@ -68,11 +69,52 @@ __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(kCsGroup) : "memory");
 }
 
-// Forward + backward sweep of one chunk (separator s = j*c, interior nodes s+1..s+m) by one group of 128 threads.
-// Same algorithm as chain_eliminate_kernel (vc_chain.cuh); the group's Schur accumulator Sacc lives on across calls.
+// where a level's node blocks come from: level 0 reads the block normal equations and applies the Jacobi scaling and
+// the LM damping on the fly (no separate pass, no copy); deeper levels read what the level above left
+struct NodeSrc {
+  const ChainLevel* L;   // level >= 1 (null at level 0)
+  Blocks b;              // level 0
+  const double* scale;
+  const double* D2x;
+  double rinv;
+  int G, nf;
+};
 template <int FD>
-__device__ inline void chain_eliminate_chunk(const ChainLevel& L, const ChainLevel& nxt, int G, int j, double* sm, int tid,
-                                             int grp, int* bad) {
+__device__ __forceinline__ double src_A(const NodeSrc& s, int64_t p, int e) {
+  if (s.L) return s.L->A[p * FD * FD + e] + (s.L->addA ? s.L->addA[p * FD * FD + e] : 0.0);
+  const int r = e / FD, c = e - r * FD;
+  const double* sf = s.scale + p * FD;
+  const double bij = s.b.B[p * FD * FD + e];
+  double v = bij * sf[r] * sf[c];
+  if (r == c) v += s.D2x ? s.D2x[p * FD + r] : lm_damp(bij, sf[r], s.rinv);
+  return v;
+}
+template <int FD>
+__device__ __forceinline__ double src_U(const NodeSrc& s, int64_t p, int e) {  // H[p-1, p]
+  if (s.L) return s.L->U[p * FD * FD + e];
+  if (p == 0) return 0.0;
+  const int r = e / FD, c = e - r * FD;
+  return s.b.U[p * FD * FD + e] * s.scale[(p - 1) * FD + r] * s.scale[p * FD + c];
+}
+template <int FD>
+__device__ __forceinline__ double src_E(const NodeSrc& s, int64_t p, int e) {
+  if (s.L) return s.L->E[p * FD * s.G + e] + (s.L->addE ? s.L->addE[p * FD * s.G + e] : 0.0);
+  const int r = e / s.G, c = e - r * s.G;
+  return s.b.E[p * FD * s.G + e] * s.scale[p * FD + r] * s.scale[static_cast<int64_t>(s.nf) * FD + c];
+}
+template <int FD>
+__device__ __forceinline__ double src_g(const NodeSrc& s, int64_t p, int e) {
+  if (s.L) return s.L->g[p * FD + e] + (s.L->addg ? s.L->addg[p * FD + e] : 0.0);
+  return s.b.gf[p * FD + e] * s.scale[p * FD + e];
+}
+
+// Forward + backward sweep of one chunk (separator s = j*c, interior nodes s+1..s+m) by one group of 128 threads.
+// Same algorithm as chain_eliminate_kernel (vc_chain.cuh); here every global load of the chunk is issued in one
+// round up front, the 9 x 9 pivots are factored right-looking with rsqrt, and the group's Schur accumulator Sacc
+// lives on across chunks and levels.
+template <int FD>
+__device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLevel& L, const ChainLevel& nxt, int G, int j, double* sm,
+                                             int tid, int grp, int* bad) {
   constexpr int c = kCsChunk, NT = kCsGroup;
   const int NS = G * G + G;
   const int w = 2 * FD + G + 1, VW = FD + w;
@@ -81,9 +123,10 @@ __device__ inline void chain_eliminate_chunk(const ChainLevel& L, const ChainLev
   double* Al = Sacc + NS;                  // [FD*FD]
   double* El = Al + FD * FD;               // [FD*G]
   double* gl = El + FD * G;                // [FD]
-  double* Ap = gl + FD;                    // [FD*FD] pivot
-  double* Uc = Ap + FD * FD;               // [FD*FD] U[p]
-  double* V = Uc + FD * FD;                // [(c-1)][FD][VW]
+  double* Ap = gl + FD;                    // [(c-1)][FD*FD] pivots
+  double* Uc = Ap + (c - 1) * FD * FD;     // [(c-1)][FD*FD] U[p] = H[p-1, p]
+  double* Ur = Uc + (c - 1) * FD * FD;     // [FD*FD] U of the right separator
+  double* V = Ur + FD * FD;                // [(c-1)][FD][VW]
   double* Eo = V + (c - 1) * FD * VW;      // [(c-1)][FD*G] the interior nodes' own global coupling
   const int s = j * c, n_eff = L.n - L.ghost;
   const int nsep = (n_eff + c - 1) / c;
@@ -92,102 +135,96 @@ __device__ inline void chain_eliminate_chunk(const ChainLevel& L, const ChainLev
   const int m = min(c - 1, n_eff - 1 - s);
   const int rIdx = s + m + 1;
   const int jr = toGhost ? nsep : j + 1;
-  const bool add = L.addA != nullptr;
   group_sync(grp);  // the previous chunk of this group is done with the workspace
-  for (int e = tid; e < FD * FD; e += NT)
-    Al[e] = L.A[static_cast<int64_t>(s) * FD * FD + e] + (add ? L.addA[static_cast<int64_t>(s) * FD * FD + e] : 0.0);
-  for (int e = tid; e < FD * G; e += NT)
-    El[e] = L.E[static_cast<int64_t>(s) * FD * G + e] + (add ? L.addE[static_cast<int64_t>(s) * FD * G + e] : 0.0);
-  for (int e = tid; e < FD; e += NT)
-    gl[e] = L.g[static_cast<int64_t>(s) * FD + e] + (add ? L.addg[static_cast<int64_t>(s) * FD + e] : 0.0);
-  // all interior nodes' right-hand sides at once (one round of global loads instead of one per node)
+  // ---- one round of global loads: separator, pivots, couplings, right-hand sides
+  for (int e = tid; e < FD * FD; e += NT) Al[e] = src_A<FD>(src, s, e);
+  for (int e = tid; e < FD * G; e += NT) El[e] = src_E<FD>(src, s, e);
+  for (int e = tid; e < FD; e += NT) gl[e] = src_g<FD>(src, s, e);
+  if (hasR)
+    for (int e = tid; e < FD * FD; e += NT) Ur[e] = src_U<FD>(src, rIdx, e);
   for (int i = 0; i < m; ++i) {
     const int64_t p = s + 1 + i;
     double* Vi = V + static_cast<int64_t>(i) * FD * VW;
     const bool lastI = i == m - 1;
     for (int e = tid; e < FD * FD; e += NT) {
       const int r = e / FD, q = e - r * FD;
-      const double unext = (!lastI || hasR) ? L.U[(p + 1) * FD * FD + e] : 0.0;  // H[p, p+1]
+      Ap[i * FD * FD + e] = src_A<FD>(src, p, e);
+      const double u = src_U<FD>(src, p, e);
+      Uc[i * FD * FD + e] = u;
+      if (i == 0) Vi[q * VW + oL + r] = u;  // H[p0, s] = U[p0]^T
+      else Vi[r * VW + oL + q] = 0.0;
+      const double unext = (!lastI || hasR) ? src_U<FD>(src, p + 1, e) : 0.0;  // H[p, p+1]
       Vi[r * VW + q] = lastI ? 0.0 : unext;
       Vi[r * VW + oR + q] = (lastI && hasR) ? unext : 0.0;
-      Vi[r * VW + oL + q] = i == 0 ? L.U[p * FD * FD + q * FD + r] : 0.0;  // H[p0, s] = U[p0]^T
     }
     for (int e = tid; e < FD * G; e += NT) {
       const int r = e / G, q = e - r * G;
-      const double v = L.E[p * FD * G + e] + (add ? L.addE[p * FD * G + e] : 0.0);
+      const double v = src_E<FD>(src, p, e);
       Vi[r * VW + oE + q] = v;
       Eo[i * FD * G + e] = v;
     }
-    for (int e = tid; e < FD; e += NT) Vi[e * VW + og] = L.g[p * FD + e] + (add ? L.addg[p * FD + e] : 0.0);
+    for (int e = tid; e < FD; e += NT) Vi[e * VW + og] = src_g<FD>(src, p, e);
   }
+  group_sync(grp);
   // ---- forward sweep
   for (int i = 0; i < m; ++i) {
-    const int64_t p = s + 1 + i;
     double* Vi = V + static_cast<int64_t>(i) * FD * VW;
-    for (int e = tid; e < FD * FD; e += NT) {
-      Ap[e] = L.A[p * FD * FD + e] + (add ? L.addA[p * FD * FD + e] : 0.0);
-      Uc[e] = L.U[p * FD * FD + e];
-    }
-    group_sync(grp);
+    double* Api = Ap + i * FD * FD;
     if (i > 0) {
       const double* Vp = V + static_cast<int64_t>(i - 1) * FD * VW;
+      const double* Uci = Uc + i * FD * FD;
       // A'_i = A_i - U^T V_U(i-1);  R'_i = R_i - U^T V_R(i-1)
       for (int e = tid; e < FD * VW; e += NT) {
         const int r = e / VW, q = e - r * VW;
         double sum = 0.0;
 #pragma unroll
-        for (int k = 0; k < FD; ++k) sum += Uc[k * FD + r] * Vp[k * VW + q];
-        if (q < FD) Ap[r * FD + q] -= sum;
+        for (int k = 0; k < FD; ++k) sum += Uci[k * FD + r] * Vp[k * VW + q];
+        if (q < FD) Api[r * FD + q] -= sum;
         else Vi[r * VW + q] -= sum;
       }
       group_sync(grp);
     }
     if (tid < VW) {
-      // every column-solving thread factors the FD x FD pivot in registers (no serial section, no barrier)
+      // every column-solving thread factors the FD x FD pivot in registers (no serial section, no barrier):
+      // right-looking Cholesky, reciprocal pivots by rsqrt
       double Lr[FD][FD], iL[FD];
 #pragma unroll
       for (int ii = 0; ii < FD; ++ii)
 #pragma unroll
-        for (int k = 0; k <= ii; ++k) Lr[ii][k] = Ap[ii * FD + k];
+        for (int k = 0; k <= ii; ++k) Lr[ii][k] = Api[ii * FD + k];
       bool ok = true;
 #pragma unroll
       for (int jj = 0; jj < FD; ++jj) {
-        double d = Lr[jj][jj];
-#pragma unroll
-        for (int k = 0; k < jj; ++k) d -= Lr[jj][k] * Lr[jj][k];
-        if (!(d > 0.0)) { ok = false; d = 1.0; }
-        d = sqrt(d);
-        Lr[jj][jj] = d;
-        const double inv = 1.0 / d;
+        const double d = Lr[jj][jj];
+        ok = ok && d > 0.0;
+        const double inv = rsqrt(d > 0.0 ? d : 1.0);
         iL[jj] = inv;
 #pragma unroll
-        for (int ii = jj + 1; ii < FD; ++ii) {
-          double t = Lr[ii][jj];
+        for (int ii = jj + 1; ii < FD; ++ii) Lr[ii][jj] *= inv;
 #pragma unroll
-          for (int k = 0; k < jj; ++k) t -= Lr[ii][k] * Lr[jj][k];
-          Lr[ii][jj] = t * inv;
-        }
+        for (int ii = jj + 1; ii < FD; ++ii)
+#pragma unroll
+          for (int k = jj + 1; k <= ii; ++k) Lr[ii][k] -= Lr[ii][jj] * Lr[k][jj];
       }
       if (!ok && tid == 0) *bad = 1;
-      for (int q = tid; q < VW; q += NT) {
-        double x[FD];
+      const int q = tid;
+      double x[FD];
 #pragma unroll
-        for (int ii = 0; ii < FD; ++ii) {
-          double t = Vi[ii * VW + q];
+      for (int ii = 0; ii < FD; ++ii) {
+        double t = Vi[ii * VW + q];
 #pragma unroll
-          for (int k = 0; k < ii; ++k) t -= Lr[ii][k] * x[k];
-          x[ii] = t * iL[ii];
-        }
-#pragma unroll
-        for (int ii = FD - 1; ii >= 0; --ii) {
-          double t = x[ii];
-#pragma unroll
-          for (int k = ii + 1; k < FD; ++k) t -= Lr[k][ii] * x[k];
-          x[ii] = t * iL[ii];
-        }
-#pragma unroll
-        for (int ii = 0; ii < FD; ++ii) Vi[ii * VW + q] = x[ii];
+        for (int k = 0; k < ii; ++k) t -= Lr[ii][k] * x[k];
+        x[ii] = t * iL[ii];
       }
+#pragma unroll
+      for (int ii = FD - 1; ii >= 0; --ii) {
+        double t = x[ii];
+#pragma unroll
+        for (int k = FD - 1; k > ii; --k) t -= Lr[k][ii] * x[k];
+        x[ii] = t * iL[ii];
+      }
+#pragma unroll
+      for (int ii = 0; ii < FD; ++ii) Vi[ii * VW + q] = x[ii];
     }
     group_sync(grp);
   }
@@ -228,15 +265,14 @@ __device__ inline void chain_eliminate_chunk(const ChainLevel& L, const ChainLev
   if (m > 0) {
     const double* X0 = V;                                          // node s+1
     const double* Xl = V + static_cast<int64_t>(m - 1) * FD * VW;  // last interior node
-    const double* U0 = L.U + static_cast<int64_t>(s + 1) * FD * FD;  // H[s, s+1]
-    const double* Ur = hasR ? L.U + static_cast<int64_t>(rIdx) * FD * FD : nullptr;  // H[rIdx-1, rIdx]
+    const double* U0 = Uc;                                         // H[s, s+1]
     for (int e = tid; e < FD * w; e += NT) {
       const int r = e / w, q = e - r * w;  // q indexes [L | R | E | g]
       double sl = 0.0, sr = 0.0;
 #pragma unroll
       for (int k = 0; k < FD; ++k) {
         sl += U0[r * FD + k] * X0[k * VW + FD + q];
-        if (hasR) sr += Ur[k * FD + r] * Xl[k * VW + FD + q];
+        if (hasR) sr += Ur[k * FD + r] * Xl[k * VW + FD + q];  // H[rIdx-1, rIdx]^T
       }
       if (q < FD) {
         Al[r * FD + q] -= sl;                                        // A_s -= H[s,p0] Z_L
@@ -256,20 +292,17 @@ __device__ inline void chain_eliminate_chunk(const ChainLevel& L, const ChainLev
   } else if (hasR) {
     // no interior node between this separator and the ghost: the coupling passes through unchanged
     for (int e = tid; e < FD * FD; e += NT) {
-      nxt.U[static_cast<int64_t>(jr) * FD * FD + e] = L.U[static_cast<int64_t>(rIdx) * FD * FD + e];
+      nxt.U[static_cast<int64_t>(jr) * FD * FD + e] = Ur[e];
       nxt.addA[static_cast<int64_t>(jr) * FD * FD + e] = 0.0;
     }
     for (int e = tid; e < FD * G; e += NT) nxt.addE[static_cast<int64_t>(jr) * FD * G + e] = 0.0;
     for (int e = tid; e < FD; e += NT) nxt.addg[static_cast<int64_t>(jr) * FD + e] = 0.0;
   }
   if (toGhost) {  // carry the ghost node itself to the next level (its Schur updates went to nxt.add*)
-    for (int e = tid; e < FD * FD; e += NT)
-      nxt.A[static_cast<int64_t>(jr) * FD * FD + e] = L.A[static_cast<int64_t>(rIdx) * FD * FD + e] + (add ? L.addA[static_cast<int64_t>(rIdx) * FD * FD + e] : 0.0);
-    for (int e = tid; e < FD * G; e += NT)
-      nxt.E[static_cast<int64_t>(jr) * FD * G + e] = L.E[static_cast<int64_t>(rIdx) * FD * G + e] + (add ? L.addE[static_cast<int64_t>(rIdx) * FD * G + e] : 0.0);
-    for (int e = tid; e < FD; e += NT)
-      nxt.g[static_cast<int64_t>(jr) * FD + e] = L.g[static_cast<int64_t>(rIdx) * FD + e] + (add ? L.addg[static_cast<int64_t>(rIdx) * FD + e] : 0.0);
-    if (tid == 0) nxt.orig[jr] = L.orig[rIdx];
+    for (int e = tid; e < FD * FD; e += NT) nxt.A[static_cast<int64_t>(jr) * FD * FD + e] = src_A<FD>(src, rIdx, e);
+    for (int e = tid; e < FD * G; e += NT) nxt.E[static_cast<int64_t>(jr) * FD * G + e] = src_E<FD>(src, rIdx, e);
+    for (int e = tid; e < FD; e += NT) nxt.g[static_cast<int64_t>(jr) * FD + e] = src_g<FD>(src, rIdx, e);
+    if (tid == 0) nxt.orig[jr] = src.L ? L.orig[rIdx] : rIdx;
   }
   group_sync(grp);
   for (int e = tid; e < FD * FD; e += NT) {
@@ -284,7 +317,45 @@ __device__ inline void chain_eliminate_chunk(const ChainLevel& L, const ChainLev
     nxt.g[static_cast<int64_t>(j) * FD + e] = gl[e];
     if (j == 0) nxt.addg[e] = 0.0;
   }
-  if (tid == 0) nxt.orig[j] = L.orig[s];
+  if (tid == 0) nxt.orig[j] = src.L ? L.orig[s] : s;
+}
+
+// x (+) step of one frame into the trial state, and the frame's share of the step statistics
+// (acc: step.g, step.D2.step, |x_new - x|^2, |x_new|^2)
+__device__ __forceinline__ void chain_update_frame(const ChainSolveArgs& a, const Blocks& b, double rinv, int f, const double* d,
+                                                   double acc[4]) {
+  constexpr int FD = 9;
+  const int cur = a.ctl->cur;
+  const double* x_cur = a.state[cur];
+  double* x_new = a.state[1 - cur];
+  double du[FD];
+#pragma unroll
+  for (int r = 0; r < FD; ++r) {
+    const int64_t k = static_cast<int64_t>(f) * FD + r;
+    const double sc = a.scale[k];
+    const double d2 = a.D2x ? a.D2x[k] : lm_damp(b.B[k * FD + r], sc, rinv);
+    acc[0] += d[r] * b.gf[k] * sc;
+    acc[1] += d[r] * d[r] * d2;
+    du[r] = d[r] * sc;
+  }
+  const double* x = x_cur + 7 * static_cast<int64_t>(f);
+  double xo[7];
+  se3_plus(x, du, xo);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    x_new[7 * static_cast<int64_t>(f) + k] = xo[k];
+    acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+    acc[3] += xo[k] * xo[k];
+  }
+  const double* v = x_cur + a.dp.off_v + 3 * static_cast<int64_t>(f);
+  double* vo = x_new + a.dp.off_v + 3 * static_cast<int64_t>(f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double nv = v[k] + du[6 + k];
+    vo[k] = nv;
+    acc[2] += (nv - v[k]) * (nv - v[k]);
+    acc[3] += nv * nv;
+  }
 }
 
 // One damped solve of the frame-chain + globals system and (optionally) the state update, all in one launch.
@@ -301,6 +372,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
   const int64_t nfp = static_cast<int64_t>(nf) * FD;
   __shared__ int bad_s[kCsGroups];
   __shared__ int bad_dense;
+  __shared__ double part[kCsThreads / 32][4];
   if (a.ctl->done) return;  // uniform over the grid: written before this launch
   const Blocks& b = a.b[a.ctl->cur];
   const double rinv = 1.0 / a.ctl->radius;
@@ -317,52 +389,43 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
   double* gsm = smem + static_cast<size_t>(grp) * chain_group_doubles(G);
   if (gtid == 0) bad_s[grp] = 0;
   for (int e = gtid; e < NS; e += kCsGroup) gsm[e] = 0.0;  // the group's Schur accumulator
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};                   // this thread's share of the step statistics
 
-  // ------------------------------------------------------------ level 0: scaled + damped blocks
-  {
-    const ChainLevel& L = a.lev[0];
-    const double* sc = a.scale + nfp;
-    for (int f = gid; f < nf; f += n_groups) {
-      const double* sf = a.scale + static_cast<int64_t>(f) * FD;
-      for (int e = gtid; e < FD * FD; e += kCsGroup) {
-        const int r = e / FD, c = e - r * FD;
-        const double bij = b.B[static_cast<int64_t>(f) * FD * FD + e];
-        double v = bij * sf[r] * sf[c];
-        if (r == c) v += a.D2x ? a.D2x[static_cast<int64_t>(f) * FD + r] : lm_damp(bij, sf[r], rinv);
-        L.A[static_cast<int64_t>(f) * FD * FD + e] = v;
-        double u = 0.0;
-        if (f > 0) u = b.U[static_cast<int64_t>(f) * FD * FD + e] * a.scale[static_cast<int64_t>(f - 1) * FD + r] * sf[c];
-        L.U[static_cast<int64_t>(f) * FD * FD + e] = u;
-      }
-      for (int e = gtid; e < FD * G; e += kCsGroup) {
-        const int r = e / G, c = e - r * G;
-        L.E[static_cast<int64_t>(f) * FD * G + e] = b.E[static_cast<int64_t>(f) * FD * G + e] * sf[r] * sc[c];
-      }
-      for (int e = gtid; e < FD; e += kCsGroup) L.g[static_cast<int64_t>(f) * FD + e] = b.gf[static_cast<int64_t>(f) * FD + e] * sf[e];
-      if (gtid == 0) L.orig[f] = f;
-    }
-  }
-  mark(kCsProfInit);
-  grid.sync();
   // ------------------------------------------------------------ elimination, level by level
   for (int l = 0; l + 1 < a.n_levels; ++l) {
-    const ChainLevel& L = a.lev[l];
+    NodeSrc src;
+    src.L = l > 0 ? &a.lev[l] : nullptr;
+    src.b = b; src.scale = a.scale; src.D2x = a.D2x; src.rinv = rinv; src.G = G; src.nf = nf;
     const int nsep = a.lev[l + 1].n - a.dp.ghost;
-    for (int j = gid; j < nsep; j += n_groups) chain_eliminate_chunk<FD>(L, a.lev[l + 1], G, j, gsm, gtid, grp, &bad_s[grp]);
+    for (int j = gid; j < nsep; j += n_groups) chain_eliminate_chunk<FD>(src, a.lev[l], a.lev[l + 1], G, j, gsm, gtid, grp, &bad_s[grp]);
     if (l + 2 == a.n_levels) {  // last level: publish this group's Schur partial
       group_sync(grp);
       double* out = a.Spart + static_cast<int64_t>(gid) * NS;
       for (int e = gtid; e < NS; e += kCsGroup) out[e] = gsm[e];
       if (gtid == 0 && bad_s[grp]) a.scalars[kScNotPD] = 1.0;
     }
+    mark(kCsProfElim + l);
     grid.sync();
   }
-  if (a.n_levels == 1) {  // nothing to eliminate: zero partials
+  if (a.n_levels == 1) {  // nothing to eliminate: the top level is the problem itself; zero partials
+    const ChainLevel& L = a.lev[0];
+    NodeSrc src;
+    src.L = nullptr; src.b = b; src.scale = a.scale; src.D2x = a.D2x; src.rinv = rinv; src.G = G; src.nf = nf;
+    if (bid == 0) {
+      for (int f = 0; f < nf; ++f) {
+        for (int e = tid; e < FD * FD; e += kCsThreads) {
+          L.A[static_cast<int64_t>(f) * FD * FD + e] = src_A<FD>(src, f, e);
+          L.U[static_cast<int64_t>(f) * FD * FD + e] = src_U<FD>(src, f, e);
+        }
+        for (int e = tid; e < FD * G; e += kCsThreads) L.E[static_cast<int64_t>(f) * FD * G + e] = src_E<FD>(src, f, e);
+        for (int e = tid; e < FD; e += kCsThreads) L.g[static_cast<int64_t>(f) * FD + e] = src_g<FD>(src, f, e);
+        if (tid == 0) L.orig[f] = f;
+      }
+    }
     double* out = a.Spart + static_cast<int64_t>(gid) * NS;
     for (int e = gtid; e < NS; e += kCsGroup) out[e] = 0.0;
     grid.sync();
   }
-  mark(kCsProfElim);
   // ------------------------------------------------------------ Schur partials -> total (fixed order), distributed
   mega_reduce_stage1(a.Spart, NS, n_groups, NS, a.Ssum, -1, -1);
   mark(kCsProfReduce);
@@ -371,8 +434,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
   {
     const ChainLevel& top = a.lev[a.n_levels - 1];
     const int nt = top.n, N = G + nt * FD;
-    double* S = smem;
-    double* rhs = S + N * N;
+    double* S = smem;         // [N][N] lower triangle; unscaled columns u_ij (L D L^T: L_ij = u_ij / d_j)
+    double* rhs = S + N * N;  // row N of the same elimination: u_Nj
+    double* wd = rhs + N;     // 1 / d_j
     const double* sc = a.scale + nfp;
     if (tid == 0) bad_dense = 0;
     for (int e = tid; e < N * N + N; e += kCsThreads) S[e] = 0.0;
@@ -411,35 +475,29 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       for (int e = tid; e < FD; e += kCsThreads)
         rhs[o + e] = -(__ldcg(top.g + static_cast<int64_t>(t) * FD + e) + (add ? __ldcg(top.addg + static_cast<int64_t>(t) * FD + e) : 0.0));
     }
-    __syncthreads();
-    // right-looking Cholesky, lower triangle; the right-hand side rides along as row N
+    // right-looking L D L^T on the lower triangle, the right-hand side riding along as row N: one barrier per
+    // column, 16 x 16 thread tiling of the trailing update
+    const int ti = tid >> 4, tk = tid & 15;
     for (int j = 0; j < N; ++j) {
-      const double d0 = S[j * N + j];
-      const bool okp = d0 > 0.0;
-      const double inv = rsqrt(okp ? d0 : 1.0);
       __syncthreads();
+      const double d = S[j * N + j];
+      const bool okp = d > 0.0;
+      const double wj = 1.0 / (okp ? d : 1.0);
       if (tid == 0) {
-        S[j * N + j] = (okp ? d0 : 1.0) * inv;
+        wd[j] = wj;
         if (!okp) bad_dense = 1;
       }
-      for (int i = j + 1 + tid; i <= N; i += kCsThreads) {
+      for (int i = j + 1 + ti; i <= N; i += 16) {
         double* row = i < N ? S + i * N : rhs;
-        row[j] *= inv;
-      }
-      __syncthreads();
-      const int rem = N - j;  // rows j+1..N (N = rhs)
-      for (int e = tid; e < rem * (rem - 1); e += kCsThreads) {
-        const int ri = e / (rem - 1), ci = e - ri * (rem - 1);
-        const int i = j + 1 + ri, k = j + 1 + ci;
-        if (k > i || k >= N) continue;
-        double* row = i < N ? S + i * N : rhs;
-        row[k] -= row[j] * S[k * N + j];
+        const double lw = row[j] * wj;
+        const int kmax = i < N ? i : N - 1;
+        for (int k = j + 1 + tk; k <= kmax; k += 16) row[k] -= lw * S[k * N + j];
       }
     }
     __syncthreads();
-    if (warp == 0) {  // L^T x = y (y = rhs after the forward elimination above)
+    if (warp == 0) {  // x_i = (u_Ni - sum_{k>i} u_ki x_k) / d_i
       for (int i = N - 1; i >= 0; --i) {
-        const double xi = rhs[i] / S[i * N + i];
+        const double xi = rhs[i] * wd[i];
         __syncwarp();
         if (lane == 0) rhs[i] = xi;
         for (int k = lane; k < i; k += 32) rhs[k] -= S[i * N + k] * xi;
@@ -452,14 +510,60 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       for (int i = tid; i < G; i += kCsThreads) a.delta[nfp + i] = bd ? 0.0 : rhs[i];
       for (int e = tid; e < nt * FD; e += kCsThreads) {
         const int t = e / FD, r = e - t * FD;
-        a.delta[static_cast<int64_t>(top.orig[t]) * FD + r] = bd ? 0.0 : rhs[G + t * FD + r];
+        a.delta[static_cast<int64_t>(a.n_levels > 1 ? top.orig[t] : t) * FD + r] = bd ? 0.0 : rhs[G + t * FD + r];
       }
       if (tid == 0 && bd) a.scalars[kScNotPD] = 1.0;
+      if (a.do_update && tid < nt) {  // the top nodes' frames
+        double d[FD];
+        for (int r = 0; r < FD; ++r) d[r] = bd ? 0.0 : rhs[G + tid * FD + r];
+        chain_update_frame(a, b, rinv, a.n_levels > 1 ? top.orig[tid] : tid, d, acc);
+      }
+      // globals: cameras + IMU parameters (one thread)
+      if (a.do_update && tid == kCsThreads - 1) {
+        const double* x_cur = a.state[a.ctl->cur];
+        double* x_new = a.state[1 - a.ctl->cur];
+        double g4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int c = 0; c < a.dp.n_cams; ++c) {
+          const CamInfo& ci = a.dp.cams[c];
+          const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
+          double* xo = x_new + a.dp.off_cam + kCamStateStride * c;
+          double du[3];
+          for (int k = 0; k < 3; ++k) du[k] = (bd ? 0.0 : rhs[ci.goff + k]) * sc[ci.goff + k];
+          double qo[4];
+          so3_plus(x, du, qo);
+          for (int k = 0; k < 4; ++k) xo[k] = qo[k];
+          for (int k = 0; k < 3; ++k) xo[4 + k] = x[4 + k] + (bd ? 0.0 : rhs[ci.goff + 3 + k]) * sc[ci.goff + 3 + k];
+          for (int k = 0; k < 10; ++k)
+            xo[7 + k] = x[7 + k] + (k < ci.K ? (bd ? 0.0 : rhs[ci.goff + 6 + k]) * sc[ci.goff + 6 + k] : 0.0);
+          for (int k = 0; k < 7 + ci.K; ++k) {
+            g4[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+            g4[3] += xo[k] * xo[k];
+          }
+        }
+        {
+          const double* x = x_cur + a.dp.off_imu;
+          double* xo = x_new + a.dp.off_imu;
+          for (int k = 0; k < kImuStateSize; ++k) {
+            const double dd = (bd ? 0.0 : rhs[a.dp.imu_goff + k]) * sc[a.dp.imu_goff + k];
+            xo[k] = x[k] + dd;
+            g4[2] += dd * dd;
+            g4[3] += xo[k] * xo[k];
+          }
+        }
+        for (int k = 0; k < G; ++k) {
+          const double d2 = a.D2x ? a.D2x[nfp + k] : lm_damp(b.C[k * G + k], sc[k], rinv);
+          const double dk = bd ? 0.0 : rhs[k];
+          g4[0] += dk * b.gc[k] * sc[k];
+          g4[1] += dk * dk * d2;
+        }
+        for (int q = 0; q < 4; ++q) a.step_part[4 * static_cast<int64_t>(nb) + q] = g4[q];
+      }
     }
   }
   mark(kCsProfDense);
   grid.sync();
-  // ------------------------------------------------------------ back-substitution, top-down
+  // ------------------------------------------------------------ back-substitution, top-down; every node's frame is
+  // updated by the warp that solves it
   {
     const int w = 2 * FD + G + 1, c = kCsChunk;
     const int gw = bid * (kCsThreads / 32) + warp, nw = nb * (kCsThreads / 32);
@@ -467,123 +571,60 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     for (int l = a.n_levels - 2; l >= 0; --l) {
       const ChainLevel& cur = a.lev[l];
       const int n_eff = cur.n - cur.ghost;
-      for (int p = gw; p < n_eff; p += nw) {
-        if (p % c == 0) continue;  // separators were solved at the level above
-        const int s = (p / c) * c;
+      const int n_chunks = (n_eff + c - 1) / c;
+      // interior node q (0..c-2) of chunk j: p = j*c + 1 + q
+      for (int t = gw; t < n_chunks * (c - 1); t += nw) {
+        const int jc = t / (c - 1), p = jc * c + 1 + (t - jc * (c - 1));
+        if (p >= n_eff) continue;
+        const int s = jc * c;
         const int r = s + c < n_eff ? s + c : (cur.ghost ? cur.n - 1 : cur.n);
-        const double* xl = a.delta + static_cast<int64_t>(cur.orig[s]) * FD;
-        const double* xr = r < cur.n ? a.delta + static_cast<int64_t>(cur.orig[r]) * FD : nullptr;
+        const int os = l > 0 ? cur.orig[s] : s, op = l > 0 ? cur.orig[p] : p;
+        const double* xl = a.delta + static_cast<int64_t>(os) * FD;
+        const double* xr = r < cur.n ? a.delta + static_cast<int64_t>(l > 0 ? cur.orig[r] : r) * FD : nullptr;
         const double* Z = cur.Z + static_cast<int64_t>(p) * FD * w;
-        double* out = a.delta + static_cast<int64_t>(cur.orig[p]) * FD;
+        double* out = a.delta + static_cast<int64_t>(op) * FD;
+        // the solved neighbours / globals this lane multiplies with (two columns per lane at most: w - 1 <= 64 ... or a loop)
+        double d[FD];
+#pragma unroll
+        for (int rr = 0; rr < FD; ++rr) d[rr] = 0.0;
+        for (int q = lane; q < w - 1; q += 32) {
+          const double x = q < FD ? __ldcg(xl + q) : q < 2 * FD ? (xr ? __ldcg(xr + q - FD) : 0.0) : __ldcg(dc + q - 2 * FD);
+#pragma unroll
+          for (int rr = 0; rr < FD; ++rr) d[rr] += __ldcg(Z + rr * w + q) * x;
+        }
 #pragma unroll
         for (int rr = 0; rr < FD; ++rr) {
-          const double* z = Z + rr * w;
-          double sum = 0.0;
-          for (int q = lane; q < w - 1; q += 32) {
-            const double x = q < FD ? __ldcg(xl + q) : q < 2 * FD ? (xr ? __ldcg(xr + q - FD) : 0.0) : __ldcg(dc + q - 2 * FD);
-            sum += __ldcg(z + q) * x;
-          }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0) out[rr] = -__ldcg(z + w - 1) - sum;
+          for (int o = 16; o > 0; o >>= 1) d[rr] += __shfl_xor_sync(0xffffffffu, d[rr], o);
+          d[rr] = -__ldcg(Z + rr * w + w - 1) - d[rr];
         }
+        if (lane < FD) {
+          double v = d[0];
+#pragma unroll
+          for (int rr = 1; rr < FD; ++rr) v = lane == rr ? d[rr] : v;
+          out[lane] = v;
+        }
+        if (a.do_update && lane == 0) chain_update_frame(a, b, rinv, op, d, acc);
       }
-      grid.sync();
+      mark(kCsProfBacksub + (a.n_levels - 2 - l));
+      if (l > 0) grid.sync();
     }
   }
-  mark(kCsProfBacksub);
   if (!a.do_update) return;
-  // ------------------------------------------------------------ x (+) step into the trial state, step statistics
-  {
-    const int cur = a.ctl->cur;
-    const double* x_cur = a.state[cur];
-    double* x_new = a.state[1 - cur];
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int f = bid * kCsThreads + tid; f < nf; f += nb * kCsThreads) {
-      double du[FD];
+  // ------------------------------------------------------------ step statistics of this CTA
 #pragma unroll
-      for (int r = 0; r < FD; ++r) {
-        const int64_t k = static_cast<int64_t>(f) * FD + r;
-        const double d = __ldcg(a.delta + k), sc = a.scale[k];
-        const double d2 = a.D2x ? a.D2x[k] : lm_damp(b.B[k * FD + r], sc, rinv);
-        acc[0] += d * b.gf[k] * sc;
-        acc[1] += d * d * d2;
-        du[r] = d * sc;
-      }
-      const double* x = x_cur + 7 * static_cast<int64_t>(f);
-      double xo[7];
-      se3_plus(x, du, xo);
+  for (int q = 0; q < 4; ++q) {
 #pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        x_new[7 * static_cast<int64_t>(f) + k] = xo[k];
-        acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
-        acc[3] += xo[k] * xo[k];
-      }
-      const double* v = x_cur + a.dp.off_v + 3 * static_cast<int64_t>(f);
-      double* vo = x_new + a.dp.off_v + 3 * static_cast<int64_t>(f);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double nv = v[k] + du[6 + k];
-        vo[k] = nv;
-        acc[2] += (nv - v[k]) * (nv - v[k]);
-        acc[3] += nv * nv;
-      }
-    }
-    __shared__ double part[kCsThreads / 32][4];
-#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+  }
+  if (lane == 0)
+    for (int q = 0; q < 4; ++q) part[warp][q] = acc[q];
+  __syncthreads();
+  if (tid == 0) {
     for (int q = 0; q < 4; ++q) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-    }
-    if (lane == 0)
-      for (int q = 0; q < 4; ++q) part[warp][q] = acc[q];
-    __syncthreads();
-    if (tid == 0) {
-      for (int q = 0; q < 4; ++q) {
-        double s = 0.0;
-        for (int w = 0; w < kCsThreads / 32; ++w) s += part[w][q];
-        a.step_part[4 * static_cast<int64_t>(bid) + q] = s;
-      }
-    }
-    // globals: cameras + IMU parameters (one thread of the last CTA)
-    if (bid == nb - 1 && tid == kCsThreads - 1) {
-      double g4[4] = {0.0, 0.0, 0.0, 0.0};
-      const double* sc = a.scale + nfp;
-      const double* dc = a.delta + nfp;
-      for (int c = 0; c < a.dp.n_cams; ++c) {
-        const CamInfo& ci = a.dp.cams[c];
-        const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
-        double* xo = x_new + a.dp.off_cam + kCamStateStride * c;
-        double du[3];
-        for (int k = 0; k < 3; ++k) du[k] = __ldcg(dc + ci.goff + k) * sc[ci.goff + k];
-        double qo[4];
-        so3_plus(x, du, qo);
-        for (int k = 0; k < 4; ++k) xo[k] = qo[k];
-        for (int k = 0; k < 3; ++k) xo[4 + k] = x[4 + k] + __ldcg(dc + ci.goff + 3 + k) * sc[ci.goff + 3 + k];
-        for (int k = 0; k < 10; ++k)
-          xo[7 + k] = x[7 + k] + (k < ci.K ? __ldcg(dc + ci.goff + 6 + k) * sc[ci.goff + 6 + k] : 0.0);
-        for (int k = 0; k < 7 + ci.K; ++k) {
-          g4[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
-          g4[3] += xo[k] * xo[k];
-        }
-      }
-      {
-        const double* x = x_cur + a.dp.off_imu;
-        double* xo = x_new + a.dp.off_imu;
-        for (int k = 0; k < kImuStateSize; ++k) {
-          const double dd = __ldcg(dc + a.dp.imu_goff + k) * sc[a.dp.imu_goff + k];
-          xo[k] = x[k] + dd;
-          g4[2] += dd * dd;
-          g4[3] += xo[k] * xo[k];
-        }
-      }
-      for (int k = 0; k < G; ++k) {
-        const double d2 = a.D2x ? a.D2x[nfp + k] : lm_damp(b.C[k * G + k], sc[k], rinv);
-        const double d = __ldcg(dc + k);
-        g4[0] += d * b.gc[k] * sc[k];
-        g4[1] += d * d * d2;
-      }
-      for (int q = 0; q < 4; ++q) a.step_part[4 * static_cast<int64_t>(nb) + q] = g4[q];
+      double sum = 0.0;
+      for (int ww = 0; ww < kCsThreads / 32; ++ww) sum += part[ww][q];
+      a.step_part[4 * static_cast<int64_t>(bid) + q] = sum;
     }
   }
   mark(kCsProfUpdate);

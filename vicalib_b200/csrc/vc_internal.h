@@ -17,7 +17,8 @@ constexpr int kCamStateStride = 17;  // q_ck(4) p_ck(3) intr(10)
 constexpr int kImuStateSize = 15;    // g2 b6 sf6 ts1
 constexpr int kMaxW = 21;            // 6 pose + (6 + K<=8) globals + residual column
 constexpr int kCgStride = 120;       // per-group packed global block: sym (6+K)^2 (<=105) + gradient (<=14)
-constexpr int kReduceBlocks = 64;    // level-1 partials of the global-block reduction
+constexpr int kReduceBlocks = 64;
+constexpr int kImuProfSlots = 64;   // phase clock slots of the persistent inertial kernels    // level-1 partials of the global-block reduction
 
 struct CamInfo {
   int model, K;
@@ -179,7 +180,8 @@ struct vcgpu_handle {
   // persistent inertial kernels (vc_imu_mega.cuh, vc_imu_eval_mega.cuh)
   bool imu_mega_ok = false;
   int imu_mega_grid = 0;
-  unsigned long long* d_prof2 = nullptr;  // [16] phase clocks: chain_solve [0,8), eval [8,16)
+  unsigned long long* d_prof2 = nullptr;  // [kImuProfSlots] phase clocks: chain_solve [0,32), eval [32,48)
+  unsigned long long phase_ns[64] = {};   // accumulated since the last vcgpu_set_profiling (vcgpu_get_phase_clocks)
   int n_step_part = 0;            // entries of d_red written by the last state update
   double* d_dl = nullptr;         // dogleg work vectors [6][nf*fd+G] + matvec partials
   double* d_dl_part = nullptr;    // [kDlBlocks][4]

@@ -112,6 +112,12 @@ extern "C" int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2) {
   h->phase_clocks = (profile & 8) != 0; // bit 3: persistent kernel records per-phase device clocks
   h->flush_l2 = flush_l2 != 0;
   for (int s = 0; s < VCGPU_STAGE_COUNT; ++s) { h->st_ms[s] = 0; h->st_n[s] = 0; h->st_used[s] = false; }
+  for (int k = 0; k < vc::kImuProfSlots; ++k) h->phase_ns[k] = 0;
+  return VCGPU_OK;
+}
+extern "C" int vcgpu_get_phase_clocks(vcgpu_handle* h, uint64_t ns[64]) {
+  if (!h || !ns) return VCGPU_ERR_INVALID;
+  for (int k = 0; k < 64; ++k) ns[k] = h->phase_ns[k];
   return VCGPU_OK;
 }
 extern "C" int vcgpu_get_stage_times(vcgpu_handle* h, double ms_total[VCGPU_STAGE_COUNT], int64_t launches[VCGPU_STAGE_COUNT]) {
