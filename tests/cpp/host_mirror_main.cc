@@ -10,7 +10,7 @@
 #include <cstdio>
 #include <vector>
 
-#include "../../vicalib_b200/host/vicalibrator.h"
+#include "../../vicalib_b200/host/vicalib_task_checks.h"
 
 using namespace visual_inertial_calibration;
 
@@ -25,7 +25,10 @@ int main(int argc, char** argv) {
   if (argc < 4) { std::fprintf(stderr, "usage: %s problem.bin result.txt cameras.xml\n", argv[0]); return 2; }
   FILE* f = fopen(argv[1], "rb");
   if (!f) return 2;
-  // header: n_cams n_frames n_obs n_imu inertial has_initial_guess max_iters dup
+  // header: n_cams n_frames n_obs n_imu inertial has_initial_guess max_iters mode
+  //   mode bit 0: emulate the residual-block duplication; bit 1: LEVENBERG_MARQUARDT instead of the reference's DOGLEG;
+  //   bit 2: run, Clear(), load the problem again and run once more (a reused object must start from scratch);
+  //   bit 3: remove_outliers
   std::vector<int64_t> hd = rd<int64_t>(f, 8);
   const int nc = static_cast<int>(hd[0]), nf = static_cast<int>(hd[1]);
   const int64_t nobs = hd[2], nimu = hd[3];
@@ -45,9 +48,19 @@ int main(int argc, char** argv) {
   CalibratorFlags flags;
   flags.calibrate_imu = inertial;
   flags.max_iters = static_cast<int>(hd[6]);
-  flags.remove_outliers = false;
+  flags.remove_outliers = (hd[7] & 8) != 0;
+  if (hd[7] & 2) flags.trust_region_strategy = 0;
   ViCalibrator cal(flags);
-  cal.SetEmulateBlockDuplication(hd[7] != 0);
+  std::vector<CameraAndPose> input_cameras;
+  for (int pass = 0; pass < ((hd[7] & 4) ? 2 : 1); ++pass) {
+  if (pass > 0) cal.Clear();
+  cal.SetEmulateBlockDuplication((hd[7] & 1) != 0);
+  input_cameras.clear();
+  for (int c = 0; c < nc; ++c) {
+    std::vector<double> params0(intr.begin() + 10 * c, intr.begin() + 10 * c + kK[model[c]]);
+    input_cameras.push_back(CameraAndPose(std::shared_ptr<CameraInterface>(new CameraInterface(kTypes[model[c]], 640, 480, params0)),
+                                          SE3d(&q[4 * c], &p[3 * c])));
+  }
   for (int c = 0; c < nc; ++c) {
     std::vector<double> params(intr.begin() + 10 * c, intr.begin() + 10 * c + kK[model[c]]);
     std::shared_ptr<CameraInterface> cam(new CameraInterface(kTypes[model[c]], 640, 480, params));
@@ -63,6 +76,7 @@ int main(int argc, char** argv) {
   cal.Start();
   while (cal.IsRunning()) usleep(2000);  // the reference polls every 30 ms (vicalib-engine.cc:388-400)
   cal.Stop();
+  }
   cal.WriteCameraModels(argv[3]);
 
   FILE* o = fopen(argv[2], "w");
@@ -96,6 +110,20 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 9; ++k) worst = std::max(worst, std::fabs(rig[c]->RDF()[k] - w.RDF()[k]));
   }
   std::fprintf(o, "xml_roundtrip %.3g\n", worst);
+  // VicalibTask::IsSuccessful (vicalib-task.cc:837-863) with the flag defaults
+  const std::vector<double> max_err(nc, SuccessThresholds().max_reprojection_error);
+  std::fprintf(o, "success %d %d\n", IsSuccessful(cal, max_err, false, input_cameras, Vector6d{{0, 0, 0, 0, 0, 0}}) ? 1 : 0,
+               IsSuccessful(cal, max_err, true, input_cameras, Vector6d{{0, 0, 0, 0, 0, 0}}) ? 1 : 0);
+  // GetIntegrationPoses (vicalibrator.h:508-533): end pose of the first interval's integration vs the second frame
+  if (inertial && nf > 1) {
+    const std::vector<ImuPose> ip = cal.GetIntegrationPoses(0);
+    double dp = -1;
+    if (!ip.empty()) {
+      dp = 0;
+      for (int k = 0; k < 3; ++k) dp = std::max(dp, std::fabs(ip.back().t_wp_.d[4 + k] - cal.GetFrame(1)->t_wp_.d[4 + k]));
+    }
+    std::fprintf(o, "integration_poses %zu %.6g %.17g\n", ip.size(), dp, ip.empty() ? 0.0 : ip.back().time_);
+  }
   fclose(o);
   return 0;
 }

@@ -27,11 +27,12 @@ def _write_problem(path, p, has_guess, max_iters, dup):
             np.ascontiguousarray(a, dtype=np.float64).tofile(f)
 
 
-def _run(tmp_path, p, has_guess=True, max_iters=200, dup=False):
-    if not os.path.exists(EXE):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")])
+def _run(tmp_path, p, has_guess=True, max_iters=200, dup=False, lm=True, reuse=False, outliers=False):
+    """mode bits of tests/cpp/host_mirror_main.cc: 1 block duplication, 2 LM (else the reference's DOGLEG),
+    4 Clear() + second run on the same object, 8 remove_outliers"""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s", "host_mirror"])
     prob, res, xml = (str(tmp_path / n) for n in ("problem.bin", "result.txt", "cameras.xml"))
-    _write_problem(prob, p, has_guess, max_iters, dup)
+    _write_problem(prob, p, has_guess, max_iters, int(dup) | (2 if lm else 0) | (4 if reuse else 0) | (8 if outliers else 0))
     subprocess.run([EXE, prob, res, xml], check=True, timeout=300)
     out = {}
     for line in open(res):
@@ -103,10 +104,93 @@ def test_inertial_with_initial_guess(tmp_path):
     assert "<right> [ 0; 0; 1 ] </right>" in xml  # RdfRobotics columns (vicalibrator.h:215)
 
 
-def test_staged_flow_runs_all_stages(tmp_path):
-    """No initial guess + IMU: visual -> rotation-only -> full+bias -> scale factors -> finished
-    (vicalibrator.h:976-1016), with the residual-block duplication quirk emulated."""
+def _staged_oracle(p, max_iters, dup, strategy, function_tol=1e-10):
+    """The stage machine of ViCalibrator::SolveThread + SetupProblem (vicalibrator.h:548-679, 919-1040) driven over the
+    CPU oracle: visual -> inertial rotation-only -> full + biases -> scale factors -> finished, residual-block
+    multiplicities growing by one per stage when the duplication quirk is emulated."""
+    import math
+
+    from oracle.binding import Oracle
+
+    o = Oracle(p)
+    inertial, rot_only, bias, scale, grav_init, finished = False, True, False, False, False, False
+    visual_adds = imu_adds = n_solves = 0
+    while not finished:
+        visual_adds += 1
+        if inertial:
+            imu_adds += 1
+        o.set_flags(inertial=int(inertial), rotation_only=int(rot_only), bias_active=int(bias), scale_active=int(scale),
+                    optimize_ts=1, visual=1, visual_mult=visual_adds if dup else 1.0,
+                    imu_mult=(imu_adds if imu_adds > 0 else 1) if dup else 1.0)
+        o.set_options(function_tol=function_tol, max_iters=max_iters, strategy=strategy)
+        st = o.state()
+        if inertial and not rot_only and not grav_init:  # gravity from the mid-frame accelerometer sample (:927-949)
+            fr = p.n_frames // 2
+            i = np.searchsorted(p.imu_t, p.ftime[fr]) - 1
+            fq = (p.ftime[fr] - p.imu_t[i]) / (p.imu_t[i + 1] - p.imu_t[i])
+            a = p.imu_a[i] * (1 - fq) + p.imu_a[i + 1] * fq
+            gw = synth.quat_to_mat(st["T_wp"][fr, :4]) @ (a / np.linalg.norm(a))
+            pp = math.asin(gw[1])
+            o.set_imu_params([pp, math.asin(-gw[0] / math.cos(pp))], st["b"], st["sf"], st["ts"])
+            grav_init = True
+        while True:
+            s = o.solve()
+            n_solves += 1
+            assert n_solves < 60
+            if int(s["termination"]) != 0:  # converged: advance the stage machine (:976-1016)
+                if not inertial:
+                    inertial = True
+                elif rot_only:
+                    rot_only, bias = False, True
+                elif not scale:
+                    scale = True
+                else:
+                    finished = True
+                break
+    return o.state(), n_solves
+
+
+@pytest.mark.parametrize("dup,lm", [(True, True), (False, True), (True, False)])
+def test_staged_flow_matches_oracle_stage_machine(tmp_path, dup, lm):
+    """No initial guess + IMU: the C++ mirror's staged flow (visual -> rotation-only -> full + bias -> scale factors ->
+    finished, vicalibrator.h:976-1016) against the oracle driven through the same stages with the same residual-block
+    multiplicities: same number of solves, same calibration."""
     p = synth.make_problem(models=("poly3",), n_frames=24, inertial=True, seed=6)
-    out, _ = _run(tmp_path, p, has_guess=False, max_iters=40, dup=True)
-    assert out["solves"] >= 4
+    out, _ = _run(tmp_path, p, has_guess=False, max_iters=40, dup=dup, lm=lm)
+    st, n_solves = _staged_oracle(p, 40, dup, 0 if lm else 1)
+    assert out["solves"] == n_solves and out["solves"] >= 4
+    assert np.allclose(out["params0"], st["intr"][0, :7], rtol=1e-6)
+    assert np.allclose(out["T_ck0"], np.concatenate([st["q_ck"][0], st["p_ck"][0]]), atol=1e-7)
+    assert np.allclose(out["biases"], st["b"], atol=1e-7)
+    assert np.allclose(out["scale"], st["sf"], atol=1e-7)
+    assert abs(out["ts"] - st["ts"]) < 1e-8
     assert out["rmse0"] < 0.25
+    # GetIntegrationPoses (vicalibrator.h:508-533): start pose + one pose per IMU sample inside the first interval + the
+    # interpolated end; the integration ends at the second frame up to the IMU residual of the solution
+    n_ip, dp, t_end = out["integration_poses"]
+    assert n_ip >= 3 and 0 <= dp < 5e-3 and abs(t_end - p.ftime[1]) < 1e-12
+
+
+def test_clear_and_reuse(tmp_path):
+    """A calibrator that is Clear()ed and fed the same problem again must reproduce its first run (observations, IMU
+    samples, outlier mask and block multiplicities start from scratch; vicalibrator.h:232-249)."""
+    p = synth.make_problem(models=("poly3",), n_frames=16, inertial=True, seed=8)
+    a, _ = _run(tmp_path, p, has_guess=False, max_iters=30, dup=True)
+    b, _ = _run(tmp_path, p, has_guess=False, max_iters=30, dup=True, reuse=True)
+    assert a["solves"] * 2 == b["solves"] or a["solves"] == b["solves"]  # num_solves_ restarts in Clear()
+    assert np.allclose(a["params0"], b["params0"], rtol=1e-12) and np.allclose(a["biases"], b["biases"], atol=1e-14)
+    assert a["mse"] == b["mse"]
+
+
+def test_success_checks(tmp_path):
+    """VicalibTask::IsSuccessful (vicalib-task.cc:837-863): a good run passes without an initial guess; with
+    -has_initial_guess the reference's IMUCalibrationDiffer (comparison direction as written, :818-833) rejects a run
+    whose biases stayed within 0.1 of the input biases."""
+    p = synth.make_problem(models=("poly3", "fov"), n_frames=20, seed=9)
+    out, _ = _run(tmp_path, p, has_guess=False)
+    assert out["rmse0"] < 0.15 and out["rmse1"] < 0.15
+    assert out["success"][0] == 1 and out["success"][1] == 0
+    # a run whose reprojection error stays above max_reprojection_error (0.15 px) fails
+    q = synth.make_problem(models=("poly3",), n_frames=12, seed=10, pixel_sigma=0.4)
+    out, _ = _run(tmp_path, q, has_guess=False)
+    assert out["rmse0"] > 0.15 and out["success"][0] == 0

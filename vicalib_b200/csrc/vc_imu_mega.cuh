@@ -69,6 +69,12 @@ __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(kCsGroup) : "memory");
 }
 
+// (r, q) of linear index e = r * W + q, advanced by `step` without a division
+__device__ __forceinline__ void adv2(int& r, int& q, int W, int step) {
+  q += step;
+  while (q >= W) { q -= W; ++r; }
+}
+
 // where a level's node blocks come from: level 0 reads the block normal equations and applies the Jacobi scaling and
 // the LM damping on the fly (no separate pass, no copy); deeper levels read what the level above left
 struct NodeSrc {
@@ -97,9 +103,9 @@ __device__ __forceinline__ double src_U(const NodeSrc& s, int64_t p, int e) {  /
   return s.b.U[p * FD * FD + e] * s.scale[(p - 1) * FD + r] * s.scale[p * FD + c];
 }
 template <int FD>
-__device__ __forceinline__ double src_E(const NodeSrc& s, int64_t p, int e) {
+__device__ __forceinline__ double src_E(const NodeSrc& s, int64_t p, int r, int c) {
+  const int e = r * s.G + c;
   if (s.L) return s.L->E[p * FD * s.G + e] + (s.L->addE ? s.L->addE[p * FD * s.G + e] : 0.0);
-  const int r = e / s.G, c = e - r * s.G;
   return s.b.E[p * FD * s.G + e] * s.scale[p * FD + r] * s.scale[static_cast<int64_t>(s.nf) * FD + c];
 }
 template <int FD>
@@ -113,7 +119,7 @@ __device__ __forceinline__ double src_g(const NodeSrc& s, int64_t p, int e) {
 // round up front, the 9 x 9 pivots are factored right-looking with rsqrt, and the group's Schur accumulator Sacc
 // lives on across chunks and levels.
 template <int FD>
-__device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLevel& L, const ChainLevel& nxt, int G, int j, double* sm,
+__device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLevel L, const ChainLevel nxt, int G, int j, double* sm,
                                              int tid, int grp, int* bad) {
   constexpr int c = kCsChunk, NT = kCsGroup;
   const int NS = G * G + G;
@@ -138,7 +144,10 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
   group_sync(grp);  // the previous chunk of this group is done with the workspace
   // ---- one round of global loads: separator, pivots, couplings, right-hand sides
   for (int e = tid; e < FD * FD; e += NT) Al[e] = src_A<FD>(src, s, e);
-  for (int e = tid; e < FD * G; e += NT) El[e] = src_E<FD>(src, s, e);
+  const int rG0 = tid / G, qG0 = tid - rG0 * G;      // (row, column) of element tid of an FD x G block
+  const int rw0 = tid / w, qw0 = tid - rw0 * w;      // ... of an FD x w block
+  const int rV0 = tid / VW, qV0 = tid - rV0 * VW;    // ... of an FD x VW block
+  for (int e = tid, r = rG0, q = qG0; e < FD * G; e += NT, adv2(r, q, G, NT)) El[e] = src_E<FD>(src, s, r, q);
   for (int e = tid; e < FD; e += NT) gl[e] = src_g<FD>(src, s, e);
   if (hasR)
     for (int e = tid; e < FD * FD; e += NT) Ur[e] = src_U<FD>(src, rIdx, e);
@@ -157,9 +166,8 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       Vi[r * VW + q] = lastI ? 0.0 : unext;
       Vi[r * VW + oR + q] = (lastI && hasR) ? unext : 0.0;
     }
-    for (int e = tid; e < FD * G; e += NT) {
-      const int r = e / G, q = e - r * G;
-      const double v = src_E<FD>(src, p, e);
+    for (int e = tid, r = rG0, q = qG0; e < FD * G; e += NT, adv2(r, q, G, NT)) {
+      const double v = src_E<FD>(src, p, r, q);
       Vi[r * VW + oE + q] = v;
       Eo[i * FD * G + e] = v;
     }
@@ -174,8 +182,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       const double* Vp = V + static_cast<int64_t>(i - 1) * FD * VW;
       const double* Uci = Uc + i * FD * FD;
       // A'_i = A_i - U^T V_U(i-1);  R'_i = R_i - U^T V_R(i-1)
-      for (int e = tid; e < FD * VW; e += NT) {
-        const int r = e / VW, q = e - r * VW;
+      for (int e = tid, r = rV0, q = qV0; e < FD * VW; e += NT, adv2(r, q, VW, NT)) {
         double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < FD; ++k) sum += Uci[k * FD + r] * Vp[k * VW + q];
@@ -232,8 +239,8 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
   for (int i = m - 2; i >= 0; --i) {
     double* Vi = V + static_cast<int64_t>(i) * FD * VW;
     const double* Vn = V + static_cast<int64_t>(i + 1) * FD * VW;
-    for (int e = tid; e < FD * w; e += NT) {
-      const int r = e / w, q = FD + (e - r * w);
+    for (int e = tid, r = rw0, qq = qw0; e < FD * w; e += NT, adv2(r, qq, w, NT)) {
+      const int q = FD + qq;
       double sum = 0.0;
 #pragma unroll
       for (int k = 0; k < FD; ++k) sum += Vi[r * VW + k] * Vn[k * VW + q];
@@ -245,29 +252,39 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
   for (int i = 0; i < m; ++i) {
     const int64_t p = s + 1 + i;
     const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
-    for (int e = tid; e < FD * w; e += NT) {
-      const int r = e / w, q = e - r * w;
-      L.Z[(p * FD + r) * w + q] = Vi[r * VW + FD + q];
-    }
+    for (int e = tid, r = rw0, q = qw0; e < FD * w; e += NT, adv2(r, q, w, NT)) L.Z[p * FD * w + e] = Vi[r * VW + FD + q];
   }
-  for (int e = tid; e < NS; e += NT) {
-    const int ra = e < G * G ? e / G : e - G * G;
-    const int cb = e < G * G ? oE + (e - ra * G) : og;
-    double sum = 0.0;
-    for (int i = 0; i < m; ++i) {
-      const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
-      const double* Ei = Eo + i * FD * G;
+  {  // lower triangle of S (row ra has ra + 1 entries), then the right-hand side
+    int ra = 0, cb = tid;
+    while (cb > ra) { cb -= ra + 1; ++ra; }
+    for (; ra < G; ) {
+      double sum = 0.0;
+      for (int i = 0; i < m; ++i) {
+        const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+        const double* Ei = Eo + i * FD * G;
 #pragma unroll
-      for (int k = 0; k < FD; ++k) sum += Ei[k * G + ra] * Vi[k * VW + cb];
+        for (int k = 0; k < FD; ++k) sum += Ei[k * G + ra] * Vi[k * VW + oE + cb];
+      }
+      Sacc[ra * G + cb] += sum;
+      cb += NT;
+      while (cb > ra) { cb -= ra + 1; ++ra; }
     }
-    Sacc[e] += sum;
+    for (int r = tid; r < G; r += NT) {
+      double sum = 0.0;
+      for (int i = 0; i < m; ++i) {
+        const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+        const double* Ei = Eo + i * FD * G;
+#pragma unroll
+        for (int k = 0; k < FD; ++k) sum += Ei[k * G + r] * Vi[k * VW + og];
+      }
+      Sacc[G * G + r] += sum;
+    }
   }
   if (m > 0) {
     const double* X0 = V;                                          // node s+1
     const double* Xl = V + static_cast<int64_t>(m - 1) * FD * VW;  // last interior node
     const double* U0 = Uc;                                         // H[s, s+1]
-    for (int e = tid; e < FD * w; e += NT) {
-      const int r = e / w, q = e - r * w;  // q indexes [L | R | E | g]
+    for (int e = tid, r = rw0, q = qw0; e < FD * w; e += NT, adv2(r, q, w, NT)) {  // q indexes [L | R | E | g]
       double sl = 0.0, sr = 0.0;
 #pragma unroll
       for (int k = 0; k < FD; ++k) {
@@ -300,7 +317,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
   }
   if (toGhost) {  // carry the ghost node itself to the next level (its Schur updates went to nxt.add*)
     for (int e = tid; e < FD * FD; e += NT) nxt.A[static_cast<int64_t>(jr) * FD * FD + e] = src_A<FD>(src, rIdx, e);
-    for (int e = tid; e < FD * G; e += NT) nxt.E[static_cast<int64_t>(jr) * FD * G + e] = src_E<FD>(src, rIdx, e);
+    for (int e = tid, r = rG0, q = qG0; e < FD * G; e += NT, adv2(r, q, G, NT)) nxt.E[static_cast<int64_t>(jr) * FD * G + e] = src_E<FD>(src, rIdx, r, q);
     for (int e = tid; e < FD; e += NT) nxt.g[static_cast<int64_t>(jr) * FD + e] = src_g<FD>(src, rIdx, e);
     if (tid == 0) nxt.orig[jr] = src.L ? L.orig[rIdx] : rIdx;
   }
@@ -417,7 +434,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
           L.A[static_cast<int64_t>(f) * FD * FD + e] = src_A<FD>(src, f, e);
           L.U[static_cast<int64_t>(f) * FD * FD + e] = src_U<FD>(src, f, e);
         }
-        for (int e = tid; e < FD * G; e += kCsThreads) L.E[static_cast<int64_t>(f) * FD * G + e] = src_E<FD>(src, f, e);
+        for (int e = tid; e < FD * G; e += kCsThreads) L.E[static_cast<int64_t>(f) * FD * G + e] = src_E<FD>(src, f, e / G, e % G);
         for (int e = tid; e < FD; e += kCsThreads) L.g[static_cast<int64_t>(f) * FD + e] = src_g<FD>(src, f, e);
         if (tid == 0) L.orig[f] = f;
       }

@@ -249,14 +249,21 @@ struct VicalibFrame {  // vicalibrator.h:76-97 (ImuPoseT fields the call sites r
 
 struct ImuMeasurement { Vector3d w_, a_; double time; };
 
+struct ImuPose {  // ImuPoseT<double> (types.h:170-205): what GetIntegrationPoses hands to the GUI
+  SE3d t_wp_;
+  Vector3d v_w_{{0, 0, 0}}, w_w_{{0, 0, 0}};
+  double time_ = 0;
+};
+
 // Flags the reference reads from gflags (vicalibrator.h:56-60; defaults vicalib-engine.cc:94, :30-104)
 struct CalibratorFlags {
   bool calibrate_imu = true;
   int max_iters = 200;
-  bool remove_outliers = true;
-  double outlier_threshold = 2.0;
-  // 0 = LEVENBERG_MARQUARDT (device default), 1 = DOGLEG, the reference's solver_options_ (vicalibrator.h:151)
-  int trust_region_strategy = 0;
+  bool remove_outliers = false;    // DEFINE_bool(remove_outliers, false, ...) vicalib-engine.cc:100
+  double outlier_threshold = 2.0;  // vicalib-engine.cc:102
+  // 1 = DOGLEG, the reference's solver_options_ (vicalibrator.h:151); 0 = LEVENBERG_MARQUARDT (what north_star
+  // benchmarks; the only strategy of frame-sharded multi-GPU solves)
+  int trust_region_strategy = 1;
 };
 
 class ViCalibrator {
@@ -334,6 +341,12 @@ class ViCalibrator {
     is_gravity_initialized_ = false;
     outliers_removed_ = false;
     num_solves_ = 0;
+    // the device still holds the previous problem: the next SetupProblem must upload observations / IMU samples again
+    // and restart the residual-block multiplicities (the reference resets num_imu_residuals_ and proj_costs_, :236-241)
+    problem_uploaded_ = false;
+    visual_adds_ = imu_adds_ = 0;
+    n_removed_ = 0;
+    stopped_by_user_ = false;
     g_[0] = g_[1] = 0;
     time_offset_ = 0;
     for (int i = 0; i < 6; ++i) { biases_[i] = 0; scale_factors_[i] = 1; }
@@ -351,6 +364,7 @@ class ViCalibrator {
   void Start() {  // :263-274
     if (!is_running_) {
       should_run_ = true;
+      stopped_by_user_ = false;
       is_running_ = true;
       pthread_create(&thread_, NULL, &ViCalibrator::SolveThreadStatic, this);
       thread_valid_ = true;
@@ -422,6 +436,32 @@ class ViCalibrator {
   const double* gravity_angles() const { return g_; }
   int num_solves() const { return num_solves_; }
   int64_t num_outliers_removed() const { return n_removed_; }
+
+  // The poses the IMU integration passes through between frame `id` and frame `id + 1` with the current
+  // biases / scale factors / gravity / time offset (vicalibrator.h:508-533; ImuResidualT::IntegrateResidual,
+  // types.h:611-687, double branch of IntegrateImu :575-590).  Host-side: the GUI polls it while drawing.
+  std::vector<ImuPose> GetIntegrationPoses(unsigned int id) {
+    std::vector<ImuPose> poses;
+    if (!(is_inertial_active_ && !optimize_rotation_only_)) return poses;
+    if (static_cast<size_t>(id) + 1 >= t_wk_.size()) return poses;  // the reference reads t_wk_[id + 1] unchecked (:517)
+    const VicalibFrame& f0 = *t_wk_[id];
+    const VicalibFrame& f1 = *t_wk_[id + 1];
+    std::vector<ImuMeasurement> meas;
+    GetRange(f0.time_, f1.time_, time_offset_, &meas);
+    if (meas.empty()) return poses;
+    const double sp = std::sin(g_[0]), cp = std::cos(g_[0]), sq = std::sin(g_[1]), cq = std::cos(g_[1]);
+    const double gv[3] = {-9.8007 * cp * sq, 9.8007 * sp, -9.8007 * cp * cq};  // GetGravityVector, types.h:93-104
+    ImuPose y;
+    y.t_wp_ = f0.t_wp_;
+    y.v_w_ = f0.v_w_;
+    y.time_ = f0.time_;
+    poses.push_back(y);
+    for (size_t i = 1; i < meas.size(); ++i) {
+      y = IntegrateImu(y, meas[i - 1], meas[i], gv);
+      poses.push_back(y);
+    }
+    return poses;
+  }
 
   void PrintResults() {  // :536-544
     std::printf("------------------------------------------\n");
@@ -523,6 +563,7 @@ class ViCalibrator {
     ViCalibrator* self = static_cast<ViCalibrator*>(user);
     ++self->num_iterations_;
     if (self->num_residuals_ > 0) self->mse_ = it->cost / self->num_residuals_;
+    if (!self->should_run_) self->stopped_by_user_ = true;  // Stop(): abort the solve (the reference lets Ceres finish)
     return self->should_run_ ? 0 : 1;  // UpdateImuWeights and the gradient-norm rule run on the device
   }
 
@@ -566,6 +607,9 @@ class ViCalibrator {
             camera_proj_rmse_[c] = n > 0 ? std::sqrt(cost / n) : 0.0;
           }
           mse_ = summary.num_residuals > 0 ? summary.final_cost / summary.num_residuals : 0.0;  // :975
+          // a solve cut short by Stop() must not advance the stage machine (it did not converge; the reference's
+          // Stop() never interrupts ceres::Solve)
+          if (stopped_by_user_) break;
           const bool converged = summary.termination != VCGPU_TERM_NO_CONVERGENCE;
           if (converged && FLAGS_.calibrate_imu) {  // :976-1022
             if (!is_inertial_active_) {
@@ -600,16 +644,99 @@ class ViCalibrator {
     is_running_ = false;
   }
 
+  // InterpolationBufferT::GetRange (interpolation-buffer.h:208-226): [element(start), samples inside, element(end)],
+  // sample i valid at time_i + offset
+  void GetRange(double t0, double t1, double off, std::vector<ImuMeasurement>* out) const {
+    if (imu_.empty() || !(t0 >= imu_.front().time + off && t0 <= imu_.back().time + off)) return;
+    auto element = [&](double t, size_t* idx) {
+      ImuMeasurement m;
+      if (imu_.front().time + off > t) { m = imu_.front(); m.time += off; *idx = 0; return m; }
+      size_t i = 0;
+      while (i + 1 < imu_.size() && imu_[i + 1].time + off < t) ++i;
+      if (i + 1 >= imu_.size()) { m = imu_.back(); m.time += off; *idx = imu_.size() - 1; return m; }
+      const double ta = imu_[i].time + off, tb = imu_[i + 1].time + off, f = (t - ta) / (tb - ta);
+      for (int k = 0; k < 3; ++k) {
+        m.w_[k] = imu_[i].w_[k] * (1 - f) + imu_[i + 1].w_[k] * f;
+        m.a_[k] = imu_[i].a_[k] * (1 - f) + imu_[i + 1].a_[k] * f;
+      }
+      m.time = t;
+      *idx = i;
+      return m;
+    };
+    size_t idx = 0;
+    out->push_back(element(t0, &idx));
+    while (idx + 1 < imu_.size() && !(imu_[idx + 1].time + off > t1)) {
+      ImuMeasurement m = imu_[++idx];
+      m.time += off;
+      out->push_back(m);
+    }
+    out->push_back(element(t1, &idx));
+  }
+  // GetPoseDerivative (types.h:380-425, value only)
+  void PoseDerivative(const ImuPose& y, const ImuMeasurement& z0, const ImuMeasurement& z1, double dt, const double gv[3],
+                      double k[9]) const {
+    const double alpha = (z1.time - (z0.time + dt)) / (z1.time - z0.time);
+    double R[9], w[3], a[3];
+    y.t_wp_.rotation(R);
+    for (int i = 0; i < 3; ++i) {
+      w[i] = (z0.w_[i] * alpha + z1.w_[i] * (1.0 - alpha)) * scale_factors_[i] + biases_[i];
+      a[i] = (z0.a_[i] * alpha + z1.a_[i] * (1.0 - alpha)) * scale_factors_[3 + i] + biases_[3 + i];
+    }
+    for (int i = 0; i < 3; ++i) {
+      k[i] = y.v_w_[i];
+      k[3 + i] = R[i * 3] * w[0] + R[i * 3 + 1] * w[1] + R[i * 3 + 2] * w[2];
+      k[6 + i] = R[i * 3] * a[0] + R[i * 3 + 1] * a[1] + R[i * 3 + 2] * a[2] - gv[i];
+    }
+  }
+  // IntegratePose (types.h:330-378, value only): p += k_v dt, q <- exp(k_w dt) * q (no renormalisation), v += k_a dt
+  static ImuPose IntegratePose(const ImuPose& y0, const double k[9], double dt) {
+    ImuPose y = y0;
+    const double wx = k[3] * dt, wy = k[4] * dt, wz = k[5] * dt, th2 = wx * wx + wy * wy + wz * wz, th = std::sqrt(th2);
+    double imag, real;
+    if (th < 1e-10) { imag = 0.5 - th2 / 48.0; real = 1.0 - th2 / 8.0; }
+    else { imag = std::sin(0.5 * th) / th; real = std::cos(0.5 * th); }
+    const double e[4] = {imag * wx, imag * wy, imag * wz, real};
+    const double* q = y0.t_wp_.d;
+    y.t_wp_.d[0] = e[3] * q[0] + e[0] * q[3] + e[1] * q[2] - e[2] * q[1];
+    y.t_wp_.d[1] = e[3] * q[1] + e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
+    y.t_wp_.d[2] = e[3] * q[2] + e[2] * q[3] + e[0] * q[1] - e[1] * q[0];
+    y.t_wp_.d[3] = e[3] * q[3] - e[0] * q[0] - e[1] * q[1] - e[2] * q[2];
+    for (int i = 0; i < 3; ++i) {
+      y.t_wp_.d[4 + i] += k[i] * dt;
+      y.v_w_[i] += k[6 + i] * dt;
+    }
+    return y;
+  }
+  // IntegrateImu, RK4 (types.h:575-594)
+  ImuPose IntegrateImu(const ImuPose& y0, const ImuMeasurement& z0, const ImuMeasurement& z1, const double gv[3]) const {
+    const double dt = z1.time - z0.time;
+    if (dt == 0) return y0;
+    double k1[9], k2[9], k3[9], k4[9], k[9];
+    PoseDerivative(y0, z0, z1, 0.0, gv, k1);
+    PoseDerivative(IntegratePose(y0, k1, dt * 0.5), z0, z1, dt / 2, gv, k2);
+    PoseDerivative(IntegratePose(y0, k2, dt * 0.5), z0, z1, dt / 2, gv, k3);
+    PoseDerivative(IntegratePose(y0, k3, dt), z0, z1, dt, gv, k4);
+    for (int i = 0; i < 9; ++i) k[i] = k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i];
+    ImuPose res = IntegratePose(y0, k, dt / 6.0);
+    for (int i = 0; i < 3; ++i) res.w_w_[i] = k[3 + i];
+    res.time_ = z1.time;
+    return res;
+  }
+
   void RemoveOutliers() {  // :859-916
     int64_t n = 0;
     Check(vcgpu_remove_outliers(h_, camera_proj_rmse_.data(), FLAGS_.outlier_threshold, &n), "remove_outliers");
     n_removed_ += n;
   }
 
-  Vector3d InterpolateAccel(double time) const {  // InterpolationBufferT::GetElement(time) with zero offset
+  // InterpolationBufferT::GetElement(time) with zero offset (interpolation-buffer.h:160-203): the first / last
+  // element outside the buffer's time span, linear interpolation between the two neighbours inside it
+  Vector3d InterpolateAccel(double time) const {
+    if (imu_.empty()) return Vector3d{{0, 0, 0}};
+    if (!(imu_.front().time < time)) return imu_.front().a_;
+    if (!(time < imu_.back().time)) return imu_.back().a_;
     size_t i = 0;
-    while (i + 1 < imu_.size() && imu_[i + 1].time < time) ++i;
-    if (i + 1 >= imu_.size()) return imu_.back().a_;
+    while (i + 2 < imu_.size() && imu_[i + 1].time < time) ++i;
     const double f = (time - imu_[i].time) / (imu_[i + 1].time - imu_[i].time);
     Vector3d a;
     for (int k = 0; k < 3; ++k) a[k] = imu_[i].a_[k] * (1 - f) + imu_[i + 1].a_[k] * f;
@@ -629,7 +756,7 @@ class ViCalibrator {
   pthread_mutex_t update_mutex_ = PTHREAD_MUTEX_INITIALIZER;
   pthread_t thread_;
   bool thread_valid_ = false;
-  volatile bool should_run_ = false, is_running_ = false;
+  volatile bool should_run_ = false, is_running_ = false, stopped_by_user_ = false;
   bool fix_intrinsics_ = false, problem_uploaded_ = false, emulate_block_duplication_ = true;
   int visual_adds_ = 0, imu_adds_ = 0;
   std::vector<std::shared_ptr<VicalibFrame> > t_wk_;
