@@ -160,6 +160,24 @@ int vcgpu_num_residuals(vcgpu_handle* h, int* out);
 int vcgpu_frame_dim(vcgpu_handle* h, int* out);   /* 6, or 9 with inertial terms */
 int vcgpu_num_globals(vcgpu_handle* h, int* out); /* sum_c (6 + K_c) (+15 with inertial terms) */
 
+/* Batched pose initialisation — replaces the per-frame, per-camera `PosePnPRansac(camera, ellipses, target.Circles3D(),
+ * ellipse_target_map, 0, 0, &t_cw)` of VicalibTask (src/vicalib-task.cc:322-325; Calibu + OpenCV solvePnP, un-vendored).
+ * View v uses camera cam_id[v] (model / intrinsics from vcgpu_set_cameras) and the correspondences
+ * [start[v], start[v] + count[v]) of pix (pixels) / pw (target points on the z = 0 plane, vicalib-task.cc:357-358).
+ * robust_its > 0: RANSAC over 4-point homographies with inlier tolerance robust_tol (normalised image coordinates);
+ * the reference calls it with 0, 0.  Out: T_cw[v] = (qx qy qz qw tx ty tz), p_c = R p_w + t; rmse[v] in normalised
+ * coordinates; n_used[v] = points in the final fit (0: fewer than 4 usable points, T_cw[v] = identity).
+ * The frame pose the solve is seeded with is T_wp = T_cw^-1 * T_ck (vicalib-task.cc:341-349). */
+int vcgpu_pose_pnp_ransac(vcgpu_handle* h, int n_views, const int32_t* cam_id, const int64_t* start, const int32_t* count,
+                          const double* pix, const double* pw, int robust_its, double robust_tol, double* T_cw /*n_views*7*/,
+                          double* rmse_or_null, int32_t* n_used_or_null);
+
+/* GetSolutionCovariance (vicalibrator.h:802-857; compiled out upstream behind COMPUTE_VICALIB_COVARIANCE): the
+ * [globals, globals] block of (J^T J)^-1 at the current state, tangent space, G x G row-major with G = vcgpu_num_globals:
+ * per camera (w_ck 3 | p_ck 3 | intrinsics K), then with inertial terms (g 2 | b 6 | sf 6 | ts 1).  Rows / columns of
+ * constant parameter blocks are zero (ceres::Covariance convention). */
+int vcgpu_get_covariance(vcgpu_handle* h, double* cov);
+
 /* ---- inspection hooks used by the parity tests (what AutoDiffCostFunction::Evaluate and the
  * normal-equation build produce inside Ceres) ------------------------------------------------ */
 /* loss-free residuals and tangent-space Jacobians per observation, caller order.

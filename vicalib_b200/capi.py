@@ -24,7 +24,7 @@ EXPORTS = [
     "vcgpu_get_obs_active", "vcgpu_update_imu_weights", "vcgpu_get_imu_weights", "vcgpu_set_imu_weights",
     "vcgpu_get_state", "vcgpu_num_residuals", "vcgpu_frame_dim", "vcgpu_num_globals", "vcgpu_eval_reproj",
     "vcgpu_eval_imu", "vcgpu_normal_equations", "vcgpu_solve_arrow", "vcgpu_comm_unique_id", "vcgpu_comm_init",
-    "vcgpu_set_profiling", "vcgpu_get_stage_times", "vcgpu_fp64_peak", "vcgpu_get_phase_clocks",
+    "vcgpu_set_profiling", "vcgpu_get_stage_times", "vcgpu_fp64_peak", "vcgpu_get_phase_clocks", "vcgpu_get_covariance", "vcgpu_pose_pnp_ransac",
 ]
 
 
@@ -288,6 +288,24 @@ class Calibrator:
         n = np.zeros(16, dtype=np.int64)
         self._chk(self.L.vcgpu_get_stage_times(self.h, _p(ms), _p(n)))
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.STAGES)}
+
+    def pose_pnp_ransac(self, cam_id, start, count, pix, pw, robust_its=0, robust_tol=0.0):
+        """batched PosePnPRansac: one (camera, correspondence range) per view -> (T_cw [n, 7], rmse [n], n_used [n])"""
+        n = len(cam_id)
+        T = np.zeros((n, 7))
+        rmse = np.zeros(n)
+        used = np.zeros(n, dtype=np.int32)
+        self._chk(self.L.vcgpu_pose_pnp_ransac(self.h, C.c_int(n), _p(_c(cam_id, np.int32)), _p(_c(start, np.int64)),
+                                               _p(_c(count, np.int32)), _p(_c(pix)), _p(_c(pw)), C.c_int(robust_its),
+                                               C.c_double(robust_tol), _p(T), _p(rmse), _p(used)))
+        return T, rmse, used
+
+    def covariance(self):
+        """GetSolutionCovariance: tangent covariance of the globals, G x G"""
+        G = self.G
+        cov = np.zeros((G, G))
+        self._chk(self.L.vcgpu_get_covariance(self.h, _p(cov)))
+        return cov
 
     def phase_clocks(self):
         """raw phase clocks (ns) of the persistent inertial kernels, see vcgpu_get_phase_clocks"""

@@ -48,10 +48,30 @@ __device__ __forceinline__ void se3_local_column(const double* x, int col, doubl
   }
 }
 
+// the same fields as ImuEvalArgs / ImuAccArgs with the problem description by reference
+struct ImuEvalView {
+  const DevProblem& dp;
+  imu::ImuBuf buf;
+  const double* ftime;
+  const double* wsqrt;
+  const double* mask;
+  double *r, *J, *cost;
+  int ni, apply_loss;
+  double mult;
+};
+struct ImuAccView {
+  const DevProblem& dp;
+  const double *r, *J;
+  double* Cg;
+  int ni;
+};
+
 constexpr int kImuWarps = 4;
 
 // residual (9) and tangent Jacobian (9 x 33) of interval k by one warp: lane -> Jacobian column
-__device__ __forceinline__ void imu_eval_interval(const ImuEvalArgs& a, int k, int lane, const double* state) {
+// A: ImuEvalArgs or a view with the same fields (the persistent kernel binds `dp` by reference to its own parameter)
+template <class A>
+__device__ __forceinline__ void imu_eval_interval(const A& a, int k, int lane, const double* state) {
   using imu::D1;
   // lane -> Jacobian column: pose2 0-5 | pose1 6-11 | (v2 12-14 analytic) | v1 15-17 | g 18-19 | b 20-25 | sf 26-31 | ts 32
   const int col = lane < 12 ? lane : lane + 3;
@@ -163,42 +183,67 @@ __device__ __forceinline__ int imu_local_col(int c) {
 }
 // frame f by a group of NT threads: interval f-1 (f is its second frame) and interval f (f is its first frame).
 // Jl: the group's [2][9][34] staging area ([which][row][local col 0..32, 33 = residual]); SYNC: the group's barrier
-template <int NT, class SYNC>
-__device__ __forceinline__ void imu_accumulate_frame(const ImuAccArgs& a, const Blocks& out, int f, int tid, double (*Jl)[9][34],
+template <int NT, class A, class SYNC>
+__device__ __forceinline__ void imu_accumulate_frame(const A& a, const Blocks& out, int f, int tid, double (*Jl)[9][34],
                                                      SYNC sync) {
   const int G = a.dp.G, nf = a.dp.n_frames, io = a.dp.imu_goff;
   const bool hasP = f > 0, hasN = f < nf - 1;
-  for (int e = tid; e < 2 * 9 * 34; e += NT) {
-    const int which = e / (9 * 34), row = (e / 34) % 9, c = e % 34;
-    const int k = which == 0 ? f - 1 : f;
-    double v = 0.0;
-    if (k >= 0 && k < a.ni) v = c < 33 ? a.J[static_cast<int64_t>(k) * 297 + row * 33 + imu_local_col(c)] : a.r[static_cast<int64_t>(k) * 9 + row];
-    Jl[which][row][c] = v;
-  }
-  sync();
-  const double m = a.dp.imu_mult;
   double* Bf = out.B + static_cast<int64_t>(f) * 81;
   double* Uf = out.U + static_cast<int64_t>(f) * 81;
   double* Ef = out.E + static_cast<int64_t>(f) * 9 * G;
   double* gf = out.gf + static_cast<int64_t>(f) * 9;
+  constexpr int kIn = 2 * 9 * 34, kOut = 81 + 81 + 135 + 9 + 135;
+  constexpr int kItIn = (kIn + NT - 1) / NT, kItOut = (kOut + NT - 1) / NT;
+  // every global load first (the two intervals' Jacobians and the entries the reprojection build left in B and the
+  // gradient), then the arithmetic: a load-use loop would pay one memory round trip per iteration
+  double vin[kItIn], old[kItOut];
+#pragma unroll
+  for (int it = 0; it < kItIn; ++it) {
+    const int e = tid + it * NT;
+    const int which = e / (9 * 34), row = (e / 34) % 9, c = e % 34;
+    const int k = which == 0 ? f - 1 : f;
+    vin[it] = 0.0;
+    if (e < kIn && k >= 0 && k < a.ni)
+      vin[it] = c < 33 ? a.J[static_cast<int64_t>(k) * 297 + row * 33 + imu_local_col(c)] : a.r[static_cast<int64_t>(k) * 9 + row];
+  }
+#pragma unroll
+  for (int it = 0; it < kItOut; ++it) {
+    const int e = tid + it * NT;
+    old[it] = e < 81 ? Bf[e] : (e >= 297 && e < 306) ? gf[e - 297] : 0.0;
+  }
+#pragma unroll
+  for (int it = 0; it < kItIn; ++it) {
+    const int e = tid + it * NT;
+    if (e < kIn) Jl[e / (9 * 34)][(e / 34) % 9][e % 34] = vin[it];
+  }
+  sync();
+  const double m = a.dp.imu_mult;
   // B (81) | U (81) | E imu columns (9*15) | g (9) | Cg of interval f (120 + 15)
-  for (int e = tid; e < 81 + 81 + 135 + 9 + 135; e += NT) {
+#pragma unroll
+  for (int it = 0; it < kItOut; ++it) {
+    const int e = tid + it * NT;
+    if (e >= kOut) break;
     if (e < 81) {
       const int i = e / 9, j = e % 9;
       double s = 0.0;
+#pragma unroll
       for (int row = 0; row < 9; ++row) {
         if (hasP) s += Jl[0][row][9 + i] * Jl[0][row][9 + j];
         if (hasN) s += Jl[1][row][i] * Jl[1][row][j];
       }
-      Bf[e] += s * m;
+      Bf[e] = old[it] + s * m;
     } else if (e < 162) {
       const int i = (e - 81) / 9, j = (e - 81) % 9;  // U[f] = H[f-1, f] = J1(f-1)^T J2(f-1)
       double s = 0.0;
-      if (hasP) for (int row = 0; row < 9; ++row) s += Jl[0][row][i] * Jl[0][row][9 + j];
+      if (hasP) {
+#pragma unroll
+        for (int row = 0; row < 9; ++row) s += Jl[0][row][i] * Jl[0][row][9 + j];
+      }
       Uf[e - 81] = s * m;
     } else if (e < 297) {
       const int i = (e - 162) / 15, j = (e - 162) % 15;
       double s = 0.0;
+#pragma unroll
       for (int row = 0; row < 9; ++row) {
         if (hasP) s += Jl[0][row][9 + i] * Jl[0][row][18 + j];
         if (hasN) s += Jl[1][row][i] * Jl[1][row][18 + j];
@@ -207,21 +252,23 @@ __device__ __forceinline__ void imu_accumulate_frame(const ImuAccArgs& a, const 
     } else if (e < 306) {
       const int i = e - 297;
       double s = 0.0;
+#pragma unroll
       for (int row = 0; row < 9; ++row) {
         if (hasP) s += Jl[0][row][9 + i] * Jl[0][row][33];
         if (hasN) s += Jl[1][row][i] * Jl[1][row][33];
       }
-      gf[i] += s * m;
+      gf[i] = old[it] + s * m;
     } else if (hasN) {
       const int q = e - 306;  // packed lower triangle of the 15x15 global block, then gradient
       double s = 0.0;
       if (q < 120) {
-        int i = static_cast<int>((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+        int i = 0;
         while ((i + 1) * (i + 2) / 2 <= q) ++i;
-        while (i * (i + 1) / 2 > q) --i;
         const int j = q - i * (i + 1) / 2;
+#pragma unroll
         for (int row = 0; row < 9; ++row) s += Jl[1][row][18 + i] * Jl[1][row][18 + j];
       } else {
+#pragma unroll
         for (int row = 0; row < 9; ++row) s += Jl[1][row][18 + (q - 120)] * Jl[1][row][33];
       }
       a.Cg[static_cast<int64_t>(f) * kImuCgStride + q] = s * m;

@@ -257,11 +257,7 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
 
   // ------------------------------------------------------------ T: task queue — IMU intervals first, then frames
   {
-    ImuEvalArgs ia;
-    ia.dp = a.dp; ia.buf = a.buf; ia.ctl = a.ctl; ia.which = a.which;
-    ia.states[0] = a.state[0]; ia.states[1] = a.state[1];
-    ia.ftime = a.ftime; ia.wsqrt = a.wsqrt; ia.mask = a.mask + a.dp.imu_goff;
-    ia.r = a.imu_r; ia.J = a.imu_J; ia.cost = a.imu_cost; ia.ni = ni; ia.apply_loss = 1; ia.mult = a.dp.imu_mult;
+    const ImuEvalView ia{a.dp, a.buf, a.ftime, a.wsqrt, a.mask + a.dp.imu_goff, a.imu_r, a.imu_J, a.imu_cost, ni, 1, a.dp.imu_mult};
     double* slab = smem + static_cast<size_t>(warp) * kWarpDoubles;
     const unsigned n_tasks = static_cast<unsigned>(ni + nf);
     for (;;) {
@@ -277,9 +273,7 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
   grid.sync();
   // ------------------------------------------------------------ A: IMU blocks of every frame
   {
-    ImuAccArgs aa;
-    aa.dp = a.dp; aa.ctl = a.ctl; aa.which = a.which; aa.r = a.imu_r; aa.J = a.imu_J;
-    aa.outs[0] = a.blk[0]; aa.outs[1] = a.blk[1]; aa.Cg = a.imuCg; aa.ni = ni;
+    const ImuAccView aa{a.dp, a.imu_r, a.imu_J, a.imuCg, ni};
     double (*Jl)[9][34] = reinterpret_cast<double (*)[9][34]>(smem + static_cast<size_t>(warp) * 2 * 9 * 34);
     for (int f = bid * kEvWarps + warp; f < nf; f += nb * kEvWarps) {
       __syncwarp();  // the warp's previous frame is done with the staging area
@@ -290,7 +284,7 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
   grid.sync();
   // ------------------------------------------------------------ R1: slice partials
   RedFinArgs ra;
-  ra.dp = a.dp; ra.ctl = a.ctl; ra.which = a.which; ra.decide_mode = a.decide_mode; ra.multi = 0; ra.level1_only = 1;
+  ra.ctl = a.ctl; ra.which = a.which; ra.decide_mode = a.decide_mode; ra.multi = 0; ra.level1_only = 1;
   ra.gf_skip_below = 0; ra.gf_skip_from = static_cast<int64_t>(nf) * a.dp.fd;
   ra.Cg = a.Cg; ra.imuCg = a.imuCg; ra.ni = ni; ra.imu_goff = a.dp.imu_goff; ra.imu_stride = kImuCgStride;
   ra.Cpart = a.Cpart; ra.red_part = a.red_part;
@@ -298,7 +292,7 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
   ra.imu_cost_part = a.imu_cost; ra.n_imu_cost_part = ni;
   ra.step_part = a.step_part; ra.n_step_part = a.n_step_part; ra.n_frames_fd = nf * a.dp.fd;
   ra.out[0] = a.blk[0]; ra.out[1] = a.blk[1]; ra.scalars = a.scalars; ra.counter = nullptr;
-  reduce_level1(ra, bt, smem, shr, bid, nb);
+  reduce_level1(ra, a.dp, bt, smem, shr, bid, nb);
   grid.sync();
   // ------------------------------------------------------------ R2: C | gc totals (contiguous in Blocks)
   mega_reduce_stage1(a.Cpart, NS, nb, NS, bt.C, -1, -1);
@@ -354,9 +348,7 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
   {
     const volatile Ctl* c = a.ctl;
     if (c->done || !(c->iter == 0 || c->last_accepted)) return;  // uniform: written before the barrier
-    wts::WeightArgs wa;
-    wa.dp = a.dp; wa.buf = a.buf; wa.ctl = a.ctl; wa.states[0] = a.state[0]; wa.states[1] = a.state[1];
-    wa.ftime = a.ftime; wa.wsqrt = a.wsqrt; wa.ni = ni; wa.sigma_g = a.sigma_g; wa.sigma_a = a.sigma_a;
+    const wts::WeightView wa{a.dp, a.buf, a.ftime, a.wsqrt, ni, a.sigma_g, a.sigma_a};
     const double* xs = a.state[c->cur];
     constexpr int kTeams = kEvThreads / wts::kTeam;
     wts::Work* work = reinterpret_cast<wts::Work*>(smem);

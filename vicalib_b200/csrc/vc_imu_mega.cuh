@@ -118,7 +118,8 @@ __device__ __forceinline__ double src_g(const NodeSrc& s, int64_t p, int e) {
 // Same algorithm as chain_eliminate_kernel (vc_chain.cuh); here every global load of the chunk is issued in one
 // round up front, the 9 x 9 pivots are factored right-looking with rsqrt, and the group's Schur accumulator Sacc
 // lives on across chunks and levels.
-template <int FD>
+// ITE: compile-time bound of the FD x G element loop (ceil(FD * G / 128)): sizes the register batch of the E loads
+template <int FD, int ITE>
 __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLevel L, const ChainLevel nxt, int G, int j, double* sm,
                                              int tid, int grp, int* bad) {
   constexpr int c = kCsChunk, NT = kCsGroup;
@@ -142,36 +143,142 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
   const int rIdx = s + m + 1;
   const int jr = toGhost ? nsep : j + 1;
   group_sync(grp);  // the previous chunk of this group is done with the workspace
-  // ---- one round of global loads: separator, pivots, couplings, right-hand sides
-  for (int e = tid; e < FD * FD; e += NT) Al[e] = src_A<FD>(src, s, e);
+  // ---- global loads, batched: every load of the chunk is in flight before the first one is used (a loop that loads,
+  // scales and stores element by element pays one memory round trip per iteration — measured: half of a chunk's time).
+  // Level 0 first stages the Jacobi scales it needs in shared memory (one round trip), then everything else is one more.
+  constexpr int kMaxNodes = c;                 // separator + interior nodes
+  constexpr int kItA = (kMaxNodes * FD * FD + NT - 1) / NT;
   const int rG0 = tid / G, qG0 = tid - rG0 * G;      // (row, column) of element tid of an FD x G block
   const int rw0 = tid / w, qw0 = tid - rw0 * w;      // ... of an FD x w block
   const int rV0 = tid / VW, qV0 = tid - rV0 * VW;    // ... of an FD x VW block
-  for (int e = tid, r = rG0, q = qG0; e < FD * G; e += NT, adv2(r, q, G, NT)) El[e] = src_E<FD>(src, s, r, q);
-  for (int e = tid; e < FD; e += NT) gl[e] = src_g<FD>(src, s, e);
-  if (hasR)
-    for (int e = tid; e < FD * FD; e += NT) Ur[e] = src_U<FD>(src, rIdx, e);
+  const bool lvl0 = src.L == nullptr;
+  double* sS = Eo;                                   // level 0: scales of nodes s-1 .. rIdx, [(c + 2)][FD], then sG [G]
+  double* sG = sS + (c + 2) * FD;                    //          (Eo is written only after the scales have been used)
+  if (lvl0) {
+    for (int e = tid; e < (m + 3) * FD; e += NT) {
+      const int64_t node = static_cast<int64_t>(s) - 1 + e / FD;
+      sS[e] = (node >= 0 && node < src.nf) ? src.scale[node * FD + e % FD] : 0.0;
+    }
+    for (int e = tid; e < G; e += NT) sG[e] = src.scale[static_cast<int64_t>(src.nf) * FD + e];
+  }
+  {
+    const int nn = m + 1;                    // nodes s .. s+m
+    const int nu = m + (hasR ? 1 : 0);       // U blocks of nodes s+1 .. s+m (+ the right separator)
+    double vA[kItA], vA2[kItA], vU[kItA], vg = 0.0, vg2 = 0.0, vE[kMaxNodes][ITE], vE2[kMaxNodes][ITE];
+    // A (and level >= 1: addA)
+#pragma unroll
+    for (int it = 0; it < kItA; ++it) {
+      const int e = tid + it * NT;
+      vA[it] = vA2[it] = vU[it] = 0.0;
+      if (e < nn * FD * FD) {
+        const int64_t off = static_cast<int64_t>(s) * FD * FD + e;
+        vA[it] = lvl0 ? src.b.B[off] : L.A[off];
+        if (!lvl0 && L.addA) vA2[it] = L.addA[off];
+        if (lvl0 && src.D2x && (e % (FD * FD)) % (FD + 1) == 0) vA2[it] = src.D2x[(s + e / (FD * FD)) * FD + (e % (FD * FD)) / (FD + 1)];
+      }
+      if (e < nu * FD * FD) {
+        const int64_t off = static_cast<int64_t>(s + 1) * FD * FD + e;
+        vU[it] = lvl0 ? src.b.U[off] : L.U[off];
+      }
+    }
+    // E (and addE), node-major so that (row, column) advance without divisions
+#pragma unroll
+    for (int nd = 0; nd < kMaxNodes; ++nd) {
+#pragma unroll
+      for (int it = 0; it < ITE; ++it) {
+        vE[nd][it] = vE2[nd][it] = 0.0;
+        const int e = tid + it * NT;
+        if (nd < nn && e < FD * G) {
+          const int64_t off = static_cast<int64_t>(s + nd) * FD * G + e;
+          vE[nd][it] = lvl0 ? src.b.E[off] : L.E[off];
+          if (!lvl0 && L.addE) vE2[nd][it] = L.addE[off];
+        }
+      }
+    }
+    if (tid < nn * FD) {
+      const int64_t off = static_cast<int64_t>(s) * FD + tid;
+      vg = lvl0 ? src.b.gf[off] : L.g[off];
+      if (!lvl0 && L.addg) vg2 = L.addg[off];
+    }
+    if (lvl0) group_sync(grp);  // the scales are in shared memory
+    // ---- scale / damp / add, and park everything in shared memory
+#pragma unroll
+    for (int it = 0; it < kItA; ++it) {
+      const int e = tid + it * NT;
+      if (e < nn * FD * FD) {
+        const int nd = e / (FD * FD), el = e - nd * FD * FD, r = el / FD, q = el - r * FD;
+        double v;
+        if (lvl0) {
+          const double sr = sS[(nd + 1) * FD + r], sq = sS[(nd + 1) * FD + q];
+          v = vA[it] * sr * sq;
+          if (r == q) v += src.D2x ? vA2[it] : lm_damp(vA[it], sr, src.rinv);
+        } else {
+          v = vA[it] + vA2[it];
+        }
+        if (nd == 0) Al[el] = v;
+        else Ap[(nd - 1) * FD * FD + el] = v;
+      }
+      if (e < nu * FD * FD) {
+        const int nd = e / (FD * FD), el = e - nd * FD * FD, r = el / FD, q = el - r * FD;  // node s + 1 + nd
+        // H[p-1, p] scaled by (scale of p-1, row) x (scale of p, column)
+        const double v = lvl0 ? vU[it] * sS[(nd + 1) * FD + r] * sS[(nd + 2) * FD + q] : vU[it];
+        if (nd < m) Uc[nd * FD * FD + el] = v;
+        else Ur[el] = v;
+      }
+    }
+    if (tid < nn * FD) {
+      const int nd = tid / FD, r = tid - nd * FD;
+      const double v = lvl0 ? vg * sS[(nd + 1) * FD + r] : vg + vg2;
+      if (nd == 0) gl[r] = v;
+      else V[static_cast<int64_t>(nd - 1) * FD * VW + r * VW + og] = v;
+    }
+    // level 0: the scales (parked in Eo's space) move to registers before Eo is written: column scales in sGq, row
+    // scales in vE2 (which level 0 does not use otherwise)
+    double sGq[ITE];
+    if (lvl0) {
+      int r = rG0, q = qG0;
+#pragma unroll
+      for (int it = 0; it < ITE; ++it) {
+        const bool in = tid + it * NT < FD * G;
+        sGq[it] = in ? sG[q] : 1.0;
+#pragma unroll
+        for (int nd = 0; nd < kMaxNodes; ++nd) vE2[nd][it] = (in && nd < nn) ? sS[(nd + 1) * FD + r] : 1.0;
+        adv2(r, q, G, NT);
+      }
+    }
+    group_sync(grp);  // everybody has read the scales: Eo may be overwritten
+#pragma unroll
+    for (int nd = 0; nd < kMaxNodes; ++nd) {
+      int r = rG0, q = qG0;
+#pragma unroll
+      for (int it = 0; it < ITE; ++it) {
+        const int e = tid + it * NT;
+        if (nd < nn && e < FD * G) {
+          const double v = lvl0 ? vE[nd][it] * vE2[nd][it] * sGq[it] : vE[nd][it] + vE2[nd][it];
+          if (nd == 0) {
+            El[e] = v;
+          } else {
+            V[static_cast<int64_t>(nd - 1) * FD * VW + r * VW + oE + q] = v;
+            Eo[(nd - 1) * FD * G + e] = v;
+          }
+        }
+        adv2(r, q, G, NT);
+      }
+    }
+  }
+  group_sync(grp);
+  // couplings of the interior nodes' right-hand sides, from the staged U blocks
   for (int i = 0; i < m; ++i) {
-    const int64_t p = s + 1 + i;
     double* Vi = V + static_cast<int64_t>(i) * FD * VW;
     const bool lastI = i == m - 1;
+    const double* Unext = lastI ? Ur : Uc + (i + 1) * FD * FD;  // H[p, p+1]
     for (int e = tid; e < FD * FD; e += NT) {
       const int r = e / FD, q = e - r * FD;
-      Ap[i * FD * FD + e] = src_A<FD>(src, p, e);
-      const double u = src_U<FD>(src, p, e);
-      Uc[i * FD * FD + e] = u;
-      if (i == 0) Vi[q * VW + oL + r] = u;  // H[p0, s] = U[p0]^T
-      else Vi[r * VW + oL + q] = 0.0;
-      const double unext = (!lastI || hasR) ? src_U<FD>(src, p + 1, e) : 0.0;  // H[p, p+1]
+      Vi[r * VW + oL + q] = i == 0 ? Uc[q * FD + r] : 0.0;  // H[p0, s] = U[p0]^T
+      const double unext = (!lastI || hasR) ? Unext[e] : 0.0;
       Vi[r * VW + q] = lastI ? 0.0 : unext;
       Vi[r * VW + oR + q] = (lastI && hasR) ? unext : 0.0;
     }
-    for (int e = tid, r = rG0, q = qG0; e < FD * G; e += NT, adv2(r, q, G, NT)) {
-      const double v = src_E<FD>(src, p, r, q);
-      Vi[r * VW + oE + q] = v;
-      Eo[i * FD * G + e] = v;
-    }
-    for (int e = tid; e < FD; e += NT) Vi[e * VW + og] = src_g<FD>(src, p, e);
   }
   group_sync(grp);
   // ---- forward sweep
@@ -414,7 +521,13 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     src.L = l > 0 ? &a.lev[l] : nullptr;
     src.b = b; src.scale = a.scale; src.D2x = a.D2x; src.rinv = rinv; src.G = G; src.nf = nf;
     const int nsep = a.lev[l + 1].n - a.dp.ghost;
-    for (int j = gid; j < nsep; j += n_groups) chain_eliminate_chunk<FD>(src, a.lev[l], a.lev[l + 1], G, j, gsm, gtid, grp, &bad_s[grp]);
+    const int ite = (FD * G + kCsGroup - 1) / kCsGroup;
+    const ChainLevel Lc = a.lev[l], Ln = a.lev[l + 1];
+    for (int j = gid; j < nsep; j += n_groups) {
+      if (ite <= 3) chain_eliminate_chunk<FD, 3>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp]);
+      else if (ite <= 5) chain_eliminate_chunk<FD, 5>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp]);
+      else chain_eliminate_chunk<FD, 8>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp]);
+    }
     if (l + 2 == a.n_levels) {  // last level: publish this group's Schur partial
       group_sync(grp);
       double* out = a.Spart + static_cast<int64_t>(gid) * NS;
@@ -504,11 +617,38 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
         wd[j] = wj;
         if (!okp) bad_dense = 1;
       }
-      for (int i = j + 1 + ti; i <= N; i += 16) {
+      // trailing update, operands staged in registers first: S rows and the pivot column alias for the compiler, so a
+      // load-compute-store loop would serialise on shared-memory latency (measured: 600 ns per column)
+      constexpr int kT = 9;  // (N + 1) / 16 rounded up for N <= 139
+      double lw[kT];
+#pragma unroll
+      for (int a_ = 0; a_ < kT; ++a_) {
+        const int i = j + 1 + ti + 16 * a_;
+        lw[a_] = i <= N ? (i < N ? S[i * N + j] : rhs[j]) * wj : 0.0;
+      }
+      double sk[kT];
+#pragma unroll
+      for (int b_ = 0; b_ < kT; ++b_) {
+        const int k = j + 1 + tk + 16 * b_;
+        sk[b_] = k < N ? S[k * N + j] : 0.0;
+      }
+#pragma unroll
+      for (int a_ = 0; a_ < kT; ++a_) {
+        const int i = j + 1 + ti + 16 * a_;
+        if (i > N) break;
         double* row = i < N ? S + i * N : rhs;
-        const double lw = row[j] * wj;
         const int kmax = i < N ? i : N - 1;
-        for (int k = j + 1 + tk; k <= kmax; k += 16) row[k] -= lw * S[k * N + j];
+        double rv[kT];
+#pragma unroll
+        for (int b_ = 0; b_ < kT; ++b_) {
+          const int k = j + 1 + tk + 16 * b_;
+          rv[b_] = k <= kmax ? row[k] : 0.0;
+        }
+#pragma unroll
+        for (int b_ = 0; b_ < kT; ++b_) {
+          const int k = j + 1 + tk + 16 * b_;
+          if (k <= kmax) row[k] = rv[b_] - lw[a_] * sk[b_];
+        }
       }
     }
     __syncthreads();
@@ -586,7 +726,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     const int gw = bid * (kCsThreads / 32) + warp, nw = nb * (kCsThreads / 32);
     const double* dc = a.delta + nfp;
     for (int l = a.n_levels - 2; l >= 0; --l) {
-      const ChainLevel& cur = a.lev[l];
+      const ChainLevel cur = a.lev[l];
       const int n_eff = cur.n - cur.ghost;
       const int n_chunks = (n_eff + c - 1) / c;
       // interior node q (0..c-2) of chunk j: p = j*c + 1 + q
@@ -595,9 +735,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
         if (p >= n_eff) continue;
         const int s = jc * c;
         const int r = s + c < n_eff ? s + c : (cur.ghost ? cur.n - 1 : cur.n);
-        const int os = l > 0 ? cur.orig[s] : s, op = l > 0 ? cur.orig[p] : p;
+        // original frame of node p of level l: p * 4^l (no ghost node on one GPU); a table lookup otherwise
+        const int sh = 2 * l;
+        const int os = cur.ghost ? (l > 0 ? cur.orig[s] : s) : s << sh, op = cur.ghost ? (l > 0 ? cur.orig[p] : p) : p << sh;
         const double* xl = a.delta + static_cast<int64_t>(os) * FD;
-        const double* xr = r < cur.n ? a.delta + static_cast<int64_t>(l > 0 ? cur.orig[r] : r) * FD : nullptr;
+        const double* xr = r < cur.n ? a.delta + static_cast<int64_t>(cur.ghost ? (l > 0 ? cur.orig[r] : r) : r << sh) * FD : nullptr;
         const double* Z = cur.Z + static_cast<int64_t>(p) * FD * w;
         double* out = a.delta + static_cast<int64_t>(op) * FD;
         // the solved neighbours / globals this lane multiplies with (two columns per lane at most: w - 1 <= 64 ... or a loop)

@@ -317,6 +317,14 @@ struct WeightArgs {
   int ni;
   double sigma_g, sigma_a;
 };
+struct WeightView {  // WeightArgs' fields with the problem description by reference (persistent kernel)
+  const DevProblem& dp;
+  imu::ImuBuf buf;
+  const double* ftime;
+  double* wsqrt;
+  int ni;
+  double sigma_g, sigma_a;
+};
 constexpr int kWtWarps = 4;                              // warps per CTA
 constexpr int kWtTeams = kWtWarps * (32 / kTeam);        // intervals per CTA
 
@@ -452,7 +460,8 @@ __device__ __forceinline__ void weight_from_cov(const Pose<double>& y, const dou
 }
 
 // UpdateImuWeights for interval kk by the team of 16 lanes `tl` belongs to (kk >= ni: the team idles along)
-__device__ __forceinline__ void imu_weights_team(const WeightArgs& a, const double* state, int kk, Work* W, int tl) {
+template <class A>
+__device__ __forceinline__ void imu_weights_team(const A& a, const double* state, int kk, Work* W, int tl) {
   const int ki = min(kk, a.ni - 1);  // an odd tail team shadows the last interval (never written)
   const double* X1 = state + 7 * static_cast<int64_t>(ki);
   const double* X2 = state + 7 * static_cast<int64_t>(ki + 1);

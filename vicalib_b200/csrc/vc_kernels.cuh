@@ -320,12 +320,13 @@ struct RedFinArgs {
 };
 // Level 1 of the reduction for slice `bid` of `nb` (256 threads): the slice's share of the per-group global blocks
 // -> Cpart[bid], of the cost / gradient-norm / step partials -> red_part[bid].  acc: NS doubles of shared memory.
-__device__ __forceinline__ void reduce_level1(const RedFinArgs& a, const Blocks& out, double* acc, double (*shr)[8], int bid, int nb) {
-  const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void reduce_level1(const RedFinArgs& a, const DevProblem& dp, const Blocks& out, double* acc, double (*shr)[8],
+                                              int bid, int nb) {
+  const int G = dp.G, tid = threadIdx.x, NS = G * G + G, lane = tid & 31, warp = tid >> 5;
   for (int k = tid; k < NS; k += 256) acc[k] = 0.0;
   __syncthreads();
-  for (int c = 0; c < a.dp.n_cams; ++c) {
-    const CamInfo& ci = a.dp.cams[c];
+  for (int c = 0; c < dp.n_cams; ++c) {
+    const CamInfo& ci = dp.cams[c];
     const int NG = 6 + ci.K, nsym = NG * (NG + 1) / 2;
     const int lo = static_cast<int>(static_cast<int64_t>(ci.n_groups) * bid / nb);
     const int hi = static_cast<int>(static_cast<int64_t>(ci.n_groups) * (bid + 1) / nb);
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(RedFinArgs a) {
   const Blocks& out = a.out[pick(a.ctl, a.which)];
   const int G = a.dp.G, tid = threadIdx.x, NS = G * G + G, lane = tid & 31, warp = tid >> 5;
   const int nb = gridDim.x, bid = blockIdx.x;
-  reduce_level1(a, out, acc, shr, bid, nb);
+  reduce_level1(a, a.dp, out, acc, shr, bid, nb);
   if (tid == 0) {
     if (a.level1_only) { is_last = 0; }
     __threadfence();

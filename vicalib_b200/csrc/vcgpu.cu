@@ -25,6 +25,7 @@
 #include "vc_imu_weights.cuh"
 #include "vc_imu_mega.cuh"
 #include "vc_imu_eval_mega.cuh"
+#include "vc_pnp.cuh"
 
 using namespace vc;
 
@@ -873,6 +874,117 @@ extern "C" int vcgpu_solve_arrow(vcgpu_handle* h, const double* scale, const dou
   VC_TRY(read_scalars(h));
   if (h->h_scalars[kScNotPD] > 0) return fail(h, VCGPU_ERR_NUMERIC, "arrow system is not positive definite");
   CUDA_TRY(h, cudaMemcpy(x, h->d_delta, np * sizeof(double), cudaMemcpyDeviceToHost));
+  return VCGPU_OK;
+}
+
+// Solution covariance of the global parameters (GetSolutionCovariance, vicalibrator.h:802-857, compiled out upstream
+// behind COMPUTE_VICALIB_COVARIANCE because ceres::Covariance on the full problem "can run out of memory"): the
+// [globals, globals] block of (J^T J)^-1 at the current state, i.e. the inverse of the Schur complement of the frames —
+// one solve of the (undamped, unscaled) arrow system per global column on the device, through the same frame
+// elimination the trust-region step uses.  Tangent space: per camera (w_ck 3 | p_ck 3 | intrinsics K), then with
+// inertial terms (g 2 | b 6 | sf 6 | ts 1); rows / columns of constant parameters are zero like ceres::Covariance's.
+extern "C" int vcgpu_get_covariance(vcgpu_handle* h, double* cov) {
+  if (!h || !cov) return VCGPU_ERR_INVALID;
+  VC_TRY(prepare(h));
+  VC_TRY(ctl_reset(h, 0, 0));
+  VC_TRY(evaluate_into(h, 0, false, -1));
+  const DevProblem& dp = h->dp;
+  const int G = dp.G;
+  const int64_t nfp = static_cast<int64_t>(dp.n_frames) * dp.fd, np = nfp + G;
+  std::vector<double> mask;
+  fill_mask(h, &mask);
+  const Blocks& b = h->blk[h->cur];
+  std::vector<double> gf0(nfp), gc0(G), ones(np, 1.0), D2(np, 0.0), col(G, 0.0), x(np);
+  CUDA_TRY(h, cudaMemcpyAsync(gf0.data(), b.gf, nfp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(gc0.data(), b.gc, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < G; ++k) D2[nfp + k] = mask[k] != 0.0 ? 0.0 : 1.0;  // constant columns are empty: keep the system definite
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_scale, ones.data(), np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_scale + np, D2.data(), np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(b.gf, 0, nfp * sizeof(double), h->stream));
+  std::fill(cov, cov + static_cast<size_t>(G) * G, 0.0);
+  int rc = VCGPU_OK;
+  for (int j = 0; j < G && rc == VCGPU_OK; ++j) {
+    if (mask[j] == 0.0) continue;
+    std::fill(col.begin(), col.end(), 0.0);
+    col[j] = -1.0;  // the solver returns x with H x = -g
+    CUDA_TRY(h, cudaMemcpyAsync(b.gc, col.data(), G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_scalars + kScNotPD, 0, sizeof(double), h->stream));
+    rc = solve_and_update(h, h->d_scale + np, false);
+    if (rc != VCGPU_OK) break;
+    CUDA_TRY(h, cudaMemcpyAsync(x.data(), h->d_delta, np * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    rc = read_scalars(h);
+    if (rc == VCGPU_OK && h->h_scalars[kScNotPD] > 0) rc = fail(h, VCGPU_ERR_NUMERIC, "covariance: J^T J is singular at the current state");
+    for (int i = 0; i < G; ++i) cov[static_cast<size_t>(i) * G + j] = mask[i] != 0.0 ? x[nfp + i] : 0.0;
+  }
+  // put the gradient back; the Jacobi scale is recomputed by the next solve
+  CUDA_TRY(h, cudaMemcpyAsync(b.gf, gf0.data(), nfp * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(b.gc, gc0.data(), G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->blocks_valid = false;
+  return rc;
+}
+
+// Batched PosePnPRansac (vicalib-task.cc:322-325): pose of the planar target in every (frame, camera) view, one warp
+// per view (vc_pnp.cuh).  Cameras (model, intrinsics) are the ones given to vcgpu_set_cameras.
+extern "C" int vcgpu_pose_pnp_ransac(vcgpu_handle* h, int n_views, const int32_t* cam_id, const int64_t* start, const int32_t* count,
+                                     const double* pix, const double* pw, int robust_its, double robust_tol, double* T_cw,
+                                     double* rmse, int32_t* n_used) {
+  if (!h || n_views < 0 || (n_views > 0 && (!cam_id || !start || !count || !pix || !pw || !T_cw)))
+    return h ? fail(h, VCGPU_ERR_INVALID, "pose_pnp_ransac: bad arguments") : VCGPU_ERR_INVALID;
+  if (h->n_cams <= 0) return fail(h, VCGPU_ERR_INVALID, "pose_pnp_ransac: cameras must be set first");
+  if (n_views == 0) return VCGPU_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int64_t N = 0;
+  for (int v = 0; v < n_views; ++v) {
+    if (cam_id[v] < 0 || cam_id[v] >= h->n_cams || start[v] < 0 || count[v] < 0)
+      return fail(h, VCGPU_ERR_INVALID, "pose_pnp_ransac: bad view description");
+    N = std::max<int64_t>(N, start[v] + count[v]);
+  }
+  int32_t *d_cam = nullptr, *d_count = nullptr, *d_model = nullptr, *d_used = nullptr;
+  int64_t* d_start = nullptr;
+  double *d_pix = nullptr, *d_pw = nullptr, *d_intr = nullptr, *d_xy = nullptr, *d_T = nullptr, *d_rmse = nullptr;
+  unsigned char* d_use = nullptr;
+  auto release = [&] {
+    cudaFree(d_cam); cudaFree(d_count); cudaFree(d_model); cudaFree(d_used); cudaFree(d_start); cudaFree(d_pix); cudaFree(d_pw);
+    cudaFree(d_intr); cudaFree(d_xy); cudaFree(d_T); cudaFree(d_rmse); cudaFree(d_use);
+  };
+  const size_t nv = static_cast<size_t>(n_views), np_ = static_cast<size_t>(std::max<int64_t>(N, 1));
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** d, const void* src, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(d, std::max<size_t>(bytes, 8));
+    if (e == cudaSuccess && src) e = cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, h->stream);
+  };
+  up(reinterpret_cast<void**>(&d_cam), cam_id, nv * sizeof(int32_t));
+  up(reinterpret_cast<void**>(&d_start), start, nv * sizeof(int64_t));
+  up(reinterpret_cast<void**>(&d_count), count, nv * sizeof(int32_t));
+  up(reinterpret_cast<void**>(&d_pix), pix, 2 * np_ * sizeof(double));
+  up(reinterpret_cast<void**>(&d_pw), pw, 3 * np_ * sizeof(double));
+  up(reinterpret_cast<void**>(&d_model), h->h_model.data(), h->n_cams * sizeof(int32_t));
+  up(reinterpret_cast<void**>(&d_intr), h->h_intr.data(), 10 * h->n_cams * sizeof(double));
+  up(reinterpret_cast<void**>(&d_xy), nullptr, 2 * np_ * sizeof(double));
+  up(reinterpret_cast<void**>(&d_use), nullptr, np_);
+  up(reinterpret_cast<void**>(&d_T), nullptr, 7 * nv * sizeof(double));
+  up(reinterpret_cast<void**>(&d_rmse), nullptr, nv * sizeof(double));
+  up(reinterpret_cast<void**>(&d_used), nullptr, nv * sizeof(int32_t));
+  if (e != cudaSuccess) { release(); h->err = std::string("pose_pnp_ransac: ") + cudaGetErrorString(e); return VCGPU_ERR_CUDA; }
+  vc::pnp::Args a;
+  a.n_views = n_views; a.cam = d_cam; a.start = d_start; a.count = d_count; a.pix = d_pix; a.pw = d_pw; a.model = d_model; a.intr = d_intr;
+  a.robust_its = robust_its; a.robust_tol = robust_tol; a.xy = d_xy; a.use = d_use; a.T_cw = d_T; a.rmse = d_rmse; a.n_used = d_used;
+  vc::pnp::pose_pnp_kernel<<<(n_views + vc::pnp::kWarps - 1) / vc::pnp::kWarps, 32 * vc::pnp::kWarps, 0, h->stream>>>(a);
+  ++h->launches;
+  std::vector<double> hr(nv);
+  std::vector<int32_t> hu(nv);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(T_cw, d_T, 7 * nv * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hr.data(), d_rmse, nv * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hu.data(), d_used, nv * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  release();
+  if (e != cudaSuccess) { h->err = std::string("pose_pnp_ransac: ") + cudaGetErrorString(e); return VCGPU_ERR_CUDA; }
+  if (rmse) std::copy(hr.begin(), hr.end(), rmse);
+  if (n_used) std::copy(hu.begin(), hu.end(), n_used);
   return VCGPU_OK;
 }
 
