@@ -28,7 +28,7 @@ int main(int argc, char** argv) {
   // header: n_cams n_frames n_obs n_imu inertial has_initial_guess max_iters mode
   //   mode bit 0: emulate the residual-block duplication; bit 1: LEVENBERG_MARQUARDT instead of the reference's DOGLEG;
   //   bit 2: run, Clear(), load the problem again and run once more (a reused object must start from scratch);
-  //   bit 3: remove_outliers
+  //   bit 3: remove_outliers; bit 4: the reference's default function tolerance 1e-6 (else 1e-10)
   std::vector<int64_t> hd = rd<int64_t>(f, 8);
   const int nc = static_cast<int>(hd[0]), nf = static_cast<int>(hd[1]);
   const int64_t nobs = hd[2], nimu = hd[3];
@@ -71,7 +71,7 @@ int main(int argc, char** argv) {
     cal.AddObservation(of[i], oc[i], Vector3d{{pw[3 * i], pw[3 * i + 1], pw[3 * i + 2]}}, Vector2d{{pc[2 * i], pc[2 * i + 1]}}, tm[of[i]]);
   for (int64_t i = 0; i < nimu; ++i)
     cal.AddImuMeasurements(Vector3d{{iw[3 * i], iw[3 * i + 1], iw[3 * i + 2]}}, Vector3d{{ia[3 * i], ia[3 * i + 1], ia[3 * i + 2]}}, it[i]);
-  cal.SetFunctionTolerance(1e-10);
+  cal.SetFunctionTolerance((hd[7] & 16) ? 1e-6 : 1e-10);
   if (has_guess) cal.SetOptimizationFlags(true, inertial, false, true);  // vicalib-task.cc:227-235
   cal.Start();
   while (cal.IsRunning()) usleep(2000);  // the reference polls every 30 ms (vicalib-engine.cc:388-400)

@@ -20,7 +20,7 @@ from vicalib_b200.capi import Calibrator  # noqa: E402
 ALL_ON = dict(inertial=1, rotation_only=0, bias_active=1, scale_active=1, optimize_ts=1)
 
 
-def run_case(rank, world, local, inertial):
+def run_case(rank, world, local, inertial, strategy=0):
     if inertial:
         p = synth.make_problem(models=("poly3", "fov"), n_frames=67, seed=34, inertial=True, ts_truth=0.002)
         flags, iters = ALL_ON, 12
@@ -34,7 +34,7 @@ def run_case(rank, world, local, inertial):
     ps = synth.shard(p, rank, world)
     g.load(ps)
     g.set_flags(**flags)
-    g.set_options(function_tol=1e-14, max_iters=iters)
+    g.set_options(function_tol=1e-14, max_iters=iters, strategy=strategy)
     s = g.solve()
     st = g.state()
     n_own = synth.shard_frames(p.n_frames, rank, world)
@@ -47,7 +47,7 @@ def run_case(rank, world, local, inertial):
         ref = Calibrator(device=local)
         ref.load(p)
         ref.set_flags(**flags)
-        ref.set_options(function_tol=1e-14, max_iters=iters)
+        ref.set_options(function_tol=1e-14, max_iters=iters, strategy=strategy)
         sr = ref.solve()
         sref = ref.state()
         T = np.concatenate([o["T"] for o in out])
@@ -65,7 +65,7 @@ def run_case(rank, world, local, inertial):
             checks["bias"] = np.abs(out[0]["b"] - sref["b"]).max() <= 1e-8
             checks["ts"] = abs(out[0]["ts"] - sref["ts"]) <= 1e-10
         ok = all(checks.values())
-        print("MG_CHECK", "inertial" if inertial else "vision", "PASS" if ok else "FAIL", checks, "cost", out[0]["cost"],
+        print("MG_CHECK", ("inertial" if inertial else "vision") + (" dogleg" if strategy else ""), "PASS" if ok else "FAIL", checks, "cost", out[0]["cost"],
               sr["final_cost"], flush=True)
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
@@ -77,6 +77,7 @@ def main():
     dist.init_process_group("gloo")
     ok = run_case(rank, world, local, False)
     ok = run_case(rank, world, local, True) and ok
+    ok = run_case(rank, world, local, False, strategy=1) and ok  # the reference's DOGLEG on frame shards (vision stages)
     if rank == 0:
         print("MG_CHECK", "ALL PASS" if ok else "SOME FAIL", flush=True)
     dist.barrier()

@@ -43,7 +43,10 @@ def test_covariance_matches_dense_inverse(models, inertial, flags):
     from oracle.binding import Oracle
     from vicalib_b200.capi import Calibrator
 
-    p = synth.make_problem(models=models, n_frames=18, inertial=inertial, seed=15)
+    # inertial problems need a few seconds of motion before biases / gravity are observable (else J^T J is singular to
+    # working precision and neither inverse means anything)
+    nf = 90 if inertial else 18
+    p = synth.make_problem(models=models, n_frames=nf, inertial=inertial, seed=15)
     g = Calibrator()
     g.load(p)
     g.set_flags(**flags)
@@ -51,7 +54,7 @@ def test_covariance_matches_dense_inverse(models, inertial, flags):
     g.solve()
     st = g.state()
     # the oracle evaluates J^T J at the state the device converged to
-    p2 = synth.make_problem(models=models, n_frames=18, inertial=inertial, seed=15)
+    p2 = synth.make_problem(models=models, n_frames=nf, inertial=inertial, seed=15)
     p2.intr, p2.q_ck, p2.p_ck, p2.T_wp, p2.v_w = st["intr"], st["q_ck"], st["p_ck"], st["T_wp"], st["v_w"]
     p2.g, p2.b, p2.sf, p2.ts = st["g"], st["b"], st["sf"], st["ts"]
     o = Oracle(p2, **flags)
@@ -63,7 +66,9 @@ def test_covariance_matches_dense_inverse(models, inertial, flags):
     sd = np.sqrt(np.maximum(np.diag(cov_o), 1e-300))
     corr_err = np.abs(cov_g - cov_o) / np.outer(sd, sd).clip(1e-300)
     live = np.diag(cov_o) > 0
-    assert corr_err[np.ix_(live, live)].max() <= 1e-6          # every entry relative to the two standard deviations
+    # every entry relative to the two standard deviations; both inverses lose cond(J^T J) * eps digits, and the inertial
+    # systems are conditioned ~1e10 even after Jacobi scaling
+    assert corr_err[np.ix_(live, live)].max() <= (1e-4 if inertial else 1e-6)
     assert np.array_equal(cov_g[~live], np.zeros_like(cov_g[~live]))  # constant blocks: zero rows (ceres::Covariance)
     assert np.abs(cov_g - cov_g.T).max() <= 1e-9 * np.abs(cov_g).max()
     # a second solve after the covariance call is unaffected by it

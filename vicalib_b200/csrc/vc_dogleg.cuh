@@ -117,19 +117,27 @@ __global__ void __launch_bounds__(32 * kMvWarps) arrow_matvec_frames_kernel(DevP
     zpart[static_cast<int64_t>(blockIdx.x) * G + c] = s;
   }
 }
+// mode 0: one GPU — sum of the per-CTA partials + C w_g.  Frame shards: mode 1 leaves this rank's sum of E^T w_f in
+// zsum [G] (all-reduced by the host code), mode 2 finishes y_g from the summed zsum.
 __global__ void __launch_bounds__(256) arrow_matvec_globals_kernel(DevProblem dp, Blocks b0, Blocks b1, const Ctl* ctl,
                                                                     const double* scale, const double* v, double* y,
-                                                                    const double* zpart, int nparts) {
+                                                                    const double* zpart, int nparts, int mode, double* zsum) {
   if (ctl->done) return;
   const Blocks& b = ctl->cur ? b1 : b0;
   const int G = dp.G;
   const int64_t nfp = static_cast<int64_t>(dp.n_frames) * dp.fd;
   for (int c = threadIdx.x; c < G; c += blockDim.x) {
-    double s0 = 0.0, s1 = 0.0;
-    int k = 0;
-    for (; k + 1 < nparts; k += 2) { s0 += zpart[static_cast<int64_t>(k) * G + c]; s1 += zpart[static_cast<int64_t>(k + 1) * G + c]; }
-    if (k < nparts) s0 += zpart[static_cast<int64_t>(k) * G + c];
-    double s = s0 + s1;
+    double s = 0.0;
+    if (mode != 2) {
+      double s0 = 0.0, s1 = 0.0;
+      int k = 0;
+      for (; k + 1 < nparts; k += 2) { s0 += zpart[static_cast<int64_t>(k) * G + c]; s1 += zpart[static_cast<int64_t>(k + 1) * G + c]; }
+      if (k < nparts) s0 += zpart[static_cast<int64_t>(k) * G + c];
+      s = s0 + s1;
+      if (mode == 1) { zsum[c] = s; continue; }
+    } else {
+      s = zsum[c];
+    }
     for (int q = 0; q < G; ++q) s += b.C[c * G + q] * (scale[nfp + q] * v[nfp + q]);
     y[nfp + c] = scale[nfp + c] * s;
   }
@@ -146,9 +154,28 @@ struct DlDotArgs {
   const double* scalars; // kSc*: not-PD flag of the solve
   double* part;          // [kDlBlocks][4]
   unsigned* counter;
-  int64_t n;
+  int64_t n;       // entries of the vectors (mode 1 stores gn for all of them)
+  int64_t n_sum;   // entries this rank sums: all of them, or on ranks > 0 of a sharded run only its frames' (the
+                   // globals' entries are replicated and counted once, by rank 0)
   int mode;
+  double* mg;      // frame shards: the two sums go here ([2], all-reduced by the host code) and dl_dots_finish_kernel
+                   // applies them; null: one GPU, applied here
 };
+__device__ inline void dl_apply_dots(Ctl* c, int mode, double t0, double t1, const double* scalars) {
+  if (mode == 0) {
+    c->dl_g2 = t0;
+    c->dl_alpha = t0 / t1;
+  } else if (mode == 1) {
+    c->dl_gn2 = t0;
+    c->dl_b = t1;
+    c->dl_ok = scalars[kScNotPD] > 0.0 ? 0 : 1;
+  } else {
+    c->dl_model_change = -t0 - 0.5 * t1;
+  }
+}
+__global__ void dl_dots_finish_kernel(Ctl* c, int mode, const double* mg, const double* scalars) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && !c->done) dl_apply_dots(c, mode, mg[0], mg[1], scalars);
+}
 __global__ void __launch_bounds__(256) dl_dots_kernel(DlDotArgs a) {
   __shared__ double sh[8][3];
   __shared__ int is_last;
@@ -157,17 +184,18 @@ __global__ void __launch_bounds__(256) dl_dots_kernel(DlDotArgs a) {
   const int64_t lo = a.n * bid / nb, hi = a.n * (bid + 1) / nb;
   double s[3] = {0.0, 0.0, 0.0};
   for (int64_t i = lo + tid; i < hi; i += 256) {
+    const double on = i < a.n_sum ? 1.0 : 0.0;
     if (a.mode == 0) {
-      s[0] += a.v.grad[i] * a.v.grad[i];
-      s[1] += a.v.vec[i] * a.v.Hv[i];
+      s[0] += on * a.v.grad[i] * a.v.grad[i];
+      s[1] += on * a.v.vec[i] * a.v.Hv[i];
     } else if (a.mode == 1) {
       const double gn = a.delta[i] * a.v.diag[i];
       a.v.gn[i] = gn;
-      s[0] += gn * gn;
-      s[1] += a.v.grad[i] * gn;
+      s[0] += on * gn * gn;
+      s[1] += on * a.v.grad[i] * gn;
     } else {
-      s[0] += a.v.vec[i] * (a.v.grad[i] * a.v.diag[i]);
-      s[1] += a.v.vec[i] * a.v.Hv[i];
+      s[0] += on * a.v.vec[i] * (a.v.grad[i] * a.v.diag[i]);
+      s[1] += on * a.v.vec[i] * a.v.Hv[i];
     }
   }
 #pragma unroll
@@ -190,17 +218,8 @@ __global__ void __launch_bounds__(256) dl_dots_kernel(DlDotArgs a) {
   __threadfence();
   double t0 = 0.0, t1 = 0.0;
   for (int k = 0; k < nb; ++k) { t0 += __ldcg(a.part + 4 * k); t1 += __ldcg(a.part + 4 * k + 1); }
-  Ctl* c = a.ctl;
-  if (a.mode == 0) {
-    c->dl_g2 = t0;
-    c->dl_alpha = t0 / t1;
-  } else if (a.mode == 1) {
-    c->dl_gn2 = t0;
-    c->dl_b = t1;
-    c->dl_ok = a.scalars[kScNotPD] > 0.0 ? 0 : 1;
-  } else {
-    c->dl_model_change = -t0 - 0.5 * t1;
-  }
+  if (a.mg) { a.mg[0] = t0; a.mg[1] = t1; }
+  else dl_apply_dots(a.ctl, a.mode, t0, t1, a.scalars);
 }
 
 // ---------------------------------------------------------------- the dogleg point (Ceres DoglegStrategy::ComputeTraditionalDoglegStep)

@@ -445,8 +445,30 @@ static int dl_matvec(vcgpu_handle* h, const double* v, double* y, double* zpart)
   const size_t sm = static_cast<size_t>(kMvWarps) * dp.G * sizeof(double);
   if (dp.fd == 6) arrow_matvec_frames_kernel<6><<<nb, 32 * kMvWarps, sm, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart);
   else arrow_matvec_frames_kernel<9><<<nb, 32 * kMvWarps, sm, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart);
-  arrow_matvec_globals_kernel<<<1, 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart, nb);
-  h->launches += 2;
+  ++h->launches;
+  if (h->nranks > 1) {  // the globals' rows need E^T w_f of every rank's frames
+    double* zsum = h->d_mg;
+    arrow_matvec_globals_kernel<<<1, 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart, nb, 1, zsum);
+    VC_TRY(all_reduce(h, zsum, dp.G));
+    arrow_matvec_globals_kernel<<<1, 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart, nb, 2, zsum);
+    h->launches += 2;
+  } else {
+    arrow_matvec_globals_kernel<<<1, 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v, y, zpart, nb, 0, nullptr);
+    ++h->launches;
+  }
+  return VCGPU_OK;
+}
+// the three pairs of inner products of a dogleg iteration; frame shards sum them over the ranks (NCCL) first
+static int dl_dots(vcgpu_handle* h, DlDotArgs da, int mode) {
+  da.mode = mode;
+  da.mg = h->nranks > 1 ? h->d_mg : nullptr;
+  dl_dots_kernel<<<kDlBlocks, 256, 0, h->stream>>>(da);
+  ++h->launches;
+  if (h->nranks > 1) {
+    VC_TRY(all_reduce(h, h->d_mg, 2));
+    dl_dots_finish_kernel<<<1, 32, 0, h->stream>>>(h->d_ctl, mode, h->d_mg, h->d_scalars);
+    ++h->launches;
+  }
   return VCGPU_OK;
 }
 static int enqueue_dogleg_iteration(vcgpu_handle* h, bool weights) {
@@ -462,21 +484,17 @@ static int enqueue_dogleg_iteration(vcgpu_handle* h, bool weights) {
   DlDotArgs da;
   da.ctl = h->d_ctl; da.v = v; da.delta = h->d_delta; da.scalars = h->d_scalars; da.part = h->d_dl_part;
   da.counter = h->d_counter + 1; da.n = np;
+  da.n_sum = (h->nranks > 1 && h->rank > 0) ? static_cast<int64_t>(dp.n_frames) * dp.fd : np;
   dl_prep_kernel<<<nblk, 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, v);
   ++h->launches;
   VC_TRY(dl_matvec(h, v.vec, v.Hv, zpart));
-  da.mode = 0;
-  dl_dots_kernel<<<kDlBlocks, 256, 0, h->stream>>>(da);
-  ++h->launches;
+  VC_TRY(dl_dots(h, da, 0));
   VC_TRY(solve_and_update(h, v.D2, false));  // Gauss-Newton step with mu D^2 regularisation -> d_delta
-  da.mode = 1;
-  dl_dots_kernel<<<kDlBlocks, 256, 0, h->stream>>>(da);
+  VC_TRY(dl_dots(h, da, 1));
   dl_combine_kernel<<<nblk, 256, 0, h->stream>>>(h->d_ctl, v, h->d_delta, np);
-  h->launches += 2;
-  VC_TRY(dl_matvec(h, v.vec, v.Hv, zpart));
-  da.mode = 2;
-  dl_dots_kernel<<<kDlBlocks, 256, 0, h->stream>>>(da);
   ++h->launches;
+  VC_TRY(dl_matvec(h, v.vec, v.Hv, zpart));
+  VC_TRY(dl_dots(h, da, 2));
   {  // x (+) S step into the trial buffer, step statistics
     UpdateArgs ua;
     ua.dp = dp; ua.b[0] = h->blk[0]; ua.b[1] = h->blk[1]; ua.ctl = h->d_ctl; ua.scale = h->d_scale; ua.D2x = v.D2;
@@ -513,8 +531,8 @@ static int enqueue_iteration(vcgpu_handle* h, bool weights) {
 // ------------------------------------------------------------------ the trust-region loop
 static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summary* out, int fixed_iters) {
   VC_TRY(prepare(h));
-  if (h->opts.strategy == 1 && h->nranks > 1)
-    return fail(h, VCGPU_ERR_INVALID, "the DOGLEG strategy runs on one GPU; frame-sharded solves use strategy 0 (LM)");
+  if (h->opts.strategy == 1 && h->nranks > 1 && h->flags.inertial)
+    return fail(h, VCGPU_ERR_INVALID, "DOGLEG on frame shards covers the vision stages; sharded inertial solves use strategy 0 (LM)");
   const DevProblem& dp = h->dp;
   const vcgpu_options& o = h->opts;
   const int64_t np = static_cast<int64_t>(dp.n_frames) * dp.fd + dp.G;

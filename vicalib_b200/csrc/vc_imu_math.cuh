@@ -73,14 +73,17 @@ template <class T> __device__ __forceinline__ Vec<T> qrot(Quat<T> q, Vec<T> v) {
   return v + scale(uv, q.w) + cross(qv, uv);
 }
 
-// Sophus SO3::exp (small-angle Taylor branch keyed on the scalar part)
+// Sophus SO3::exp: imag = sin(theta/2)/theta, real = cos(theta/2).  Below theta^2 = 1e-3 both are evaluated by their
+// Taylor series to theta^8 / theta^10 (truncation < 1e-25 relative, i.e. the same double as the closed form): an IMU
+// sub-step rotates by milliradians, and the series needs no square root, sine / cosine or division — which matters
+// most when T is a dual number.  Sophus' own theta < 1e-10 branch is the first two terms of the same series.
 template <class T> __device__ inline Quat<T> so3_exp(Vec<T> om) {
   const T th2 = dot(om, om);
   T imag, real;
-  if (val(th2) < kSophusEps * kSophusEps) {
-    const T th4 = th2 * th2;
-    imag = T(0.5) - th2 * T(1.0 / 48.0) + th4 * T(1.0 / 3840.0);
-    real = T(1.0) - th2 * T(1.0 / 8.0) + th4 * T(1.0 / 384.0);
+  if (val(th2) < 1e-3) {
+    imag = T(0.5) + th2 * (T(-1.0 / 48.0) + th2 * (T(1.0 / 3840.0) + th2 * (T(-1.0 / 645120.0) + th2 * T(1.0 / 185794560.0))));
+    real = T(1.0) + th2 * (T(-1.0 / 8.0) + th2 * (T(1.0 / 384.0) + th2 * (T(-1.0 / 46080.0) + th2 * (T(1.0 / 10321920.0) +
+                                                                                                   th2 * T(-1.0 / 3715891200.0)))));
   } else {
     const T th = dsqrt(th2);
     T s, c;

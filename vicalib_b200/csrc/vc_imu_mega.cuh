@@ -121,7 +121,16 @@ __device__ __forceinline__ double src_g(const NodeSrc& s, int64_t p, int e) {
 // ITE: compile-time bound of the FD x G element loop (ceil(FD * G / 128)): sizes the register batch of the E loads
 template <int FD, int ITE>
 __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLevel L, const ChainLevel nxt, int G, int j, double* sm,
-                                             int tid, int grp, int* bad) {
+                                             int tid, int grp, int* bad, unsigned long long* dbg = nullptr) {
+  // dbg: cycle counts of the chunk's phases (measurement hook: phase clocks [40..51], one group)
+  long long dbg_t = dbg ? clock64() : 0;
+  auto tick = [&](int slot) {
+    if (dbg && tid == 0) {
+      const long long t = clock64();
+      dbg[slot] += static_cast<unsigned long long>(t - dbg_t);
+      dbg_t = t;
+    }
+  };
   constexpr int c = kCsChunk, NT = kCsGroup;
   const int NS = G * G + G;
   const int w = 2 * FD + G + 1, VW = FD + w;
@@ -143,6 +152,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
   const int rIdx = s + m + 1;
   const int jr = toGhost ? nsep : j + 1;
   group_sync(grp);  // the previous chunk of this group is done with the workspace
+  tick(0);
   // ---- global loads, batched: every load of the chunk is in flight before the first one is used (a loop that loads,
   // scales and stores element by element pays one memory round trip per iteration — measured: half of a chunk's time).
   // Level 0 first stages the Jacobi scales it needs in shared memory (one round trip), then everything else is one more.
@@ -201,6 +211,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       if (!lvl0 && L.addg) vg2 = L.addg[off];
     }
     if (lvl0) group_sync(grp);  // the scales are in shared memory
+    tick(1);
     // ---- scale / damp / add, and park everything in shared memory
 #pragma unroll
     for (int it = 0; it < kItA; ++it) {
@@ -247,6 +258,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       }
     }
     group_sync(grp);  // everybody has read the scales: Eo may be overwritten
+    tick(2);
 #pragma unroll
     for (int nd = 0; nd < kMaxNodes; ++nd) {
       int r = rG0, q = qG0;
@@ -267,6 +279,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
     }
   }
   group_sync(grp);
+  tick(3);
   // couplings of the interior nodes' right-hand sides, from the staged U blocks
   for (int i = 0; i < m; ++i) {
     double* Vi = V + static_cast<int64_t>(i) * FD * VW;
@@ -281,6 +294,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
     }
   }
   group_sync(grp);
+  tick(4);
   // ---- forward sweep
   for (int i = 0; i < m; ++i) {
     double* Vi = V + static_cast<int64_t>(i) * FD * VW;
@@ -342,6 +356,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
     }
     group_sync(grp);
   }
+  tick(5);
   // ---- backward sweep: X_i = V_R(i) - V_U(i) X_{i+1}
   for (int i = m - 2; i >= 0; --i) {
     double* Vi = V + static_cast<int64_t>(i) * FD * VW;
@@ -355,26 +370,39 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
     }
     group_sync(grp);
   }
+  tick(6);
   // ---- store Z, accumulate the Schur terms: S += E_i^T X_i[E], rhs += E_i^T X_i[g]
   for (int i = 0; i < m; ++i) {
     const int64_t p = s + 1 + i;
     const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
     for (int e = tid, r = rw0, q = qw0; e < FD * w; e += NT, adv2(r, q, w, NT)) L.Z[p * FD * w + e] = Vi[r * VW + FD + q];
   }
-  {  // lower triangle of S (row ra has ra + 1 entries), then the right-hand side
+  tick(7);
+  {  // lower triangle of S (row ra has ra + 1 entries), then the right-hand side; four entries in flight per thread
     int ra = 0, cb = tid;
     while (cb > ra) { cb -= ra + 1; ++ra; }
-    for (; ra < G; ) {
-      double sum = 0.0;
+    while (ra < G) {
+      int r4[4], c4[4];
+      double sum[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        r4[u] = ra; c4[u] = cb;
+        cb += NT;
+        while (cb > ra && ra < G) { cb -= ra + 1; ++ra; }
+      }
       for (int i = 0; i < m; ++i) {
-        const double* Vi = V + static_cast<int64_t>(i) * FD * VW;
+        const double* Vi = V + static_cast<int64_t>(i) * FD * VW + oE;
         const double* Ei = Eo + i * FD * G;
 #pragma unroll
-        for (int k = 0; k < FD; ++k) sum += Ei[k * G + ra] * Vi[k * VW + oE + cb];
+        for (int k = 0; k < FD; ++k) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (r4[u] < G) sum[u] += Ei[k * G + r4[u]] * Vi[k * VW + c4[u]];
+        }
       }
-      Sacc[ra * G + cb] += sum;
-      cb += NT;
-      while (cb > ra) { cb -= ra + 1; ++ra; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r4[u] < G) Sacc[r4[u] * G + c4[u]] += sum[u];
     }
     for (int r = tid; r < G; r += NT) {
       double sum = 0.0;
@@ -387,6 +415,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       Sacc[G * G + r] += sum;
     }
   }
+  tick(8);
   if (m > 0) {
     const double* X0 = V;                                          // node s+1
     const double* Xl = V + static_cast<int64_t>(m - 1) * FD * VW;  // last interior node
@@ -442,6 +471,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
     if (j == 0) nxt.addg[e] = 0.0;
   }
   if (tid == 0) nxt.orig[j] = src.L ? L.orig[s] : s;
+  tick(9);
 }
 
 // x (+) step of one frame into the trial state, and the frame's share of the step statistics
@@ -523,8 +553,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     const int nsep = a.lev[l + 1].n - a.dp.ghost;
     const int ite = (FD * G + kCsGroup - 1) / kCsGroup;
     const ChainLevel Lc = a.lev[l], Ln = a.lev[l + 1];
+    unsigned long long* dbg = (a.prof && gid == 0 && l == 1) ? a.prof + 40 : nullptr;
     for (int j = gid; j < nsep; j += n_groups) {
-      if (ite <= 3) chain_eliminate_chunk<FD, 3>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp]);
+      if (ite <= 3) chain_eliminate_chunk<FD, 3>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp], dbg);
       else if (ite <= 5) chain_eliminate_chunk<FD, 5>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp]);
       else chain_eliminate_chunk<FD, 8>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp]);
     }
@@ -561,6 +592,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
   mark(kCsProfReduce);
   grid.sync();
   // ------------------------------------------------------------ dense solve of [globals | top nodes], every CTA
+  long long dt0 = 0;
   {
     const ChainLevel& top = a.lev[a.n_levels - 1];
     const int nt = top.n, N = G + nt * FD;
@@ -606,52 +638,38 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
         rhs[o + e] = -(__ldcg(top.g + static_cast<int64_t>(t) * FD + e) + (add ? __ldcg(top.addg + static_cast<int64_t>(t) * FD + e) : 0.0));
     }
     // right-looking L D L^T on the lower triangle, the right-hand side riding along as row N: one barrier per
-    // column, 16 x 16 thread tiling of the trailing update
+    // column, 16 x 16 thread tiling of the trailing update.  The reciprocal of the next pivot is taken by the one
+    // thread that finishes that pivot, while the others are still in their share of the update (a division on every
+    // thread's path was a third of the column time).
+    dt0 = clock64();
     const int ti = tid >> 4, tk = tid & 15;
+    __syncthreads();  // the system is assembled
+    if (tid == 0) {
+      const double d = S[0];
+      const bool okp = d > 0.0;
+      wd[0] = 1.0 / (okp ? d : 1.0);
+      if (!okp) bad_dense = 1;
+    }
     for (int j = 0; j < N; ++j) {
       __syncthreads();
-      const double d = S[j * N + j];
-      const bool okp = d > 0.0;
-      const double wj = 1.0 / (okp ? d : 1.0);
-      if (tid == 0) {
-        wd[j] = wj;
-        if (!okp) bad_dense = 1;
-      }
-      // trailing update, operands staged in registers first: S rows and the pivot column alias for the compiler, so a
-      // load-compute-store loop would serialise on shared-memory latency (measured: 600 ns per column)
-      constexpr int kT = 9;  // (N + 1) / 16 rounded up for N <= 139
-      double lw[kT];
-#pragma unroll
-      for (int a_ = 0; a_ < kT; ++a_) {
-        const int i = j + 1 + ti + 16 * a_;
-        lw[a_] = i <= N ? (i < N ? S[i * N + j] : rhs[j]) * wj : 0.0;
-      }
-      double sk[kT];
-#pragma unroll
-      for (int b_ = 0; b_ < kT; ++b_) {
-        const int k = j + 1 + tk + 16 * b_;
-        sk[b_] = k < N ? S[k * N + j] : 0.0;
-      }
-#pragma unroll
-      for (int a_ = 0; a_ < kT; ++a_) {
-        const int i = j + 1 + ti + 16 * a_;
-        if (i > N) break;
+      const double wj = wd[j];
+      for (int i = j + 1 + ti; i <= N; i += 16) {
         double* row = i < N ? S + i * N : rhs;
+        const double lw = row[j] * wj;
         const int kmax = i < N ? i : N - 1;
-        double rv[kT];
-#pragma unroll
-        for (int b_ = 0; b_ < kT; ++b_) {
-          const int k = j + 1 + tk + 16 * b_;
-          rv[b_] = k <= kmax ? row[k] : 0.0;
-        }
-#pragma unroll
-        for (int b_ = 0; b_ < kT; ++b_) {
-          const int k = j + 1 + tk + 16 * b_;
-          if (k <= kmax) row[k] = rv[b_] - lw[a_] * sk[b_];
+        for (int k = j + 1 + tk; k <= kmax; k += 16) {
+          const double v = row[k] - lw * S[k * N + j];
+          row[k] = v;
+          if (k == j + 1 && i == j + 1) {  // the next pivot is final: its reciprocal now
+            const bool okp = v > 0.0;
+            wd[j + 1] = 1.0 / (okp ? v : 1.0);
+            if (!okp) bad_dense = 1;
+          }
         }
       }
     }
     __syncthreads();
+    if (prof) { const long long t = clock64(); a.prof[53] += static_cast<unsigned long long>(t - dt0); dt0 = t; }
     if (warp == 0) {  // x_i = (u_Ni - sum_{k>i} u_ki x_k) / d_i
       for (int i = N - 1; i >= 0; --i) {
         const double xi = rhs[i] * wd[i];
@@ -662,6 +680,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       }
     }
     __syncthreads();
+    if (prof) { const long long t = clock64(); a.prof[54] += static_cast<unsigned long long>(t - dt0); dt0 = t; }
     if (bid == 0) {
       const int bd = bad_dense;
       for (int i = tid; i < G; i += kCsThreads) a.delta[nfp + i] = bd ? 0.0 : rhs[i];
@@ -717,6 +736,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       }
     }
   }
+  if (prof) { const long long t = clock64(); a.prof[55] += static_cast<unsigned long long>(t - dt0); }
   mark(kCsProfDense);
   grid.sync();
   // ------------------------------------------------------------ back-substitution, top-down; every node's frame is

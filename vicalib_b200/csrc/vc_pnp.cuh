@@ -234,8 +234,9 @@ __device__ inline void lm_system(const double R[9], const double t[3], const dou
     c += r0 * r0 + r1 * r1;
     // J = dpi * [I | -[p]x],  dpi = [iz 0 -px iz^2; 0 iz -py iz^2]
     const double d02 = -px * iz * iz, d12 = -py * iz * iz;
-    const double J0[6] = {iz, 0.0, d02, -d02 * py, iz * pz + d02 * px, -iz * py};
-    const double J1[6] = {0.0, iz, d12, -iz * pz - d12 * py, d12 * px, iz * px};
+    // rows of dpi * [I | -[p]x] with -[p]x = [0 pz -py; -pz 0 px; py -px 0]
+    const double J0[6] = {iz, 0.0, d02, d02 * py, iz * pz - d02 * px, -iz * py};
+    const double J1[6] = {0.0, iz, d12, -iz * pz + d12 * py, -d12 * px, iz * px};
     int k = 0;
 #pragma unroll
     for (int p = 0; p < 6; ++p) {

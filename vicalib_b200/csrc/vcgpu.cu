@@ -894,20 +894,26 @@ extern "C" int vcgpu_get_covariance(vcgpu_handle* h, double* cov) {
   std::vector<double> mask;
   fill_mask(h, &mask);
   const Blocks& b = h->blk[h->cur];
-  std::vector<double> gf0(nfp), gc0(G), ones(np, 1.0), D2(np, 0.0), col(G, 0.0), x(np);
+  std::vector<double> gf0(nfp), gc0(G), D2(np, 0.0), col(G, 0.0), x(np);
   CUDA_TRY(h, cudaMemcpyAsync(gf0.data(), b.gf, nfp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(gc0.data(), b.gc, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   for (int k = 0; k < G; ++k) D2[nfp + k] = mask[k] != 0.0 ? 0.0 : 1.0;  // constant columns are empty: keep the system definite
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_scale, ones.data(), np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // Jacobi-scaled like the trust-region steps (focal lengths next to distortion coefficients and a time offset: the raw
+  // J^T J does not survive an unpivoted Cholesky): cov = S (S H S)^-1 S
+  jacobi_scale_kernel<<<static_cast<int>((np + 255) / 256), 256, 0, h->stream>>>(dp, h->blk[0], h->blk[1], h->d_ctl, h->d_scale, nullptr);
+  ++h->launches;
+  std::vector<double> sc(G);
+  CUDA_TRY(h, cudaMemcpyAsync(sc.data(), h->d_scale + nfp, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_scale + np, D2.data(), np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(b.gf, 0, nfp * sizeof(double), h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   std::fill(cov, cov + static_cast<size_t>(G) * G, 0.0);
   int rc = VCGPU_OK;
   for (int j = 0; j < G && rc == VCGPU_OK; ++j) {
     if (mask[j] == 0.0) continue;
     std::fill(col.begin(), col.end(), 0.0);
-    col[j] = -1.0;  // the solver returns x with H x = -g
+    col[j] = -1.0;  // the solver forms the right-hand side -g_c * scale and returns the scaled solution
     CUDA_TRY(h, cudaMemcpyAsync(b.gc, col.data(), G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->d_scalars + kScNotPD, 0, sizeof(double), h->stream));
     rc = solve_and_update(h, h->d_scale + np, false);
@@ -915,7 +921,7 @@ extern "C" int vcgpu_get_covariance(vcgpu_handle* h, double* cov) {
     CUDA_TRY(h, cudaMemcpyAsync(x.data(), h->d_delta, np * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     rc = read_scalars(h);
     if (rc == VCGPU_OK && h->h_scalars[kScNotPD] > 0) rc = fail(h, VCGPU_ERR_NUMERIC, "covariance: J^T J is singular at the current state");
-    for (int i = 0; i < G; ++i) cov[static_cast<size_t>(i) * G + j] = mask[i] != 0.0 ? x[nfp + i] : 0.0;
+    for (int i = 0; i < G; ++i) cov[static_cast<size_t>(i) * G + j] = mask[i] != 0.0 ? sc[i] * x[nfp + i] : 0.0;
   }
   // put the gradient back; the Jacobi scale is recomputed by the next solve
   CUDA_TRY(h, cudaMemcpyAsync(b.gf, gf0.data(), nfp * sizeof(double), cudaMemcpyHostToDevice, h->stream));
