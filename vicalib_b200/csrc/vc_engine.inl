@@ -154,6 +154,7 @@ static int imu_mega_solve(vcgpu_handle* h, const double* D2x, bool do_update) {
   ca.Spart = h->d_Spart; ca.Ssum = d->Ssum; ca.delta = h->d_delta; ca.scalars = h->d_scalars;
   ca.state[0] = h->d_state[0]; ca.state[1] = h->d_state[1]; ca.step_part = h->d_red; ca.do_update = do_update ? 1 : 0;
   ca.prof = (h->phase_clocks || h->profiling) ? h->d_prof2 : nullptr;
+  ca.narrow_ok = std::getenv("VCGPU_NO_NARROW") ? 0 : 1;
   void* args[] = {&ca};
   CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chain_solve_kernel), dim3(h->imu_mega_grid), dim3(kCsThreads), args,
                                           chain_solve_smem_doubles(dp.G) * sizeof(double), h->stream));

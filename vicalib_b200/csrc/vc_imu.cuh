@@ -145,7 +145,7 @@ __device__ __forceinline__ void imu_eval_interval(const A& a, int k, int lane, c
     for (int j = 0; j < 9; ++j) rk[j] = rw[j].a * sc;
     a.cost[k] = cost;
   }
-  const double m = col >= 18 ? a.mask[col - 18] : 1.0;
+  const double m = (col >= 18 && col < 33) ? a.mask[col - 18] : 1.0;  // lanes 30, 31 carry no column
   if (lane < 30) {
 #pragma unroll
     for (int j = 0; j < 9; ++j) Jk[j * 33 + col] = rw[j].v * sc * m;

@@ -50,6 +50,7 @@ struct ChainSolveArgs {
   double* state[2];
   double* step_part;            // [grid + 1][4]
   int do_update;                // 1: trial state + step statistics
+  int narrow_ok;                // 1: levels with fewer chunks than CTAs run one chunk per CTA (0: A/B switch)
   unsigned long long* prof;     // [kCsProfCount] ns per phase (CTA 0) or null
 };
 
@@ -118,9 +119,16 @@ __device__ __forceinline__ double src_g(const NodeSrc& s, int64_t p, int e) {
 // Same algorithm as chain_eliminate_kernel (vc_chain.cuh); here every global load of the chunk is issued in one
 // round up front, the 9 x 9 pivots are factored right-looking with rsqrt, and the group's Schur accumulator Sacc
 // lives on across chunks and levels.
-// ITE: compile-time bound of the FD x G element loop (ceil(FD * G / 128)): sizes the register batch of the E loads
-template <int FD, int ITE>
-__device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLevel L, const ChainLevel nxt, int G, int j, double* sm,
+// NT: threads working on the chunk — a group of 128 (two chunks per CTA in flight: the wide levels) or the whole CTA of
+// 256 (levels with fewer chunks than CTAs, where the other group would idle).  ITE: compile-time bound of the FD x G
+// element loop (>= ceil(FD * G / NT)): sizes the register batch of the E loads
+template <int NT>
+__device__ __forceinline__ void gsync(int grp) {
+  if (NT == kCsThreads) __syncthreads();
+  else group_sync(grp);
+}
+template <int FD, int NT, int ITE>
+__device__ __forceinline__ void chain_eliminate_chunk(const NodeSrc& src, const ChainLevel L, const ChainLevel nxt, int G, int j, double* sm,
                                              int tid, int grp, int* bad, unsigned long long* dbg = nullptr) {
   // dbg: cycle counts of the chunk's phases (measurement hook: phase clocks [40..51], one group)
   long long dbg_t = dbg ? clock64() : 0;
@@ -131,7 +139,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       dbg_t = t;
     }
   };
-  constexpr int c = kCsChunk, NT = kCsGroup;
+  constexpr int c = kCsChunk;
   const int NS = G * G + G;
   const int w = 2 * FD + G + 1, VW = FD + w;
   const int oL = FD, oR = 2 * FD, oE = 3 * FD, og = 3 * FD + G;  // column offsets inside a V row
@@ -151,7 +159,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
   const int m = min(c - 1, n_eff - 1 - s);
   const int rIdx = s + m + 1;
   const int jr = toGhost ? nsep : j + 1;
-  group_sync(grp);  // the previous chunk of this group is done with the workspace
+  gsync<NT>(grp);  // the previous chunk of this group is done with the workspace
   tick(0);
   // ---- global loads, batched: every load of the chunk is in flight before the first one is used (a loop that loads,
   // scales and stores element by element pays one memory round trip per iteration — measured: half of a chunk's time).
@@ -210,7 +218,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       vg = lvl0 ? src.b.gf[off] : L.g[off];
       if (!lvl0 && L.addg) vg2 = L.addg[off];
     }
-    if (lvl0) group_sync(grp);  // the scales are in shared memory
+    if (lvl0) gsync<NT>(grp);  // the scales are in shared memory
     tick(1);
     // ---- scale / damp / add, and park everything in shared memory
 #pragma unroll
@@ -257,7 +265,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
         adv2(r, q, G, NT);
       }
     }
-    group_sync(grp);  // everybody has read the scales: Eo may be overwritten
+    gsync<NT>(grp);  // everybody has read the scales: Eo may be overwritten
     tick(2);
 #pragma unroll
     for (int nd = 0; nd < kMaxNodes; ++nd) {
@@ -278,7 +286,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       }
     }
   }
-  group_sync(grp);
+  gsync<NT>(grp);
   tick(3);
   // couplings of the interior nodes' right-hand sides, from the staged U blocks
   for (int i = 0; i < m; ++i) {
@@ -293,7 +301,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       Vi[r * VW + oR + q] = (lastI && hasR) ? unext : 0.0;
     }
   }
-  group_sync(grp);
+  gsync<NT>(grp);
   tick(4);
   // ---- forward sweep
   for (int i = 0; i < m; ++i) {
@@ -310,7 +318,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
         if (q < FD) Api[r * FD + q] -= sum;
         else Vi[r * VW + q] -= sum;
       }
-      group_sync(grp);
+      gsync<NT>(grp);
     }
     if (tid < VW) {
       // every column-solving thread factors the FD x FD pivot in registers (no serial section, no barrier):
@@ -354,7 +362,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
 #pragma unroll
       for (int ii = 0; ii < FD; ++ii) Vi[ii * VW + q] = x[ii];
     }
-    group_sync(grp);
+    gsync<NT>(grp);
   }
   tick(5);
   // ---- backward sweep: X_i = V_R(i) - V_U(i) X_{i+1}
@@ -368,7 +376,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
       for (int k = 0; k < FD; ++k) sum += Vi[r * VW + k] * Vn[k * VW + q];
       Vi[r * VW + q] -= sum;
     }
-    group_sync(grp);
+    gsync<NT>(grp);
   }
   tick(6);
   // ---- store Z, accumulate the Schur terms: S += E_i^T X_i[E], rhs += E_i^T X_i[g]
@@ -457,7 +465,7 @@ __device__ inline void chain_eliminate_chunk(const NodeSrc& src, const ChainLeve
     for (int e = tid; e < FD; e += NT) nxt.g[static_cast<int64_t>(jr) * FD + e] = src_g<FD>(src, rIdx, e);
     if (tid == 0) nxt.orig[jr] = src.L ? L.orig[rIdx] : rIdx;
   }
-  group_sync(grp);
+  gsync<NT>(grp);
   for (int e = tid; e < FD * FD; e += NT) {
     nxt.A[static_cast<int64_t>(j) * FD * FD + e] = Al[e];
     if (j == 0) { nxt.U[e] = 0.0; nxt.addA[e] = 0.0; }
@@ -551,13 +559,22 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     src.L = l > 0 ? &a.lev[l] : nullptr;
     src.b = b; src.scale = a.scale; src.D2x = a.D2x; src.rinv = rinv; src.G = G; src.nf = nf;
     const int nsep = a.lev[l + 1].n - a.dp.ghost;
-    const int ite = (FD * G + kCsGroup - 1) / kCsGroup;
     const ChainLevel Lc = a.lev[l], Ln = a.lev[l + 1];
-    unsigned long long* dbg = (a.prof && gid == 0 && l == 1) ? a.prof + 40 : nullptr;
-    for (int j = gid; j < nsep; j += n_groups) {
-      if (ite <= 3) chain_eliminate_chunk<FD, 3>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp], dbg);
-      else if (ite <= 5) chain_eliminate_chunk<FD, 5>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp]);
-      else chain_eliminate_chunk<FD, 8>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp]);
+    if (nsep > nb || !a.narrow_ok) {  // wide level: two chunks per CTA in flight
+      const int ite = (FD * G + kCsGroup - 1) / kCsGroup;
+      for (int j = gid; j < nsep; j += n_groups) {
+        if (ite <= 3) chain_eliminate_chunk<FD, kCsGroup, 3>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp], nullptr);
+        else if (ite <= 5) chain_eliminate_chunk<FD, kCsGroup, 5>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp], nullptr);
+        else chain_eliminate_chunk<FD, kCsGroup, 8>(src, Lc, Ln, G, j, gsm, gtid, grp, &bad_s[grp], nullptr);
+      }
+    } else {          // narrow level: the whole CTA on one chunk (group 0's workspace and Schur accumulator)
+      const int ite = (FD * G + kCsThreads - 1) / kCsThreads;
+      unsigned long long* dbg = (a.prof && bid == 0 && l == 1) ? a.prof + 40 : nullptr;
+      for (int j = bid; j < nsep; j += nb) {
+        if (ite <= 3) chain_eliminate_chunk<FD, kCsThreads, 3>(src, Lc, Ln, G, j, smem, tid, 0, &bad_s[0], dbg);
+        else chain_eliminate_chunk<FD, kCsThreads, 5>(src, Lc, Ln, G, j, smem, tid, 0, &bad_s[0], dbg);
+      }
+      __syncthreads();
     }
     if (l + 2 == a.n_levels) {  // last level: publish this group's Schur partial
       group_sync(grp);
@@ -783,13 +800,31 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
           for (int rr = 1; rr < FD; ++rr) v = lane == rr ? d[rr] : v;
           out[lane] = v;
         }
-        if (a.do_update && lane == 0) chain_update_frame(a, b, rinv, op, d, acc);
       }
       mark(kCsProfBacksub + (a.n_levels - 2 - l));
-      if (l > 0) grid.sync();
+      grid.sync();
     }
   }
   if (!a.do_update) return;
+  // ------------------------------------------------------------ x (+) step of every frame, one thread each (the top
+  // nodes' frames were done with the dense solve); a serial tail per node inside the level loop above cost more than
+  // this one barrier
+  {
+    const ChainLevel top = a.lev[a.n_levels - 1];
+    for (int f = bid * kCsThreads + tid; f < nf; f += nb * kCsThreads) {
+      bool is_top = false;
+      if (a.n_levels > 1) {
+        for (int t = 0; t < top.n; ++t) is_top = is_top || (top.ghost ? top.orig[t] : t << (2 * (a.n_levels - 1))) == f;
+      } else {
+        is_top = true;
+      }
+      if (is_top) continue;
+      double d[FD];
+#pragma unroll
+      for (int r = 0; r < FD; ++r) d[r] = __ldcg(a.delta + static_cast<int64_t>(f) * FD + r);
+      chain_update_frame(a, b, rinv, f, d, acc);
+    }
+  }
   // ------------------------------------------------------------ step statistics of this CTA
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
