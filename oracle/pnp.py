@@ -194,7 +194,8 @@ def pnp_planar(model, intr, pix, pw, robust_its=0, robust_tol=0.0, view=0):
             s = _sample4(view, it, n)
             H = homography(XY[s], xy[s])
             q = (H @ np.c_[XY, np.ones(n)].T).T
-            e = np.sqrt(((q[:, :2] / q[:, 2:3] - xy) ** 2).sum(1))
+            with np.errstate(divide="ignore", invalid="ignore"):  # a degenerate sample maps points to infinity
+                e = np.sqrt(((q[:, :2] / q[:, 2:3] - xy) ** 2).sum(1))
             inl = e < robust_tol
             if inl.sum() > best:
                 best, use = int(inl.sum()), inl

@@ -168,7 +168,9 @@ def test_staged_flow_matches_oracle_stage_machine(tmp_path, dup, lm):
     # (intrinsics above, rotation, time offset) agree much tighter
     assert np.allclose(out["T_ck0"][:4], st["q_ck"][0], atol=1e-6)
     assert np.allclose(out["T_ck0"][4:], st["p_ck"][0], atol=2e-5)
-    assert np.allclose(out["biases"], st["b"], atol=2e-5)
+    assert np.allclose(out["biases"][:3], st["b"][:3], atol=2e-6)  # gyro bias: well determined
+    # accelerometer bias (~0.5 m/s^2 here) trades against gravity direction and lever arm over 0.8 s: 1e-4 of its size
+    assert np.allclose(out["biases"][3:], st["b"][3:], atol=1e-4)
     assert np.allclose(out["scale"], st["sf"], atol=2e-5)
     assert abs(out["ts"] - st["ts"]) < 1e-7
     assert out["rmse0"] < 0.25
