@@ -99,15 +99,27 @@ static int eval_reproj(vcgpu_handle* h, int which, bool jac, bool apply_loss, co
   return VCGPU_OK;
 }
 
-// ------------------------------------------------------------------ persistent inertial kernels (one GPU)
-// chain_solve_kernel + eval_mega_kernel (vc_imu_mega.cuh, vc_imu_eval_mega.cuh): two cooperative launches per iteration
+// ------------------------------------------------------------------ persistent inertial kernels
+// chain_solve_kernel + eval_mega_kernel (vc_imu_mega.cuh, vc_imu_eval_mega.cuh): two cooperative launches per iteration.
+// Frame-sharded runs use them too when the ranks' totals buffers are mapped (vcgpu_comm_init): the two reductions of
+// an iteration then go through the in-kernel exchange (vc_xchg.cuh) instead of NCCL launches between kernels.
 static bool imu_mega_applies(const vcgpu_handle* h) {
-  return h->imu_mega_ok && h->dp.inertial && h->nranks == 1 && !h->materialize && !h->multi_launch;
+  return h->imu_mega_ok && h->dp.inertial && (h->nranks == 1 || h->xchg_ready) && !h->materialize && !h->multi_launch;
 }
+static void imu_mega_xchg(const vcgpu_handle* h, Xchg* x, size_t off, int stride, unsigned tag) {
+  x->rank = h->rank; x->nranks = h->nranks; x->off = off; x->stride = stride; x->tag = tag; x->ctl = h->d_ctl;
+  for (int r = 0; r < kMaxRanks; ++r) x->buf[r] = reinterpret_cast<unsigned long long*>(h->xchg_peer[r]);
+}
+static int imu_mega_dense_stride(const DevProblem& dp) { return dp.G * dp.G + dp.G + 2 * chain_top_block(dp.G); }
+static int imu_mega_eval_stride(const DevProblem& dp) { return dp.G * dp.G + dp.G + 8 + 4 * 9; }
 static int imu_mega_prepare(vcgpu_handle* h) {
   const DevProblem& dp = h->dp;
   h->imu_mega_ok = false;
-  if (!dp.inertial || h->nranks > 1) return VCGPU_OK;
+  if (!dp.inertial || (h->nranks > 1 && !h->xchg_ready)) return VCGPU_OK;
+  if (h->nranks > 1) {  // the exchange regions must hold [2 parities][ranks][stride] entries of two words
+    const size_t nd = 4 * static_cast<size_t>(h->nranks) * imu_mega_dense_stride(dp), ne = 4 * static_cast<size_t>(h->nranks) * imu_mega_eval_stride(dp);
+    if (kXchgImuDenseOff + nd > kXchgImuEvalOff || kXchgImuEvalOff + ne > kXchgWords) return VCGPU_OK;
+  }
   if (h->dev_sms == 0) {
     int coop = 0, smem_optin = 0, sms = 0;
     CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
@@ -116,7 +128,7 @@ static int imu_mega_prepare(vcgpu_handle* h) {
     h->dev_sms = sms;
     h->dev_smem_optin = coop ? smem_optin : 0;
   }
-  const size_t sm_solve = chain_solve_smem_doubles(dp.G) * sizeof(double);
+  const size_t sm_solve = chain_solve_smem_doubles(dp.G, h->nranks) * sizeof(double);
   const size_t sm_eval = eval_mega_smem_doubles(dp.G) * sizeof(double);
   vc::ImuDev* d = imu_dev(h);
   if (h->dev_smem_optin == 0 || sm_solve > static_cast<size_t>(h->dev_smem_optin) || sm_eval > static_cast<size_t>(h->dev_smem_optin) ||
@@ -137,6 +149,7 @@ static int imu_mega_prepare(vcgpu_handle* h) {
   VC_TRY(dev_alloc(h, &h->d_red, 4 * (std::max<size_t>(dp.n_frames, grid) + 2)));
   VC_TRY(dev_alloc(h, &h->d_prof2, kImuProfSlots));
   CUDA_TRY(h, cudaMemsetAsync(h->d_prof2, 0, kImuProfSlots * sizeof(unsigned long long), h->stream));
+  if (h->nranks > 1) VC_TRY(dev_alloc(h, &h->d_dsys, NS + static_cast<size_t>(h->nranks) * chain_top_block(dp.G)));
   VC_TRY(dev_alloc(h, &d->d_levels, d->levels.size()));
   CUDA_TRY(h, cudaMemcpyAsync(d->d_levels, d->levels.data(), d->levels.size() * sizeof(vc::ChainLevel), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -155,9 +168,12 @@ static int imu_mega_solve(vcgpu_handle* h, const double* D2x, bool do_update) {
   ca.state[0] = h->d_state[0]; ca.state[1] = h->d_state[1]; ca.step_part = h->d_red; ca.do_update = do_update ? 1 : 0;
   ca.prof = (h->phase_clocks || h->profiling) ? h->d_prof2 : nullptr;
   ca.narrow_ok = std::getenv("VCGPU_NO_NARROW") ? 0 : 1;
+  imu_mega_xchg(h, &ca.x, kXchgImuDenseOff, imu_mega_dense_stride(dp), h->nranks > 1 ? ++h->xchg_tag_dense : 0u);
+  ca.sepdiag = h->nranks > 1 ? h->d_sep : nullptr;
+  ca.dsys = h->d_dsys;
   void* args[] = {&ca};
   CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chain_solve_kernel), dim3(h->imu_mega_grid), dim3(kCsThreads), args,
-                                          chain_solve_smem_doubles(dp.G) * sizeof(double), h->stream));
+                                          chain_solve_smem_doubles(dp.G, h->nranks) * sizeof(double), h->stream));
   ++h->launches;
   if (do_update) h->n_step_part = h->imu_mega_grid + 1;
   return VCGPU_OK;
@@ -178,8 +194,11 @@ static int imu_mega_eval(vcgpu_handle* h, int which, bool with_step, int decide_
   ea.buf = d->buf; ea.ftime = d->ftime; ea.wsqrt = h->d_wsqrt; ea.imu_r = h->d_imu_r; ea.imu_J = h->d_imu_J;
   ea.imu_cost = d->cost; ea.imuCg = d->Cg; ea.sigma_g = h->sigma_g; ea.sigma_a = h->sigma_a;
   ea.Cpart = h->d_Cpart; ea.red_part = h->d_red_part;
-  ea.step_part = with_step ? h->d_red : nullptr; ea.n_step_part = h->n_step_part;
+  // the last step_part slot is the globals' share: counted once (rank 0) in a sharded run
+  ea.step_part = with_step ? h->d_red : nullptr; ea.n_step_part = h->n_step_part - (h->rank == 0 ? 0 : 1);
   ea.scalars = h->d_scalars; ea.counter = h->d_counter + 2;
+  imu_mega_xchg(h, &ea.x, kXchgImuEvalOff, imu_mega_eval_stride(dp), h->nranks > 1 ? ++h->xchg_tag_eval : 0u);
+  ea.sep_out = h->d_sep;
   ea.prof = (h->phase_clocks || h->profiling) ? h->d_prof2 + 32 : nullptr;
   void* args[] = {&ea};
   CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(eval_mega_kernel), dim3(h->imu_mega_grid), dim3(kEvThreads), args,

@@ -26,6 +26,7 @@
 #include "vc_imu.cuh"
 #include "vc_imu_mega.cuh"
 #include "vc_imu_weights.cuh"
+#include "vc_xchg.cuh"
 
 namespace vc {
 
@@ -56,6 +57,10 @@ struct EvalMegaArgs {
   int n_step_part;
   double* scalars;
   unsigned* counter;   // task queue
+  // frame-sharded run (x.nranks > 1): global blocks, scalars and the separator frames' diagonal / gradient are summed
+  // over the ranks through the in-kernel exchange before the decision
+  Xchg x;
+  double* sep_out;     // [2][ranks * 9] summed diag(B) | gradient of every rank's first frame
   unsigned long long* prof;  // [kEvProfCount] or null
 };
 
@@ -285,7 +290,10 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
   // ------------------------------------------------------------ R1: slice partials
   RedFinArgs ra;
   ra.ctl = a.ctl; ra.which = a.which; ra.decide_mode = a.decide_mode; ra.multi = 0; ra.level1_only = 1;
-  ra.gf_skip_below = 0; ra.gf_skip_from = static_cast<int64_t>(nf) * a.dp.fd;
+  const bool sharded = a.x.nranks > 1;
+  // sharded: the separator frames' (first frame, ghost) gradients are normed after they have been summed
+  ra.gf_skip_below = sharded ? a.dp.fd : 0;
+  ra.gf_skip_from = static_cast<int64_t>(sharded ? a.dp.n_own : nf) * a.dp.fd;
   ra.Cg = a.Cg; ra.imuCg = a.imuCg; ra.ni = ni; ra.imu_goff = a.dp.imu_goff; ra.imu_stride = kImuCgStride;
   ra.Cpart = a.Cpart; ra.red_part = a.red_part;
   ra.cost_part = a.cost_part; ra.n_cost_part = nf;
@@ -299,16 +307,22 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
   mark(kEvProfReduce);
   grid.sync();
   // ------------------------------------------------------------ D: scalars + decision (CTA 0)
+  // entries of a rank's slot in the exchange: C | gc (NS), 7 scalars (+ 1 pad), own first frame diag 9 | gradient 9,
+  // ghost diag 9 | gradient 9
+  constexpr int kSepFd = 9;
+  const int eSc = NS, eSep = NS + 8;
   if (bid == 0) {
     double w[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int b = tid; b < nb; b += kEvThreads) {
       for (int q = 0; q < 6; ++q) w[q] += __ldcg(a.red_part + 8 * b + q);
       w[6] = fmax(w[6], __ldcg(a.red_part + 8 * b + 6));
     }
-    for (int k = tid; k < G; k += kEvThreads) {
-      const double v = __ldcg(bt.gc + k);
-      w[1] += v * v;
-      w[6] = fmax(w[6], fabs(v));
+    if (!sharded) {
+      for (int k = tid; k < G; k += kEvThreads) {
+        const double v = __ldcg(bt.gc + k);
+        w[1] += v * v;
+        w[6] = fmax(w[6], fabs(v));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -326,19 +340,98 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
         for (int q = 0; q < 6; ++q) t[q] += shr[ww][q];
         t[6] = fmax(t[6], shr[ww][6]);
       }
-      *bt.cost = t[0];
-      a.scalars[kScCost] = t[0];
-      a.scalars[kScGmax] = t[6];
-      a.scalars[kScGnorm2] = t[1];
-      if (a.step_part) {
-        a.scalars[kScDotG] = t[2];
-        a.scalars[kScDotD] = t[3];
-        a.scalars[kScStep2] = t[4];
-        a.scalars[kScXnorm2] = t[5];
+      if (sharded) {  // this rank's share; the totals are formed below
+        for (int q = 0; q < 7; ++q) xchg_put(a.x, eSc + q, t[q]);
+      } else {
+        *bt.cost = t[0];
+        a.scalars[kScCost] = t[0];
+        a.scalars[kScGmax] = t[6];
+        a.scalars[kScGnorm2] = t[1];
+        if (a.step_part) {
+          a.scalars[kScDotG] = t[2];
+          a.scalars[kScDotD] = t[3];
+          a.scalars[kScStep2] = t[4];
+          a.scalars[kScXnorm2] = t[5];
+        }
+        if (a.decide_mode >= 0) decide_step(a.ctl, a.scalars, a.decide_mode);
+        *a.counter = 0u;  // the task queue of the next launch
+        __threadfence();
       }
-      if (a.decide_mode >= 0) decide_step(a.ctl, a.scalars, a.decide_mode);
-      *a.counter = 0u;  // the task queue of the next launch
-      __threadfence();
+    }
+  }
+  if (sharded) {
+    // publish this rank's global blocks and separator entries; one reader per entry sums the ranks (in order)
+    const int nsep = (1 + a.dp.ghost) * 2 * kSepFd;
+    for (int e = bid * kEvThreads + tid; e < NS + nsep; e += nb * kEvThreads) {
+      if (e < NS) {
+        xchg_put(a.x, e, __ldcg(bt.C + e));  // C | gc are contiguous
+      } else {
+        const int o = e - NS, t = o / (2 * kSepFd), q = o - t * 2 * kSepFd;
+        const int64_t f = t == 0 ? 0 : nf - 1;
+        const double v = q < kSepFd ? __ldcg(bt.B + (f * kSepFd + q) * kSepFd + q) : __ldcg(bt.gf + f * kSepFd + (q - kSepFd));
+        xchg_put(a.x, eSep + o, v);
+      }
+    }
+    const int nslot = a.x.nranks * 2 * kSepFd;
+    for (int e = bid * kEvThreads + tid; e < NS + nslot; e += nb * kEvThreads) {
+      double v = 0.0;
+      if (e < NS) {
+        for (int r = 0; r < a.x.nranks; ++r) v += xchg_get(a.x, r, e);
+        bt.C[e] = v;
+      } else {
+        const int o = e - NS, k = o / (2 * kSepFd), q = o - k * 2 * kSepFd;  // slot k = rank k's first frame
+        if (k > 0) v = xchg_get(a.x, k - 1, eSep + 2 * kSepFd + q);          // rank k-1's ghost copy
+        v += xchg_get(a.x, k, eSep + q);
+        a.sep_out[(q < kSepFd ? 0 : a.x.nranks * kSepFd) + k * kSepFd + (q < kSepFd ? q : q - kSepFd)] = v;
+      }
+    }
+    grid.sync();
+    if (bid == 0) {
+      double* tot = &shr[0][0];  // [ranks][8] the ranks' scalars
+      if (tid < a.x.nranks * 7) tot[(tid / 7) * 8 + tid % 7] = xchg_get(a.x, tid / 7, eSc + tid % 7);
+      double gm = 0.0, g2 = 0.0;
+      for (int k = tid; k < G; k += kEvThreads) {
+        const double v = __ldcg(bt.gc + k);
+        g2 += v * v;
+        gm = fmax(gm, fabs(v));
+      }
+      for (int k = tid; k < a.x.nranks * kSepFd; k += kEvThreads) {
+        const double v = __ldcg(a.sep_out + a.x.nranks * kSepFd + k);
+        g2 += v * v;
+        gm = fmax(gm, fabs(v));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        g2 += __shfl_down_sync(0xffffffffu, g2, o);
+        gm = fmax(gm, __shfl_down_sync(0xffffffffu, gm, o));
+      }
+      __shared__ double gsh[kEvWarps][2];
+      if (lane == 0) { gsh[warp][0] = g2; gsh[warp][1] = gm; }
+      __syncthreads();
+      if (tid == 0) {
+        double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r < a.x.nranks; ++r) {
+          for (int q = 0; q < 6; ++q) t[q] += tot[r * 8 + q];
+          t[6] = fmax(t[6], tot[r * 8 + 6]);
+        }
+        for (int ww = 0; ww < kEvWarps; ++ww) {
+          t[1] += gsh[ww][0];
+          t[6] = fmax(t[6], gsh[ww][1]);
+        }
+        *bt.cost = t[0];
+        a.scalars[kScCost] = t[0];
+        a.scalars[kScGmax] = t[6];
+        a.scalars[kScGnorm2] = t[1];
+        if (a.step_part) {
+          a.scalars[kScDotG] = t[2];
+          a.scalars[kScDotD] = t[3];
+          a.scalars[kScStep2] = t[4];
+          a.scalars[kScXnorm2] = t[5];
+        }
+        if (a.decide_mode >= 0) decide_step(a.ctl, a.scalars, a.decide_mode);
+        *a.counter = 0u;
+        __threadfence();
+      }
     }
   }
   mark(kEvProfDecide);

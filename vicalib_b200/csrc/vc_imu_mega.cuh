@@ -24,6 +24,7 @@
 #include "vc_chain.cuh"
 #include "vc_kernels.cuh"
 #include "vc_mega.cuh"
+#include "vc_xchg.cuh"
 
 namespace vc {
 
@@ -51,6 +52,11 @@ struct ChainSolveArgs {
   double* step_part;            // [grid + 1][4]
   int do_update;                // 1: trial state + step statistics
   int narrow_ok;                // 1: levels with fewer chunks than CTAs run one chunk per CTA (0: A/B switch)
+  // frame-sharded run (x.nranks > 1): every rank reduces its chain to its first frame (+ the ghost = the next rank's
+  // first frame); the partial [globals | one slot per rank] systems meet through the in-kernel exchange
+  Xchg x;
+  const double* sepdiag;        // [ranks][9] diag(B) of the ranks' first frames summed over both owners, or null
+  double* dsys;                 // [NS + ranks * kTopBlock] summed dense system in block form
   unsigned long long* prof;     // [kCsProfCount] ns per phase (CTA 0) or null
 };
 
@@ -59,9 +65,11 @@ __host__ __device__ inline size_t chain_group_doubles(int G) {
   const size_t NS = static_cast<size_t>(G) * G + G, VW = FD + 2 * FD + G + 1;
   return NS + FD * FD + FD * G + FD + (2 * (kCsChunk - 1) + 1) * FD * FD + (kCsChunk - 1) * FD * VW + (kCsChunk - 1) * FD * G;
 }
-__host__ __device__ inline size_t chain_solve_smem_doubles(int G) {
+// a top node's blocks in the exchanged dense system: A 81 | U 81 (coupling to the previous slot) | E 9G | -g 9
+__host__ __device__ inline int chain_top_block(int G) { return 2 * 81 + 9 * G + 9; }
+__host__ __device__ inline size_t chain_solve_smem_doubles(int G, int nranks = 1) {
   const size_t grp = kCsGroups * chain_group_doubles(G);
-  const size_t N = static_cast<size_t>(G) + kCsChunk * 9;
+  const size_t N = static_cast<size_t>(G) + (nranks > kCsChunk ? nranks : kCsChunk) * 9;
   const size_t dense = N * N + 2 * N;
   return (grp > dense ? grp : dense) + 16;
 }
@@ -85,6 +93,8 @@ struct NodeSrc {
   const double* D2x;
   double rinv;
   int G, nf;
+  const double* sepdiag;  // sharded: summed diagonal of the ranks' first frames (damping of frame 0; the ghost is damped by its owner)
+  int rank, ghost;
 };
 template <int FD>
 __device__ __forceinline__ double src_A(const NodeSrc& s, int64_t p, int e) {
@@ -93,7 +103,13 @@ __device__ __forceinline__ double src_A(const NodeSrc& s, int64_t p, int e) {
   const double* sf = s.scale + p * FD;
   const double bij = s.b.B[p * FD * FD + e];
   double v = bij * sf[r] * sf[c];
-  if (r == c) v += s.D2x ? s.D2x[p * FD + r] : lm_damp(bij, sf[r], s.rinv);
+  if (r == c) {
+    const bool is_ghost = s.ghost && p == s.nf - 1;
+    if (is_ghost) ;  // damped once, by the rank that owns the frame
+    else if (s.D2x) v += s.D2x[p * FD + r];
+    else if (s.sepdiag && p == 0) v += lm_damp(s.sepdiag[s.rank * FD + r], sf[r], s.rinv);
+    else v += lm_damp(bij, sf[r], s.rinv);
+  }
   return v;
 }
 template <int FD>
@@ -230,7 +246,11 @@ __device__ __forceinline__ void chain_eliminate_chunk(const NodeSrc& src, const 
         if (lvl0) {
           const double sr = sS[(nd + 1) * FD + r], sq = sS[(nd + 1) * FD + q];
           v = vA[it] * sr * sq;
-          if (r == q) v += src.D2x ? vA2[it] : lm_damp(vA[it], sr, src.rinv);
+          if (r == q) {
+            if (src.D2x) v += vA2[it];
+            else if (src.sepdiag && s + nd == 0) v += lm_damp(src.sepdiag[src.rank * FD + r], sr, src.rinv);
+            else v += lm_damp(vA[it], sr, src.rinv);
+          }
         } else {
           v = vA[it] + vA2[it];
         }
@@ -491,11 +511,18 @@ __device__ __forceinline__ void chain_update_frame(const ChainSolveArgs& a, cons
   const double* x_cur = a.state[cur];
   double* x_new = a.state[1 - cur];
   double du[FD];
+  // sharded: a rank's first frame is damped from the diagonal summed over both owners; its ghost copy on the previous
+  // rank moves with the same step but is counted (damping term, norms) by the owner only
+  const bool is_ghost = a.dp.ghost && f == a.dp.n_frames - 1;
 #pragma unroll
   for (int r = 0; r < FD; ++r) {
     const int64_t k = static_cast<int64_t>(f) * FD + r;
     const double sc = a.scale[k];
-    const double d2 = a.D2x ? a.D2x[k] : lm_damp(b.B[k * FD + r], sc, rinv);
+    double d2;
+    if (is_ghost) d2 = 0.0;
+    else if (a.D2x) d2 = a.D2x[k];
+    else if (a.sepdiag && f == 0) d2 = lm_damp(a.sepdiag[a.dp.rank * FD + r], sc, rinv);
+    else d2 = lm_damp(b.B[k * FD + r], sc, rinv);
     acc[0] += d[r] * b.gf[k] * sc;
     acc[1] += d[r] * d[r] * d2;
     du[r] = d[r] * sc;
@@ -506,8 +533,10 @@ __device__ __forceinline__ void chain_update_frame(const ChainSolveArgs& a, cons
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
     x_new[7 * static_cast<int64_t>(f) + k] = xo[k];
-    acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
-    acc[3] += xo[k] * xo[k];
+    if (!is_ghost) {
+      acc[2] += (xo[k] - x[k]) * (xo[k] - x[k]);
+      acc[3] += xo[k] * xo[k];
+    }
   }
   const double* v = x_cur + a.dp.off_v + 3 * static_cast<int64_t>(f);
   double* vo = x_new + a.dp.off_v + 3 * static_cast<int64_t>(f);
@@ -515,8 +544,10 @@ __device__ __forceinline__ void chain_update_frame(const ChainSolveArgs& a, cons
   for (int k = 0; k < 3; ++k) {
     const double nv = v[k] + du[6 + k];
     vo[k] = nv;
-    acc[2] += (nv - v[k]) * (nv - v[k]);
-    acc[3] += nv * nv;
+    if (!is_ghost) {
+      acc[2] += (nv - v[k]) * (nv - v[k]);
+      acc[3] += nv * nv;
+    }
   }
 }
 
@@ -558,6 +589,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     NodeSrc src;
     src.L = l > 0 ? &a.lev[l] : nullptr;
     src.b = b; src.scale = a.scale; src.D2x = a.D2x; src.rinv = rinv; src.G = G; src.nf = nf;
+    src.sepdiag = a.sepdiag; src.rank = a.dp.rank; src.ghost = a.dp.ghost;
     const int nsep = a.lev[l + 1].n - a.dp.ghost;
     const ChainLevel Lc = a.lev[l], Ln = a.lev[l + 1];
     if (nsep > nb || !a.narrow_ok) {  // wide level: two chunks per CTA in flight
@@ -589,6 +621,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     const ChainLevel& L = a.lev[0];
     NodeSrc src;
     src.L = nullptr; src.b = b; src.scale = a.scale; src.D2x = a.D2x; src.rinv = rinv; src.G = G; src.nf = nf;
+    src.sepdiag = a.sepdiag; src.rank = a.dp.rank; src.ghost = a.dp.ghost;
     if (bid == 0) {
       for (int f = 0; f < nf; ++f) {
         for (int e = tid; e < FD * FD; e += kCsThreads) {
@@ -608,11 +641,71 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
   mega_reduce_stage1(a.Spart, NS, n_groups, NS, a.Ssum, -1, -1);
   mark(kCsProfReduce);
   grid.sync();
-  // ------------------------------------------------------------ dense solve of [globals | top nodes], every CTA
-  long long dt0 = 0;
-  {
+  // ------------------------------------------------------------ sharded: the ranks' partial systems meet here
+  const bool sharded = a.x.nranks > 1;
+  const int TB = chain_top_block(G);
+  if (sharded) {
     const ChainLevel& top = a.lev[a.n_levels - 1];
-    const int nt = top.n, N = G + nt * FD;
+    const bool add = top.addA != nullptr;
+    const double* sc = a.scale + nfp;
+    const int P = NS + top.n * TB;  // this rank's entries: globals, own first frame (+ the ghost)
+    for (int e = bid * kCsThreads + tid; e < P; e += nb * kCsThreads) {
+      double v;
+      if (e < NS) {
+        const double p = __ldcg(a.Ssum + e);
+        if (e < G * G) {
+          v = -p;
+          if (a.x.rank == 0) {  // the globals' own block joins once
+            const int r = e / G, c = e - r * G;
+            v += b.C[e] * sc[r] * sc[c];
+            if (r == c) v += a.D2x ? a.D2x[nfp + r] : lm_damp(b.C[e], sc[r], rinv);
+          }
+        } else {
+          v = p - (a.x.rank == 0 ? b.gc[e - G * G] * sc[e - G * G] : 0.0);
+        }
+      } else {
+        const int t = (e - NS) / TB, o = (e - NS) - t * TB;
+        if (o < 81) {
+          v = __ldcg(top.A + static_cast<int64_t>(t) * 81 + o) + (add ? __ldcg(top.addA + static_cast<int64_t>(t) * 81 + o) : 0.0);
+        } else if (o < 162) {
+          v = t > 0 ? __ldcg(top.U + static_cast<int64_t>(t) * 81 + (o - 81)) : 0.0;  // H[own first frame, ghost]
+        } else if (o < 162 + FD * G) {
+          const int64_t q = static_cast<int64_t>(t) * FD * G + (o - 162);
+          v = __ldcg(top.E + q) + (add ? __ldcg(top.addE + q) : 0.0);
+        } else {
+          const int64_t q = static_cast<int64_t>(t) * FD + (o - 162 - FD * G);
+          v = -(__ldcg(top.g + q) + (add ? __ldcg(top.addg + q) : 0.0));
+        }
+      }
+      xchg_put(a.x, e, v);
+    }
+    // one reader per entry of the summed system (slot k = rank k's first frame: its own blocks + the ghost blocks of
+    // rank k-1, whose U block is the coupling between slots k-1 and k), ranks in order
+    const int Q = NS + a.x.nranks * TB;
+    for (int e = bid * kCsThreads + tid; e < Q; e += nb * kCsThreads) {
+      double v = 0.0;
+      if (e < NS) {
+        for (int r = 0; r < a.x.nranks; ++r) v += xchg_get(a.x, r, e);
+      } else {
+        const int k = (e - NS) / TB, o = (e - NS) - k * TB;
+        if (o >= 81 && o < 162) {
+          v = k > 0 ? xchg_get(a.x, k - 1, NS + TB + o) : 0.0;
+        } else {
+          if (k > 0) v = xchg_get(a.x, k - 1, NS + TB + o);
+          v += xchg_get(a.x, k, NS + o);
+        }
+      }
+      a.dsys[e] = v;
+    }
+    grid.sync();
+  }
+  // ------------------------------------------------------------ dense solve of [globals | top nodes]: CTA 0 (the step
+  // of the globals and of the top nodes goes through a.delta; everybody waits at the barrier below)
+  long long dt0 = 0;
+  if (bid == 0) {
+    const ChainLevel& top = a.lev[a.n_levels - 1];
+    const int nt = top.n, n_slots = sharded ? a.x.nranks : nt, N = G + n_slots * FD;
+    const int slot0 = sharded ? a.x.rank : 0;  // slot of top node 0
     double* S = smem;         // [N][N] lower triangle; unscaled columns u_ij (L D L^T: L_ij = u_ij / d_j)
     double* rhs = S + N * N;  // row N of the same elimination: u_Nj
     double* wd = rhs + N;     // 1 / d_j
@@ -620,6 +713,35 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     if (tid == 0) bad_dense = 0;
     for (int e = tid; e < N * N + N; e += kCsThreads) S[e] = 0.0;
     __syncthreads();
+    if (sharded) {
+      for (int e = tid; e < NS; e += kCsThreads) {
+        const double v = __ldcg(a.dsys + e);
+        if (e < G * G) S[(e / G) * N + e % G] = v;
+        else rhs[e - G * G] = v;
+      }
+      for (int k = 0; k < n_slots; ++k) {
+        const double* blk = a.dsys + NS + static_cast<int64_t>(k) * TB;
+        const int o = G + k * FD, op = o - FD;
+        for (int e = tid; e < TB; e += kCsThreads) {
+          const double v = __ldcg(blk + e);
+          if (e < 81) {
+            S[(o + e / FD) * N + o + e % FD] = v;
+          } else if (e < 162) {
+            if (k > 0) {
+              const int r = (e - 81) / FD, c = (e - 81) % FD;
+              S[(op + r) * N + o + c] = v;
+              S[(o + c) * N + op + r] = v;
+            }
+          } else if (e < 162 + FD * G) {
+            const int r = (e - 162) / G, c = (e - 162) % G;
+            S[(o + r) * N + c] = v;
+            S[c * N + o + r] = v;
+          } else {
+            rhs[o + e - 162 - FD * G] = v;
+          }
+        }
+      }
+    } else {
     for (int e = tid; e < NS; e += kCsThreads) {
       const double p = __ldcg(a.Ssum + e);
       if (e < G * G) {
@@ -653,6 +775,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       }
       for (int e = tid; e < FD; e += kCsThreads)
         rhs[o + e] = -(__ldcg(top.g + static_cast<int64_t>(t) * FD + e) + (add ? __ldcg(top.addg + static_cast<int64_t>(t) * FD + e) : 0.0));
+    }
     }
     // right-looking L D L^T on the lower triangle, the right-hand side riding along as row N: one barrier per
     // column, 16 x 16 thread tiling of the trailing update.  The reciprocal of the next pivot is taken by the one
@@ -698,17 +821,17 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     }
     __syncthreads();
     if (prof) { const long long t = clock64(); a.prof[54] += static_cast<unsigned long long>(t - dt0); dt0 = t; }
-    if (bid == 0) {
+    {
       const int bd = bad_dense;
       for (int i = tid; i < G; i += kCsThreads) a.delta[nfp + i] = bd ? 0.0 : rhs[i];
       for (int e = tid; e < nt * FD; e += kCsThreads) {
         const int t = e / FD, r = e - t * FD;
-        a.delta[static_cast<int64_t>(a.n_levels > 1 ? top.orig[t] : t) * FD + r] = bd ? 0.0 : rhs[G + t * FD + r];
+        a.delta[static_cast<int64_t>(a.n_levels > 1 ? top.orig[t] : t) * FD + r] = bd ? 0.0 : rhs[G + (slot0 + t) * FD + r];
       }
       if (tid == 0 && bd) a.scalars[kScNotPD] = 1.0;
       if (a.do_update && tid < nt) {  // the top nodes' frames
         double d[FD];
-        for (int r = 0; r < FD; ++r) d[r] = bd ? 0.0 : rhs[G + tid * FD + r];
+        for (int r = 0; r < FD; ++r) d[r] = bd ? 0.0 : rhs[G + (slot0 + tid) * FD + r];
         chain_update_frame(a, b, rinv, a.n_levels > 1 ? top.orig[tid] : tid, d, acc);
       }
       // globals: cameras + IMU parameters (one thread)

@@ -39,14 +39,14 @@ constexpr int kSlabDoubles = kFusedCols * kSlabLd;     // one warp's tile
 constexpr int kWarpDoubles = kSlabDoubles + 48;        // + frame block (36) + frame gradient (6), padded
 constexpr int kGtabMax = 256;
 constexpr int kMegaPartExtra = 8;  // scalars appended to each CTA's partial slot
-// Totals buffer: every rank owns one (4 MiB); in a frame-sharded run (one process per GPU) all ranks of the
+// Totals buffer: every rank owns one (32 MiB, the vision kernel uses the first 4); in a frame-sharded run (one process per GPU) all ranks of the
 // node map all of them (CUDA IPC).  A total is published as two 64-bit words {low half | tag}, {high half | tag}
 // (tag = exchange number): an 8-byte store is single-copy atomic, so a reader that sees both tags has the value —
 // no fence, no flag, no barrier between publishing and reading.  Layout in 64-bit words: Schur totals
 // [2 parities][ranks][NS+8][2] at 0, packed camera blocks [2][ranks][NP+8][2] at kXchgCOff, control words at
 // kXchgCtlOff: exchange counters (S, C), exit word (bit 0: CTA 0 decided to stop, bit 1: a reader timed out).
 constexpr int kMaxRanks = 8;
-constexpr size_t kXchgBytes = 4u << 20;
+constexpr size_t kXchgBytes = 32u << 20;  // the inertial kernels' regions follow the vision kernel's (vc_xchg.cuh)
 constexpr int kXchgCOff = 409600;
 constexpr int kXchgCtlOff = 442368;
 constexpr int kMegaCommFailed = 1000;  // Ctl::done value when a peer never showed up

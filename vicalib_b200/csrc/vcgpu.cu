@@ -219,7 +219,7 @@ extern "C" int vcgpu_destroy(vcgpu_handle* h) {
   dev_free(&h->d_dl); dev_free(&h->d_dl_part); dev_free(&h->d_partS); dev_free(&h->d_partC); dev_free(&h->d_prof); dev_free(&h->d_prof2);
   dev_free(&h->d_imu); dev_free(&h->d_wsqrt); dev_free(&h->d_imu_r); dev_free(&h->d_imu_J);
   imu_free(h);
-  dev_free(&h->d_mg); dev_free(&h->d_sep); dev_free(&h->d_dense);
+  dev_free(&h->d_mg); dev_free(&h->d_sep); dev_free(&h->d_dense); dev_free(&h->d_dsys);
   xchg_release(h);
   if (h->comm) ncclCommDestroy(static_cast<ncclComm_t>(h->comm));
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
