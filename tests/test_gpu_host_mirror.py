@@ -172,7 +172,7 @@ def test_staged_flow_matches_oracle_stage_machine(tmp_path, dup, lm):
     # accelerometer bias (~0.5 m/s^2 here) trades against gravity direction and lever arm over 0.8 s: 1e-4 of its size
     assert np.allclose(out["biases"][3:], st["b"][3:], atol=1e-4)
     assert np.allclose(out["scale"], st["sf"], atol=2e-5)
-    assert abs(out["ts"] - st["ts"]) < 1e-7
+    assert abs(out["ts"] - st["ts"]) < 5e-7  # 0.8 s of motion: the time offset (microseconds here) moves with the valley too
     assert out["rmse0"] < 0.25
     # GetIntegrationPoses (vicalibrator.h:508-533): start pose + one pose per IMU sample inside the first interval + the
     # interpolated end; the integration ends at the second frame up to the IMU residual of the solution

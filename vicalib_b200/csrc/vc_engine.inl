@@ -150,6 +150,10 @@ static int imu_mega_prepare(vcgpu_handle* h) {
   VC_TRY(dev_alloc(h, &h->d_prof2, kImuProfSlots));
   CUDA_TRY(h, cudaMemsetAsync(h->d_prof2, 0, kImuProfSlots * sizeof(unsigned long long), h->stream));
   if (h->nranks > 1) VC_TRY(dev_alloc(h, &h->d_dsys, NS + static_cast<size_t>(h->nranks) * chain_top_block(dp.G)));
+  if (!h->d_csync) {
+    CUDA_TRY(h, cudaMalloc(&h->d_csync, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_csync, 0, 8 * sizeof(unsigned long long), h->stream));
+  }
   VC_TRY(dev_alloc(h, &d->d_levels, d->levels.size()));
   CUDA_TRY(h, cudaMemcpyAsync(d->d_levels, d->levels.data(), d->levels.size() * sizeof(vc::ChainLevel), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -157,7 +161,7 @@ static int imu_mega_prepare(vcgpu_handle* h) {
   h->imu_mega_ok = true;
   return VCGPU_OK;
 }
-static int imu_mega_solve(vcgpu_handle* h, const double* D2x, bool do_update) {
+static int imu_mega_solve(vcgpu_handle* h, const double* D2x, bool do_update, bool deferred_weights = false) {
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
   ChainSolveArgs ca;
@@ -171,6 +175,11 @@ static int imu_mega_solve(vcgpu_handle* h, const double* D2x, bool do_update) {
   imu_mega_xchg(h, &ca.x, kXchgImuDenseOff, imu_mega_dense_stride(dp), h->nranks > 1 ? ++h->xchg_tag_dense : 0u);
   ca.sepdiag = h->nranks > 1 ? h->d_sep : nullptr;
   ca.dsys = h->d_dsys;
+  static const int n_solver_env = std::getenv("VCGPU_N_SOLVER") ? std::atoi(std::getenv("VCGPU_N_SOLVER")) : 16;
+  ca.wts_on = deferred_weights ? 1 : 0; ca.n_solver = n_solver_env;
+  ca.buf = d->buf; ca.ftime = d->ftime; ca.wsqrt = h->d_wsqrt; ca.sigma_g = h->sigma_g; ca.sigma_a = h->sigma_a;
+  const int par = static_cast<int>(h->cs_launches++ & 1u);
+  ca.sync = h->d_csync + 4 * par; ca.sync_next = h->d_csync + 4 * (1 - par);
   void* args[] = {&ca};
   CUDA_TRY(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chain_solve_kernel), dim3(h->imu_mega_grid), dim3(kCsThreads), args,
                                           chain_solve_smem_doubles(dp.G, h->nranks) * sizeof(double), h->stream));
@@ -216,7 +225,8 @@ static int imu_mega_collect_clocks(vcgpu_handle* h, int iters) {
   bool seen[VCGPU_STAGE_COUNT] = {};
   auto add = [&](int stage, unsigned long long v) { h->st_ms[stage] += v * 1e-6; seen[stage] = true; };
   for (int k = 0; k < kCsProfCount; ++k)
-    add(k < kCsProfReduce ? VCGPU_STAGE_FRAME_SOLVE : k <= kCsProfDense ? VCGPU_STAGE_GLOBAL_SOLVE : VCGPU_STAGE_BACKSUB, ns[k]);
+    add(k < kCsProfReduce ? VCGPU_STAGE_FRAME_SOLVE : k <= kCsProfDense ? VCGPU_STAGE_GLOBAL_SOLVE : k == kCsProfWeights ? VCGPU_STAGE_IMU_WEIGHTS
+                                                                                                     : VCGPU_STAGE_BACKSUB, ns[k]);
   const int map_e[kEvProfCount] = {VCGPU_STAGE_EVAL_TASKS, VCGPU_STAGE_IMU_ACCUM, VCGPU_STAGE_REDUCE, VCGPU_STAGE_FINALIZE,
                                    VCGPU_STAGE_IMU_WEIGHTS};
   for (int k = 0; k < kEvProfCount; ++k) add(map_e[k], ns[32 + k]);
@@ -535,12 +545,23 @@ static int enqueue_dogleg_iteration(vcgpu_handle* h, bool weights) {
 }
 
 // one trust-region iteration, enqueued (no host wait)
+static bool deferred_off() {
+  static const bool off = std::getenv("VCGPU_NO_DEFERRED_WEIGHTS") != nullptr;  // A/B switch
+  return off;
+}
+// the weight update of the last LM iteration of a persistent inertial run (earlier ones ride in the next solve launch)
+static int imu_mega_finish_weights(vcgpu_handle* h, bool weights) {
+  if (!weights || h->opts.strategy == 1 || !imu_mega_applies(h) || deferred_off()) return VCGPU_OK;
+  return imu_update_weights(h, false, true);
+}
 static int enqueue_iteration(vcgpu_handle* h, bool weights) {
   if (h->opts.strategy == 1) return enqueue_dogleg_iteration(h, weights);
   if (mega_applies(h)) return mega_launch(h, 1);
-  if (imu_mega_applies(h)) {  // two cooperative launches: solve + update, evaluate + decide + UpdateImuWeights
-    VC_TRY(imu_mega_solve(h, nullptr, true));
-    return imu_mega_eval(h, 1, true, 1, weights);
+  if (imu_mega_applies(h)) {
+    // two cooperative launches: solve + update (+ the UpdateImuWeights the previous iteration's accepted step calls
+    // for, on the CTAs the solve leaves idle), evaluate + decide.  The last iteration's update: imu_mega_finish_weights
+    VC_TRY(imu_mega_solve(h, nullptr, true, weights && !deferred_off()));
+    return imu_mega_eval(h, 1, true, 1, weights && deferred_off());
   }
   VC_TRY(solve_and_update(h, nullptr, false));
   VC_TRY(evaluate_into(h, 1, true, 1));
@@ -632,6 +653,7 @@ static int run_solve(vcgpu_handle* h, vcgpu_iter_cb cb, void* user, vcgpu_summar
       if (h->h_ctl->done) break;
     }
   }
+  VC_TRY(imu_mega_finish_weights(h, weights));
   VC_TRY(wts_join(h));
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   VC_TRY(ctl_download(h));

@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
   __shared__ unsigned char tri_lut[128];
   __shared__ double shr[8][8];
   __shared__ unsigned task_s[kEvWarps];
+  __shared__ unsigned long long* xbufs[kMaxRanks];
+  xchg_stage(a.x, xbufs);  // (visible after the first barrier below)
   if (a.ctl->done) return;  // uniform over the grid: written before this launch
   const int buf = a.which ? 1 - a.ctl->cur : a.ctl->cur;
   const Blocks& bt = a.blk[buf];
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
         t[6] = fmax(t[6], shr[ww][6]);
       }
       if (sharded) {  // this rank's share; the totals are formed below
-        for (int q = 0; q < 7; ++q) xchg_put(a.x, eSc + q, t[q]);
+        for (int q = 0; q < 7; ++q) xchg_put(a.x, xbufs, eSc + q, t[q]);
       } else {
         *bt.cost = t[0];
         a.scalars[kScCost] = t[0];
@@ -364,31 +366,31 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_mega_kernel(EvalMegaArgs a
     const int nsep = (1 + a.dp.ghost) * 2 * kSepFd;
     for (int e = bid * kEvThreads + tid; e < NS + nsep; e += nb * kEvThreads) {
       if (e < NS) {
-        xchg_put(a.x, e, __ldcg(bt.C + e));  // C | gc are contiguous
+        xchg_put(a.x, xbufs, e, __ldcg(bt.C + e));  // C | gc are contiguous
       } else {
         const int o = e - NS, t = o / (2 * kSepFd), q = o - t * 2 * kSepFd;
         const int64_t f = t == 0 ? 0 : nf - 1;
         const double v = q < kSepFd ? __ldcg(bt.B + (f * kSepFd + q) * kSepFd + q) : __ldcg(bt.gf + f * kSepFd + (q - kSepFd));
-        xchg_put(a.x, eSep + o, v);
+        xchg_put(a.x, xbufs, eSep + o, v);
       }
     }
     const int nslot = a.x.nranks * 2 * kSepFd;
     for (int e = bid * kEvThreads + tid; e < NS + nslot; e += nb * kEvThreads) {
       double v = 0.0;
       if (e < NS) {
-        for (int r = 0; r < a.x.nranks; ++r) v += xchg_get(a.x, r, e);
+        for (int r = 0; r < a.x.nranks; ++r) v += xchg_get(a.x, xbufs, r, e);
         bt.C[e] = v;
       } else {
         const int o = e - NS, k = o / (2 * kSepFd), q = o - k * 2 * kSepFd;  // slot k = rank k's first frame
-        if (k > 0) v = xchg_get(a.x, k - 1, eSep + 2 * kSepFd + q);          // rank k-1's ghost copy
-        v += xchg_get(a.x, k, eSep + q);
+        if (k > 0) v = xchg_get(a.x, xbufs, k - 1, eSep + 2 * kSepFd + q);          // rank k-1's ghost copy
+        v += xchg_get(a.x, xbufs, k, eSep + q);
         a.sep_out[(q < kSepFd ? 0 : a.x.nranks * kSepFd) + k * kSepFd + (q < kSepFd ? q : q - kSepFd)] = v;
       }
     }
     grid.sync();
     if (bid == 0) {
       double* tot = &shr[0][0];  // [ranks][8] the ranks' scalars
-      if (tid < a.x.nranks * 7) tot[(tid / 7) * 8 + tid % 7] = xchg_get(a.x, tid / 7, eSc + tid % 7);
+      if (tid < a.x.nranks * 7) tot[(tid / 7) * 8 + tid % 7] = xchg_get(a.x, xbufs, tid / 7, eSc + tid % 7);
       double gm = 0.0, g2 = 0.0;
       for (int k = tid; k < G; k += kEvThreads) {
         const double v = __ldcg(bt.gc + k);

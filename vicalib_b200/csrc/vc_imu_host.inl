@@ -257,7 +257,7 @@ static int wts_join(vcgpu_handle* h) {
   }
   return VCGPU_OK;
 }
-static int imu_update_weights(vcgpu_handle* h, bool side_stream = false) {
+static int imu_update_weights(vcgpu_handle* h, bool side_stream = false, bool deferred = false) {
   vc::ImuDev* d = imu_dev(h);
   const DevProblem& dp = h->dp;
   if (!dp.inertial || dp.rotation_only) return VCGPU_OK;
@@ -273,7 +273,7 @@ static int imu_update_weights(vcgpu_handle* h, bool side_stream = false) {
   vc::wts::WeightArgs a;
   a.dp = dp; a.buf = d->buf; a.ctl = h->d_ctl; a.states[0] = h->d_state[0]; a.states[1] = h->d_state[1];
   a.ftime = d->ftime; a.wsqrt = h->d_wsqrt;
-  a.ni = dp.n_frames - 1; a.sigma_g = h->sigma_g; a.sigma_a = h->sigma_a;
+  a.ni = dp.n_frames - 1; a.sigma_g = h->sigma_g; a.sigma_a = h->sigma_a; a.deferred = deferred ? 1 : 0;
   vc::wts::imu_weights_kernel<<<(a.ni + vc::wts::kWtTeams - 1) / vc::wts::kWtTeams, 32 * vc::wts::kWtWarps, 0, st_launch>>>(a);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());

@@ -25,6 +25,7 @@
 #include "vc_kernels.cuh"
 #include "vc_mega.cuh"
 #include "vc_xchg.cuh"
+#include "vc_imu_weights.cuh"
 
 namespace vc {
 
@@ -34,7 +35,8 @@ constexpr int kCsGroup = 128;                // threads per elimination group
 constexpr int kCsGroups = kCsThreads / kCsGroup;
 constexpr int kCsChunk = 4;                  // every 4th node of a level is a separator
 // phase clock slots: elimination levels [0, 10), reduce 10, dense 11, back-substitution levels [12, 22), update 22
-enum { kCsProfElim = 0, kCsProfReduce = kMaxChainLevels, kCsProfDense, kCsProfBacksub, kCsProfUpdate = kCsProfBacksub + kMaxChainLevels, kCsProfCount };
+enum { kCsProfElim = 0, kCsProfReduce = kMaxChainLevels, kCsProfDense, kCsProfBacksub, kCsProfUpdate = kCsProfBacksub + kMaxChainLevels,
+       kCsProfWeights, kCsProfCount };
 
 struct ChainSolveArgs {
   DevProblem dp;
@@ -58,6 +60,17 @@ struct ChainSolveArgs {
   const double* sepdiag;        // [ranks][9] diag(B) of the ranks' first frames summed over both owners, or null
   double* dsys;                 // [NS + ranks * kTopBlock] summed dense system in block form
   unsigned long long* prof;     // [kCsProfCount] ns per phase (CTA 0) or null
+  // deferred UpdateImuWeights (the reference's iteration callback, vicalibrator.h:690-721): the weights at the point the
+  // previous iteration accepted are needed by the next EVALUATION, not by this solve — CTAs that have run out of
+  // elimination work (levels with fewer chunks than CTAs, the dense solve) compute them here, off a queue
+  int wts_on;                   // 1: run the update if the previous iteration accepted its step
+  int n_solver;                 // CTAs that stay with the solve after the elimination levels
+  imu::ImuBuf buf;
+  const double* ftime;
+  double* wsqrt;
+  double sigma_g, sigma_a;
+  unsigned long long* sync;     // {barrier counter, weights queue, barrier counter of the closing phases} of this launch
+  unsigned long long* sync_next;  // ... of the next launch (the host alternates two pairs): zeroed here
 };
 
 __host__ __device__ inline size_t chain_group_doubles(int G) {
@@ -71,7 +84,9 @@ __host__ __device__ inline size_t chain_solve_smem_doubles(int G, int nranks = 1
   const size_t grp = kCsGroups * chain_group_doubles(G);
   const size_t N = static_cast<size_t>(G) + (nranks > kCsChunk ? nranks : kCsChunk) * 9;
   const size_t dense = N * N + 2 * N;
-  return (grp > dense ? grp : dense) + 16;
+  const size_t wts = (kCsThreads / wts::kTeam) * (sizeof(wts::Work) / sizeof(double) + 1);
+  const size_t m = grp > dense ? grp : dense;
+  return (m > wts ? m : wts) + 16;
 }
 
 __device__ __forceinline__ void group_sync(int grp) {
@@ -502,6 +517,50 @@ __device__ __forceinline__ void chain_eliminate_chunk(const NodeSrc& src, const 
   tick(9);
 }
 
+// Back-substitution of one level: x_p = -Z_g - Z_L x_left - Z_R x_right - Z_E dc for every interior node p, one warp each
+// (warp gw of nw)
+template <int FD>
+__device__ __forceinline__ void chain_backsub_level(const ChainLevel cur, int l, double* delta, int64_t nfp, int G, int gw, int nw, int lane) {
+  const int w = 2 * FD + G + 1, c = kCsChunk;
+  const double* dc = delta + nfp;
+  const int n_eff = cur.n - cur.ghost;
+  const int n_chunks = (n_eff + c - 1) / c;
+  // interior node q (0..c-2) of chunk j: p = j*c + 1 + q
+  for (int t = gw; t < n_chunks * (c - 1); t += nw) {
+    const int jc = t / (c - 1), p = jc * c + 1 + (t - jc * (c - 1));
+    if (p >= n_eff) continue;
+    const int s = jc * c;
+    const int r = s + c < n_eff ? s + c : (cur.ghost ? cur.n - 1 : cur.n);
+    // original frame of node p of level l: p * 4^l (no ghost node on one GPU); a table lookup otherwise
+    const int sh = 2 * l;
+    const int os = cur.ghost ? (l > 0 ? cur.orig[s] : s) : s << sh, op = cur.ghost ? (l > 0 ? cur.orig[p] : p) : p << sh;
+    const double* xl = delta + static_cast<int64_t>(os) * FD;
+    const double* xr = r < cur.n ? delta + static_cast<int64_t>(cur.ghost ? (l > 0 ? cur.orig[r] : r) : r << sh) * FD : nullptr;
+    const double* Z = cur.Z + static_cast<int64_t>(p) * FD * w;
+    double* out = delta + static_cast<int64_t>(op) * FD;
+    double d[FD];
+#pragma unroll
+    for (int rr = 0; rr < FD; ++rr) d[rr] = 0.0;
+    for (int q = lane; q < w - 1; q += 32) {
+      const double x = q < FD ? __ldcg(xl + q) : q < 2 * FD ? (xr ? __ldcg(xr + q - FD) : 0.0) : __ldcg(dc + q - 2 * FD);
+#pragma unroll
+      for (int rr = 0; rr < FD; ++rr) d[rr] += __ldcg(Z + rr * w + q) * x;
+    }
+#pragma unroll
+    for (int rr = 0; rr < FD; ++rr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d[rr] += __shfl_xor_sync(0xffffffffu, d[rr], o);
+      d[rr] = -__ldcg(Z + rr * w + w - 1) - d[rr];
+    }
+    if (lane < FD) {
+      double v = d[0];
+#pragma unroll
+      for (int rr = 1; rr < FD; ++rr) v = lane == rr ? d[rr] : v;
+      out[lane] = v;
+    }
+  }
+}
+
 // x (+) step of one frame into the trial state, and the frame's share of the step statistics
 // (acc: step.g, step.D2.step, |x_new - x|^2, |x_new|^2)
 __device__ __forceinline__ void chain_update_frame(const ChainSolveArgs& a, const Blocks& b, double rinv, int f, const double* d,
@@ -551,11 +610,37 @@ __device__ __forceinline__ void chain_update_frame(const ChainSolveArgs& a, cons
   }
 }
 
+// The deferred UpdateImuWeights as a function of its own (its own register allocation: inlined into the solve kernel
+// it ran 60 % slower, with the solve's live values squeezed into the same 255 registers).  Everything by value — a
+// reference to the kernel's parameter block would force the whole block into local memory.
+struct WeightQueueArgs {
+  struct { int64_t off_v, off_imu; } dp;
+  imu::ImuBuf buf;
+  const double* ftime;
+  double* wsqrt;
+  int ni;
+  double sigma_g, sigma_a;
+};
+__device__ __noinline__ void chain_weights_queue(const WeightQueueArgs w, const double* xs, unsigned long long* wq, double* smem,
+                                                 unsigned long long* wtask) {
+  constexpr int kTeams = kCsThreads / wts::kTeam;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  wts::Work* work = reinterpret_cast<wts::Work*>(smem);
+  const int team = tid / wts::kTeam, tl = tid & (wts::kTeam - 1);
+  for (;;) {
+    __syncthreads();  // the workspace (and *wtask) are free
+    if (tid == 0) *wtask = atomicAdd(wq, 1ull);
+    __syncthreads();
+    const long long base = static_cast<long long>(*wtask) * kTeams;
+    if (base >= w.ni) break;
+    if (base + (warp * (32 / wts::kTeam)) < w.ni) wts::imu_weights_team(w, xs, static_cast<int>(base) + team, &work[team], tl);
+  }
+}
+
 // One damped solve of the frame-chain + globals system and (optionally) the state update, all in one launch.
 __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveArgs a) {
   extern __shared__ double smem[];
   namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
   constexpr int FD = 9;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = tid / kCsGroup, gtid = tid - grp * kCsGroup;
@@ -566,6 +651,10 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
   __shared__ int bad_s[kCsGroups];
   __shared__ int bad_dense;
   __shared__ double part[kCsThreads / 32][4];
+  __shared__ unsigned long long wtask;
+  __shared__ unsigned long long* xbufs[kMaxRanks];
+  xchg_stage(a.x, xbufs);  // (visible after the first barrier below)
+  if (bid == 0 && tid == 0) { a.sync_next[0] = 0ull; a.sync_next[1] = 0ull; a.sync_next[2] = 0ull; }
   if (a.ctl->done) return;  // uniform over the grid: written before this launch
   const Blocks& b = a.b[a.ctl->cur];
   const double rinv = 1.0 / a.ctl->radius;
@@ -579,11 +668,45 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       t_prev = t;
     }
   };
+  // ---- who does what.  Without a pending weight update every CTA stays with the solve (ns = grid).  With one, the
+  // CTAs [ns, grid) leave after their last elimination level and work the weights queue; the solve goes on among the
+  // first ns CTAs, which join the queue when they are done.  Barriers therefore count arrivals: everybody who took
+  // part in a phase arrives, only those who go on wait.
+  const bool wts_go = a.wts_on && !a.dp.rotation_only && a.ctl->iter > 0 && a.ctl->last_accepted;
+  const int ns = wts_go ? min(max(a.n_solver, 1), nb) : nb;
+  unsigned long long* bar = a.sync;      // this launch's counters (the host alternates the pair)
+  unsigned long long* wq = a.sync + 1;
+  unsigned long long bar_target = 0;
+  int n_act = nb;
+  // The CTAs that left come back for the widest phases at the end (back-substitution of level 0, the state update).
+  // Those barriers count on a second counter: a CTA that is back early must not be mistaken for an arrival at one of
+  // the barriers the solve is still passing through.
+  auto barrier = [&](int n_next) -> bool {
+    __syncthreads();
+    bar_target += static_cast<unsigned long long>(n_act);
+    const bool stay = bid < n_next;
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(bar, 1ull);
+      if (stay) {
+        unsigned long long v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+        } while (v < bar_target);
+        __threadfence();
+      }
+    }
+    n_act = n_next;
+    __syncthreads();
+    return stay;
+  };
   double* gsm = smem + static_cast<size_t>(grp) * chain_group_doubles(G);
   if (gtid == 0) bad_s[grp] = 0;
   for (int e = gtid; e < NS; e += kCsGroup) gsm[e] = 0.0;  // the group's Schur accumulator
   double acc[4] = {0.0, 0.0, 0.0, 0.0};                   // this thread's share of the step statistics
 
+  bool left = false;  // this CTA has left the solve (its elimination work is done): straight to the weights queue
+  do {
   // ------------------------------------------------------------ elimination, level by level
   for (int l = 0; l + 1 < a.n_levels; ++l) {
     NodeSrc src;
@@ -608,15 +731,26 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       }
       __syncthreads();
     }
-    if (l + 2 == a.n_levels) {  // last level: publish this group's Schur partial
+    // who goes on: everybody the next level needs (all of them if it is a wide one), never fewer than ns
+    int n_next = ns;
+    if (l + 2 < a.n_levels) {
+      const int nsep2 = a.lev[l + 2].n - a.dp.ghost;
+      n_next = (nsep2 > nb || !a.narrow_ok) ? nb : max(ns, nsep2);
+    }
+    n_next = min(n_next, n_act);
+    if (l + 2 == a.n_levels || bid >= n_next) {  // last level of this CTA: publish the groups' Schur partials
       group_sync(grp);
       double* out = a.Spart + static_cast<int64_t>(gid) * NS;
       for (int e = gtid; e < NS; e += kCsGroup) out[e] = gsm[e];
       if (gtid == 0 && bad_s[grp]) a.scalars[kScNotPD] = 1.0;
     }
     mark(kCsProfElim + l);
-    grid.sync();
+    if (!barrier(n_next)) {
+      left = true;
+      break;
+    }
   }
+  if (left) break;
   if (a.n_levels == 1) {  // nothing to eliminate: the top level is the problem itself; zero partials
     const ChainLevel& L = a.lev[0];
     NodeSrc src;
@@ -635,12 +769,15 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     }
     double* out = a.Spart + static_cast<int64_t>(gid) * NS;
     for (int e = gtid; e < NS; e += kCsGroup) out[e] = 0.0;
-    grid.sync();
+    if (!barrier(ns)) {
+      left = true;
+      break;
+    }
   }
   // ------------------------------------------------------------ Schur partials -> total (fixed order), distributed
-  mega_reduce_stage1(a.Spart, NS, n_groups, NS, a.Ssum, -1, -1);
+  mega_reduce_stage1(a.Spart, NS, n_groups, NS, a.Ssum, -1, -1, bid, ns);
   mark(kCsProfReduce);
-  grid.sync();
+  barrier(ns);
   // ------------------------------------------------------------ sharded: the ranks' partial systems meet here
   const bool sharded = a.x.nranks > 1;
   const int TB = chain_top_block(G);
@@ -649,7 +786,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     const bool add = top.addA != nullptr;
     const double* sc = a.scale + nfp;
     const int P = NS + top.n * TB;  // this rank's entries: globals, own first frame (+ the ghost)
-    for (int e = bid * kCsThreads + tid; e < P; e += nb * kCsThreads) {
+    for (int e = bid * kCsThreads + tid; e < P; e += ns * kCsThreads) {
       double v;
       if (e < NS) {
         const double p = __ldcg(a.Ssum + e);
@@ -677,27 +814,27 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
           v = -(__ldcg(top.g + q) + (add ? __ldcg(top.addg + q) : 0.0));
         }
       }
-      xchg_put(a.x, e, v);
+      xchg_put(a.x, xbufs, e, v);
     }
     // one reader per entry of the summed system (slot k = rank k's first frame: its own blocks + the ghost blocks of
     // rank k-1, whose U block is the coupling between slots k-1 and k), ranks in order
     const int Q = NS + a.x.nranks * TB;
-    for (int e = bid * kCsThreads + tid; e < Q; e += nb * kCsThreads) {
+    for (int e = bid * kCsThreads + tid; e < Q; e += ns * kCsThreads) {
       double v = 0.0;
       if (e < NS) {
-        for (int r = 0; r < a.x.nranks; ++r) v += xchg_get(a.x, r, e);
+        for (int r = 0; r < a.x.nranks; ++r) v += xchg_get(a.x, xbufs, r, e);
       } else {
         const int k = (e - NS) / TB, o = (e - NS) - k * TB;
         if (o >= 81 && o < 162) {
-          v = k > 0 ? xchg_get(a.x, k - 1, NS + TB + o) : 0.0;
+          v = k > 0 ? xchg_get(a.x, xbufs, k - 1, NS + TB + o) : 0.0;
         } else {
-          if (k > 0) v = xchg_get(a.x, k - 1, NS + TB + o);
-          v += xchg_get(a.x, k, NS + o);
+          if (k > 0) v = xchg_get(a.x, xbufs, k - 1, NS + TB + o);
+          v += xchg_get(a.x, xbufs, k, NS + o);
         }
       }
       a.dsys[e] = v;
     }
-    grid.sync();
+    barrier(ns);
   }
   // ------------------------------------------------------------ dense solve of [globals | top nodes]: CTA 0 (the step
   // of the globals and of the top nodes goes through a.delta; everybody waits at the barrier below)
@@ -878,93 +1015,75 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
   }
   if (prof) { const long long t = clock64(); a.prof[55] += static_cast<unsigned long long>(t - dt0); }
   mark(kCsProfDense);
-  grid.sync();
-  // ------------------------------------------------------------ back-substitution, top-down; every node's frame is
-  // updated by the warp that solves it
-  {
-    const int w = 2 * FD + G + 1, c = kCsChunk;
-    const int gw = bid * (kCsThreads / 32) + warp, nw = nb * (kCsThreads / 32);
-    const double* dc = a.delta + nfp;
-    for (int l = a.n_levels - 2; l >= 0; --l) {
-      const ChainLevel cur = a.lev[l];
-      const int n_eff = cur.n - cur.ghost;
-      const int n_chunks = (n_eff + c - 1) / c;
-      // interior node q (0..c-2) of chunk j: p = j*c + 1 + q
-      for (int t = gw; t < n_chunks * (c - 1); t += nw) {
-        const int jc = t / (c - 1), p = jc * c + 1 + (t - jc * (c - 1));
-        if (p >= n_eff) continue;
-        const int s = jc * c;
-        const int r = s + c < n_eff ? s + c : (cur.ghost ? cur.n - 1 : cur.n);
-        // original frame of node p of level l: p * 4^l (no ghost node on one GPU); a table lookup otherwise
-        const int sh = 2 * l;
-        const int os = cur.ghost ? (l > 0 ? cur.orig[s] : s) : s << sh, op = cur.ghost ? (l > 0 ? cur.orig[p] : p) : p << sh;
-        const double* xl = a.delta + static_cast<int64_t>(os) * FD;
-        const double* xr = r < cur.n ? a.delta + static_cast<int64_t>(cur.ghost ? (l > 0 ? cur.orig[r] : r) : r << sh) * FD : nullptr;
-        const double* Z = cur.Z + static_cast<int64_t>(p) * FD * w;
-        double* out = a.delta + static_cast<int64_t>(op) * FD;
-        // the solved neighbours / globals this lane multiplies with (two columns per lane at most: w - 1 <= 64 ... or a loop)
+  if (a.n_levels <= 2) break;  // the next barrier is the one the whole grid meets at
+  barrier(ns);
+  // ------------------------------------------------------------ back-substitution, top-down, levels >= 1
+  for (int l = a.n_levels - 2; l >= 1; --l) {
+    chain_backsub_level<FD>(a.lev[l], l, a.delta, nfp, G, bid * (kCsThreads / 32) + warp, ns * (kCsThreads / 32), lane);
+    mark(kCsProfBacksub + (a.n_levels - 2 - l));
+    if (l > 1) barrier(ns);
+  }
+  } while (false);
+  // step 0: the CTAs that left the solve work the weights queue.  step 1: everybody — back-substitution of level 0,
+  // x (+) step, step statistics.  step 2: the CTAs that stayed with the solve take what is left in the queue.
+  for (int step = 0; step < 3; ++step) {
+    if (step != 1) {
+      if (!wts_go || (step == 0) != left) continue;
+      // ---------------------------------------------------------- deferred UpdateImuWeights
+      WeightQueueArgs wa;
+      wa.dp.off_v = a.dp.off_v; wa.dp.off_imu = a.dp.off_imu; wa.buf = a.buf; wa.ftime = a.ftime; wa.wsqrt = a.wsqrt;
+      wa.ni = nf - 1; wa.sigma_g = a.sigma_g; wa.sigma_a = a.sigma_a;
+      chain_weights_queue(wa, a.state[a.ctl->cur], wq, smem, &wtask);
+      if (step == 2) mark(kCsProfWeights);
+      continue;
+    }
+    bar = a.sync + 2;  // the closing phases: the whole grid again, on their own counter
+    bar_target = 0;
+    n_act = nb;
+    barrier(nb);
+    if (a.n_levels >= 2) {
+      chain_backsub_level<FD>(a.lev[0], 0, a.delta, nfp, G, bid * (kCsThreads / 32) + warp, nb * (kCsThreads / 32), lane);
+      mark(kCsProfBacksub + (a.n_levels - 2));
+      barrier(nb);
+    }
+    if (!a.do_update) continue;
+    // ---------------------------------------------------------- x (+) step of every frame, one thread each (the top
+    // nodes' frames were done with the dense solve); a serial tail per node inside the level loop above cost more than
+    // this one barrier
+    {
+      const ChainLevel top = a.lev[a.n_levels - 1];
+      for (int f = bid * kCsThreads + tid; f < nf; f += nb * kCsThreads) {
+        bool is_top = false;
+        if (a.n_levels > 1) {
+          for (int t = 0; t < top.n; ++t) is_top = is_top || (top.ghost ? top.orig[t] : t << (2 * (a.n_levels - 1))) == f;
+        } else {
+          is_top = true;
+        }
+        if (is_top) continue;
         double d[FD];
 #pragma unroll
-        for (int rr = 0; rr < FD; ++rr) d[rr] = 0.0;
-        for (int q = lane; q < w - 1; q += 32) {
-          const double x = q < FD ? __ldcg(xl + q) : q < 2 * FD ? (xr ? __ldcg(xr + q - FD) : 0.0) : __ldcg(dc + q - 2 * FD);
-#pragma unroll
-          for (int rr = 0; rr < FD; ++rr) d[rr] += __ldcg(Z + rr * w + q) * x;
-        }
-#pragma unroll
-        for (int rr = 0; rr < FD; ++rr) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) d[rr] += __shfl_xor_sync(0xffffffffu, d[rr], o);
-          d[rr] = -__ldcg(Z + rr * w + w - 1) - d[rr];
-        }
-        if (lane < FD) {
-          double v = d[0];
-#pragma unroll
-          for (int rr = 1; rr < FD; ++rr) v = lane == rr ? d[rr] : v;
-          out[lane] = v;
-        }
+        for (int r = 0; r < FD; ++r) d[r] = __ldcg(a.delta + static_cast<int64_t>(f) * FD + r);
+        chain_update_frame(a, b, rinv, f, d, acc);
       }
-      mark(kCsProfBacksub + (a.n_levels - 2 - l));
-      grid.sync();
     }
-  }
-  if (!a.do_update) return;
-  // ------------------------------------------------------------ x (+) step of every frame, one thread each (the top
-  // nodes' frames were done with the dense solve); a serial tail per node inside the level loop above cost more than
-  // this one barrier
-  {
-    const ChainLevel top = a.lev[a.n_levels - 1];
-    for (int f = bid * kCsThreads + tid; f < nf; f += nb * kCsThreads) {
-      bool is_top = false;
-      if (a.n_levels > 1) {
-        for (int t = 0; t < top.n; ++t) is_top = is_top || (top.ghost ? top.orig[t] : t << (2 * (a.n_levels - 1))) == f;
-      } else {
-        is_top = true;
-      }
-      if (is_top) continue;
-      double d[FD];
+    // ---------------------------------------------------------- step statistics of this CTA
 #pragma unroll
-      for (int r = 0; r < FD; ++r) d[r] = __ldcg(a.delta + static_cast<int64_t>(f) * FD + r);
-      chain_update_frame(a, b, rinv, f, d, acc);
-    }
-  }
-  // ------------------------------------------------------------ step statistics of this CTA
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-  }
-  if (lane == 0)
-    for (int q = 0; q < 4; ++q) part[warp][q] = acc[q];
-  __syncthreads();
-  if (tid == 0) {
     for (int q = 0; q < 4; ++q) {
-      double sum = 0.0;
-      for (int ww = 0; ww < kCsThreads / 32; ++ww) sum += part[ww][q];
-      a.step_part[4 * static_cast<int64_t>(bid) + q] = sum;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
     }
+    if (lane == 0)
+      for (int q = 0; q < 4; ++q) part[warp][q] = acc[q];
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 0; q < 4; ++q) {
+        double sum = 0.0;
+        for (int ww = 0; ww < kCsThreads / 32; ++ww) sum += part[ww][q];
+        a.step_part[4 * static_cast<int64_t>(bid) + q] = sum;
+      }
+    }
+    mark(kCsProfUpdate);
   }
-  mark(kCsProfUpdate);
 }
 
 }  // namespace vc

@@ -316,6 +316,7 @@ struct WeightArgs {
   double* wsqrt;
   int ni;
   double sigma_g, sigma_a;
+  int deferred;  // 1: the update the persistent solve kernel would have run for the last iteration (ignores `done`)
 };
 struct WeightView {  // WeightArgs' fields with the problem description by reference (persistent kernel)
   const DevProblem& dp;
@@ -498,9 +499,13 @@ __global__ void __launch_bounds__(32 * kWtWarps, 2) imu_weights_kernel(WeightArg
   __shared__ Work work[kWtTeams];
   const int tl = threadIdx.x & (kTeam - 1);
   const int team = threadIdx.x / kTeam;
-  if (a.ctl->done) return;
-  // a rejected step leaves the accepted state — hence the weights — unchanged
-  if (a.ctl->iter > 0 && !a.ctl->last_accepted) return;
+  if (a.deferred) {
+    if (!(a.ctl->iter > 0 && a.ctl->last_accepted)) return;
+  } else {
+    if (a.ctl->done) return;
+    // a rejected step leaves the accepted state — hence the weights — unchanged
+    if (a.ctl->iter > 0 && !a.ctl->last_accepted) return;
+  }
   if (blockIdx.x * kWtTeams + (threadIdx.x >> 5) * (32 / kTeam) >= a.ni) return;  // whole warp past the end
   imu_weights_team(a, a.states[a.ctl->cur], blockIdx.x * kWtTeams + team, &work[team], tl);
 }

@@ -206,6 +206,8 @@ struct vcgpu_handle {
   int rank = 0, nranks = 1;
   double* d_mg = nullptr;         // all-reduce buffer [G*G+G+6+nranks (+ 18*nranks)]
   double* d_sep = nullptr;        // [2][nranks*9]: summed diag(B) and g of the separator frames (sharded inertial runs)
+  unsigned long long* d_csync = nullptr;  // persistent inertial solve: two {barrier counter, weights queue} pairs
+  unsigned cs_launches = 0;
   double* d_dsys = nullptr;       // persistent sharded inertial solve: the summed dense system in block form
   unsigned xchg_tag_dense = 0, xchg_tag_eval = 0;  // exchange numbers of the persistent inertial kernels (vc_xchg.cuh)
   double* d_dense = nullptr;      // [N*N+N] all-reduced dense system, N = G + 9*nranks

@@ -29,21 +29,33 @@ struct Xchg {
   Ctl* ctl;                             // a reader that times out sets done = kMegaCommFailed
 };
 
+// The peer pointers move to shared memory once per launch: indexing the kernel-parameter array with a run-time rank
+// would make the compiler copy the whole parameter block to local memory.
+__device__ __forceinline__ void xchg_stage(const Xchg& x, unsigned long long** bufs_s) {
+  if (threadIdx.x < kMaxRanks) {
+    unsigned long long* p = x.buf[0];
+#pragma unroll
+    for (int r = 1; r < kMaxRanks; ++r)
+      if (threadIdx.x == r) p = x.buf[r];
+    bufs_s[threadIdx.x] = p;
+  }
+}
+
 // entry e of this rank's slot -> every rank's buffer
-__device__ __forceinline__ void xchg_put(const Xchg& x, int e, double v) {
+__device__ __forceinline__ void xchg_put(const Xchg& x, unsigned long long* const* bufs, int e, double v) {
   const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
   const unsigned long long hi_tag = static_cast<unsigned long long>(x.tag) << 32;
   const unsigned long long w0 = (bits & 0xffffffffull) | hi_tag, w1 = (bits >> 32) | hi_tag;
   const size_t w = x.off + 2 * (static_cast<size_t>((x.tag & 1u) * x.nranks + x.rank) * x.stride + e);
   for (int r = 0; r < x.nranks; ++r) {
     const int rr = (x.rank + r) % x.nranks;  // start with the local copy, then walk the peers (spreads the links)
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(x.buf[rr] + w), "l"(w0), "l"(w1) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(bufs[rr] + w), "l"(w0), "l"(w1) : "memory");
   }
 }
 
 // entry e of rank r's slot, from the local buffer; spins until the words carry this exchange's tag
-__device__ __forceinline__ double xchg_get(const Xchg& x, int r, int e) {
-  const unsigned long long* w = x.buf[x.rank] + x.off + 2 * (static_cast<size_t>((x.tag & 1u) * x.nranks + r) * x.stride + e);
+__device__ __forceinline__ double xchg_get(const Xchg& x, unsigned long long* const* bufs, int r, int e) {
+  const unsigned long long* w = bufs[x.rank] + x.off + 2 * (static_cast<size_t>((x.tag & 1u) * x.nranks + r) * x.stride + e);
   unsigned long long w0, w1;
   unsigned polls = 0;
   unsigned long long t0 = 0;
