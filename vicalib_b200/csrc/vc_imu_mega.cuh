@@ -78,12 +78,19 @@ __host__ __device__ inline size_t chain_group_doubles(int G) {
   const size_t NS = static_cast<size_t>(G) * G + G, VW = FD + 2 * FD + G + 1;
   return NS + FD * FD + FD * G + FD + (2 * (kCsChunk - 1) + 1) * FD * FD + (kCsChunk - 1) * FD * VW + (kCsChunk - 1) * FD * G;
 }
+// tiles of the register version that fits N (0: none does — shared-memory version), and the layout of S that goes with it
+__host__ __device__ inline int dense_tiles(int N) {
+  const int t = (N + 1 + 15) / 16;
+  return t <= 6 ? 6 : t <= 7 ? 7 : t <= 9 ? 9 : 0;
+}
+__host__ __device__ inline int dense_rows(int N) { return dense_tiles(N) ? 16 * dense_tiles(N) : N + 1; }
+__host__ __device__ inline int dense_ld(int N) { return dense_tiles(N) ? 16 * dense_tiles(N) + 1 : (N | 1); }
 // a top node's blocks in the exchanged dense system: A 81 | U 81 (coupling to the previous slot) | E 9G | -g 9
 __host__ __device__ inline int chain_top_block(int G) { return 2 * 81 + 9 * G + 9; }
 __host__ __device__ inline size_t chain_solve_smem_doubles(int G, int nranks = 1) {
   const size_t grp = kCsGroups * chain_group_doubles(G);
   const size_t N = static_cast<size_t>(G) + (nranks > kCsChunk ? nranks : kCsChunk) * 9;
-  const size_t dense = N * N + 2 * N;
+  const size_t dense = static_cast<size_t>(dense_rows(static_cast<int>(N))) * dense_ld(static_cast<int>(N)) + N + 2;
   const size_t wts = (kCsThreads / wts::kTeam) * (sizeof(wts::Work) / sizeof(double) + 1);
   const size_t m = grp > dense ? grp : dense;
   return (m > wts ? m : wts) + 16;
@@ -637,6 +644,108 @@ __device__ __noinline__ void chain_weights_queue(const WeightQueueArgs w, const 
   }
 }
 
+// ---- dense L D L^T of the [globals | top nodes] system (one CTA of 256 threads; S: [N + 1][LD], row N = right-hand side)
+// shared-memory version: any N
+__device__ __noinline__ void dense_ldlt_smem(double* S, int N, int LD, double* wd, int* bad) {
+  const int tid = threadIdx.x, ti = tid >> 4, tk = tid & 15;
+  if (tid == 0) {
+    const double d = S[0];
+    const bool okp = d > 0.0;
+    wd[0] = 1.0 / (okp ? d : 1.0);
+    if (!okp) *bad = 1;
+  }
+  for (int j = 0; j < N; ++j) {
+    __syncthreads();
+    const double wj = wd[j];
+    for (int i = j + 1 + ti; i <= N; i += 16) {
+      double* row = S + i * LD;
+      const double lw = row[j] * wj;
+      const int kmax = i < N ? i : N - 1;
+      for (int k = j + 1 + tk; k <= kmax; k += 16) {
+        const double v = row[k] - lw * S[k * LD + j];
+        row[k] = v;
+        if (k == j + 1 && i == j + 1) {  // the next pivot is final: its reciprocal now
+          const bool okp = v > 0.0;
+          wd[j + 1] = 1.0 / (okp ? v : 1.0);
+          if (!okp) *bad = 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+// register version: T x T tiles of 16 x 16 cover the N + 1 rows.  S is padded to 16 T rows of LD >= 16 T columns (zeros
+// outside the system), so nothing in the column loop needs a bounds check: an update that should not happen (row or
+// column already finished, padding) only ever lands in an element above the diagonal or in a column that has already
+// gone back to shared memory — registers nobody reads again.  ~45 instructions per column instead of ~150; the loop is
+// issue-bound (two warps per scheduler, dependent instructions), so that is what counts.
+template <int T, int KK>
+__device__ __forceinline__ void dense_col_back(const double (&R)[T][T], double* Sc, int LD, int jn, int ti, double* wd, int* bad) {
+  // Sc = &S[ti][jn]; rows 16 ii + ti for ii >= KK (rows above the diagonal get dead values)
+#pragma unroll
+  for (int ii = KK; ii < T; ++ii) Sc[16 * ii * LD] = R[ii][KK];
+  if (16 * KK + ti == jn) {  // the pivot: its reciprocal for the next column step
+    const double v = R[KK][KK];
+    const bool okp = v > 0.0;
+    wd[jn] = __drcp_rn(okp ? v : 1.0);
+    if (!okp) *bad = 1;
+  }
+}
+template <int T, int JT>
+__device__ __forceinline__ void dense_tile_columns(double (&R)[T][T], double* S, int N, int LD, double* wd, int* bad, int ti, int tk) {
+  const double* pi = S + ti * LD + 16 * JT;  // S[ti][j]
+  const double* pk = S + tk * LD + 16 * JT;  // S[tk][j]
+  for (int jr = 0; jr < 16; ++jr, ++pi, ++pk) {
+    const int j = 16 * JT + jr;
+    if (j >= N) break;
+    __syncthreads();  // column j and 1 / d_j are in shared memory
+    const double wj = wd[j];
+    double ci[T], ck[T];
+#pragma unroll
+    for (int ii = JT; ii < T; ++ii) ci[ii] = pi[16 * ii * LD] * wj;
+#pragma unroll
+    for (int kk = JT; kk < T; ++kk) ck[kk] = pk[16 * kk * LD];
+    // column tile by column tile, the one that holds column j + 1 first: that column is then final, its owners put it
+    // back (and take the pivot's reciprocal) while everybody goes on with the rest of the update
+    const int jn = j + 1;
+    const bool owner = jn < N && tk == (jn & 15);
+#pragma unroll
+    for (int kk = JT; kk < T; ++kk) {
+#pragma unroll
+      for (int ii = kk; ii < T; ++ii) R[ii][kk] -= ci[ii] * ck[kk];
+      if (kk == JT && jr < 15 && owner) dense_col_back<T, JT>(R, S + ti * LD + jn, LD, jn, ti, wd, bad);
+      if (kk == JT + 1 && jr == 15 && owner) dense_col_back<T, (JT + 1 < T ? JT + 1 : JT)>(R, S + ti * LD + jn, LD, jn, ti, wd, bad);
+    }
+  }
+}
+template <int T, int JT>
+struct DenseTiles {
+  static __device__ __forceinline__ void run(double (&R)[T][T], double* S, int N, int LD, double* wd, int* bad, int ti, int tk) {
+    dense_tile_columns<T, JT>(R, S, N, LD, wd, bad, ti, tk);
+    if (16 * (JT + 1) < N) DenseTiles<T, JT + 1>::run(R, S, N, LD, wd, bad, ti, tk);
+  }
+};
+template <int T>
+struct DenseTiles<T, T> {
+  static __device__ __forceinline__ void run(double (&)[T][T], double*, int, int, double*, int*, int, int) {}
+};
+template <int T>
+__device__ __noinline__ void dense_ldlt_tiles(double* S, int N, int LD, double* wd, int* bad) {
+  const int tid = threadIdx.x, ti = tid >> 4, tk = tid & 15;
+  double R[T][T];  // (only kk <= ii is used)
+#pragma unroll
+  for (int ii = 0; ii < T; ++ii)
+#pragma unroll
+    for (int kk = 0; kk <= ii; ++kk) R[ii][kk] = S[(16 * ii + ti) * LD + 16 * kk + tk];
+  if (tid == 0) {
+    const double d = S[0];
+    const bool okp = d > 0.0;
+    wd[0] = __drcp_rn(okp ? d : 1.0);
+    if (!okp) *bad = 1;
+  }
+  DenseTiles<T, 0>::run(R, S, N, LD, wd, bad, ti, tk);
+  __syncthreads();
+}
 // One damped solve of the frame-chain + globals system and (optionally) the state update, all in one launch.
 __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveArgs a) {
   extern __shared__ double smem[];
@@ -843,17 +952,18 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     const ChainLevel& top = a.lev[a.n_levels - 1];
     const int nt = top.n, n_slots = sharded ? a.x.nranks : nt, N = G + n_slots * FD;
     const int slot0 = sharded ? a.x.rank : 0;  // slot of top node 0
-    double* S = smem;         // [N][N] lower triangle; unscaled columns u_ij (L D L^T: L_ij = u_ij / d_j)
-    double* rhs = S + N * N;  // row N of the same elimination: u_Nj
-    double* wd = rhs + N;     // 1 / d_j
+    const int LD = dense_ld(N), RT = dense_rows(N);  // odd leading dimension: a column walks all shared-memory banks
+    double* S = smem;          // [RT][LD] lower triangle; unscaled columns u_ij (L D L^T: L_ij = u_ij / d_j)
+    double* rhs = S + N * LD;  // row N of the same elimination: u_Nj
+    double* wd = S + RT * LD;  // 1 / d_j
     const double* sc = a.scale + nfp;
     if (tid == 0) bad_dense = 0;
-    for (int e = tid; e < N * N + N; e += kCsThreads) S[e] = 0.0;
+    for (int e = tid; e < RT * LD; e += kCsThreads) S[e] = 0.0;
     __syncthreads();
     if (sharded) {
       for (int e = tid; e < NS; e += kCsThreads) {
         const double v = __ldcg(a.dsys + e);
-        if (e < G * G) S[(e / G) * N + e % G] = v;
+        if (e < G * G) S[(e / G) * LD + e % G] = v;
         else rhs[e - G * G] = v;
       }
       for (int k = 0; k < n_slots; ++k) {
@@ -862,33 +972,44 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
         for (int e = tid; e < TB; e += kCsThreads) {
           const double v = __ldcg(blk + e);
           if (e < 81) {
-            S[(o + e / FD) * N + o + e % FD] = v;
+            S[(o + e / FD) * LD + o + e % FD] = v;
           } else if (e < 162) {
             if (k > 0) {
               const int r = (e - 81) / FD, c = (e - 81) % FD;
-              S[(op + r) * N + o + c] = v;
-              S[(o + c) * N + op + r] = v;
+              S[(op + r) * LD + o + c] = v;
+              S[(o + c) * LD + op + r] = v;
             }
           } else if (e < 162 + FD * G) {
             const int r = (e - 162) / G, c = (e - 162) % G;
-            S[(o + r) * N + c] = v;
-            S[c * N + o + r] = v;
+            S[(o + r) * LD + c] = v;
+            S[c * LD + o + r] = v;
           } else {
             rhs[o + e - 162 - FD * G] = v;
           }
         }
       }
     } else {
-    for (int e = tid; e < NS; e += kCsThreads) {
-      const double p = __ldcg(a.Ssum + e);
-      if (e < G * G) {
-        const int r = e / G, c = e - r * G;
-        double v = b.C[e] * sc[r] * sc[c] - p;
-        if (r == c) v += a.D2x ? a.D2x[nfp + r] : lm_damp(b.C[e], sc[r], rinv);
-        S[r * N + c] = v;
-      } else {
-        const int r = e - G * G;
-        rhs[r] = -b.gc[r] * sc[r] + p;
+    for (int e0 = tid; e0 < NS; e0 += 4 * kCsThreads) {  // four entries per round: their loads are all in flight together
+      double p[4], cv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kCsThreads;
+        p[u] = e < NS ? __ldcg(a.Ssum + e) : 0.0;
+        cv[u] = e < NS ? b.C[e] : 0.0;  // C | gc are contiguous
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kCsThreads;
+        if (e >= NS) continue;
+        if (e < G * G) {
+          const int r = e / G, c = e - r * G;
+          double v = cv[u] * sc[r] * sc[c] - p[u];
+          if (r == c) v += a.D2x ? a.D2x[nfp + r] : lm_damp(cv[u], sc[r], rinv);
+          S[r * LD + c] = v;
+        } else {
+          const int r = e - G * G;
+          rhs[r] = -cv[u] * sc[r] + p[u];
+        }
       }
     }
     const bool add = top.addA != nullptr;
@@ -896,55 +1017,36 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       const int o = G + t * FD;
       for (int e = tid; e < FD * FD; e += kCsThreads) {
         const int r = e / FD, c = e - r * FD;
-        S[(o + r) * N + o + c] = __ldcg(top.A + static_cast<int64_t>(t) * FD * FD + e) + (add ? __ldcg(top.addA + static_cast<int64_t>(t) * FD * FD + e) : 0.0);
+        S[(o + r) * LD + o + c] = __ldcg(top.A + static_cast<int64_t>(t) * FD * FD + e) + (add ? __ldcg(top.addA + static_cast<int64_t>(t) * FD * FD + e) : 0.0);
         if (t > 0) {
           const int op = o - FD;
           const double u = __ldcg(top.U + static_cast<int64_t>(t) * FD * FD + e);  // H[t-1, t]
-          S[(op + r) * N + o + c] = u;
-          S[(o + c) * N + op + r] = u;
+          S[(op + r) * LD + o + c] = u;
+          S[(o + c) * LD + op + r] = u;
         }
       }
       for (int e = tid; e < FD * G; e += kCsThreads) {
         const int r = e / G, c = e - r * G;
         const double v = __ldcg(top.E + static_cast<int64_t>(t) * FD * G + e) + (add ? __ldcg(top.addE + static_cast<int64_t>(t) * FD * G + e) : 0.0);
-        S[(o + r) * N + c] = v;
-        S[c * N + o + r] = v;
+        S[(o + r) * LD + c] = v;
+        S[c * LD + o + r] = v;
       }
       for (int e = tid; e < FD; e += kCsThreads)
         rhs[o + e] = -(__ldcg(top.g + static_cast<int64_t>(t) * FD + e) + (add ? __ldcg(top.addg + static_cast<int64_t>(t) * FD + e) : 0.0));
     }
     }
-    // right-looking L D L^T on the lower triangle, the right-hand side riding along as row N: one barrier per
-    // column, 16 x 16 thread tiling of the trailing update.  The reciprocal of the next pivot is taken by the one
-    // thread that finishes that pivot, while the others are still in their share of the update (a division on every
-    // thread's path was a third of the column time).
+    // right-looking L D L^T on the lower triangle, the right-hand side riding along as row N.  The matrix lives in
+    // registers for the whole factorisation (16 x 16 thread tiling: thread (ti, tk) owns the elements (i, k) = (ti, tk)
+    // mod 16); a finished column goes back to shared memory, is read by everybody after ONE barrier, and nothing else
+    // touches shared memory.  (The shared-memory version of this loop — read, update, write every element every column —
+    // was 0.35 us per column; a sharded run has up to 135 columns.)
     dt0 = clock64();
-    const int ti = tid >> 4, tk = tid & 15;
     __syncthreads();  // the system is assembled
-    if (tid == 0) {
-      const double d = S[0];
-      const bool okp = d > 0.0;
-      wd[0] = 1.0 / (okp ? d : 1.0);
-      if (!okp) bad_dense = 1;
-    }
-    for (int j = 0; j < N; ++j) {
-      __syncthreads();
-      const double wj = wd[j];
-      for (int i = j + 1 + ti; i <= N; i += 16) {
-        double* row = i < N ? S + i * N : rhs;
-        const double lw = row[j] * wj;
-        const int kmax = i < N ? i : N - 1;
-        for (int k = j + 1 + tk; k <= kmax; k += 16) {
-          const double v = row[k] - lw * S[k * N + j];
-          row[k] = v;
-          if (k == j + 1 && i == j + 1) {  // the next pivot is final: its reciprocal now
-            const bool okp = v > 0.0;
-            wd[j + 1] = 1.0 / (okp ? v : 1.0);
-            if (!okp) bad_dense = 1;
-          }
-        }
-      }
-    }
+    const int tiles = dense_tiles(N);
+    if (tiles == 6) dense_ldlt_tiles<6>(S, N, LD, wd, &bad_dense);
+    else if (tiles == 7) dense_ldlt_tiles<7>(S, N, LD, wd, &bad_dense);
+    else if (tiles == 9) dense_ldlt_tiles<9>(S, N, LD, wd, &bad_dense);
+    else dense_ldlt_smem(S, N, LD, wd, &bad_dense);
     __syncthreads();
     if (prof) { const long long t = clock64(); a.prof[53] += static_cast<unsigned long long>(t - dt0); dt0 = t; }
     if (warp == 0) {  // x_i = (u_Ni - sum_{k>i} u_ki x_k) / d_i
@@ -952,7 +1054,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
         const double xi = rhs[i] * wd[i];
         __syncwarp();
         if (lane == 0) rhs[i] = xi;
-        for (int k = lane; k < i; k += 32) rhs[k] -= S[i * N + k] * xi;
+        for (int k = lane; k < i; k += 32) rhs[k] -= S[i * LD + k] * xi;
         __syncwarp();
       }
     }
@@ -971,11 +1073,25 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
         for (int r = 0; r < FD; ++r) d[r] = bd ? 0.0 : rhs[G + (slot0 + tid) * FD + r];
         chain_update_frame(a, b, rinv, a.n_levels > 1 ? top.orig[tid] : tid, d, acc);
       }
-      // globals: cameras + IMU parameters (one thread)
+      // globals: cameras + IMU parameters (one thread; the step.g / step.D2.step sums over the globals by its warp)
+      double gs0 = 0.0, gs1 = 0.0;
+      if (a.do_update && warp == kCsThreads / 32 - 1) {
+        for (int k = lane; k < G; k += 32) {
+          const double d2 = a.D2x ? a.D2x[nfp + k] : lm_damp(b.C[k * G + k], sc[k], rinv);
+          const double dk = bd ? 0.0 : rhs[k];
+          gs0 += dk * b.gc[k] * sc[k];
+          gs1 += dk * dk * d2;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {  // the total lands in lane 31
+          const double t0 = __shfl_up_sync(0xffffffffu, gs0, o), t1 = __shfl_up_sync(0xffffffffu, gs1, o);
+          if (lane >= o) { gs0 += t0; gs1 += t1; }
+        }
+      }
       if (a.do_update && tid == kCsThreads - 1) {
         const double* x_cur = a.state[a.ctl->cur];
         double* x_new = a.state[1 - a.ctl->cur];
-        double g4[4] = {0.0, 0.0, 0.0, 0.0};
+        double g4[4] = {gs0, gs1, 0.0, 0.0};
         for (int c = 0; c < a.dp.n_cams; ++c) {
           const CamInfo& ci = a.dp.cams[c];
           const double* x = x_cur + a.dp.off_cam + kCamStateStride * c;
@@ -1002,12 +1118,6 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
             g4[2] += dd * dd;
             g4[3] += xo[k] * xo[k];
           }
-        }
-        for (int k = 0; k < G; ++k) {
-          const double d2 = a.D2x ? a.D2x[nfp + k] : lm_damp(b.C[k * G + k], sc[k], rinv);
-          const double dk = bd ? 0.0 : rhs[k];
-          g4[0] += dk * b.gc[k] * sc[k];
-          g4[1] += dk * dk * d2;
         }
         for (int q = 0; q < 4; ++q) a.step_part[4 * static_cast<int64_t>(nb) + q] = g4[q];
       }
