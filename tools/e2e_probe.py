@@ -6,6 +6,8 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("E2E_TORCH"):  # bench.py runs with torch imported (torch.distributed plumbing): same timings?
+    import torch  # noqa: F401
 from vicalib_b200 import synth
 from vicalib_b200.capi import Calibrator
 
@@ -18,6 +20,13 @@ g.load(p)
 g.set_flags(**flags)
 g.set_options(max_iters=K, function_tol=0.0, gradient_tol=0.0, param_tol=0.0)
 g.iterate(3)
+if os.environ.get("E2E_FRESH"):  # bench.py times a second handle while the first is still alive
+    g0 = g
+    g = Calibrator()
+    g.load(p)
+    g.set_flags(**flags)
+    g.set_options(max_iters=K, function_tol=0.0, gradient_tol=0.0, param_tol=0.0)
+    g.solve()
 for mode in ("iterate", "solve(cb)"):
     best = None
     for rep in range(6):

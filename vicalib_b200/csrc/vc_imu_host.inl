@@ -29,12 +29,13 @@ static void imu_free(vcgpu_handle* h) {
 }
 
 static int imu_prepare(vcgpu_handle* h) {
-  imu_free(h);
   const DevProblem& dp = h->dp;
   if (!dp.inertial) return VCGPU_OK;
   if (dp.n_frames < 2) return fail(h, VCGPU_ERR_INVALID, "inertial terms need at least two frames");
-  vc::ImuDev* d = new vc::ImuDev();
-  h->imu = d;
+  // the host-side record lives as long as the handle: its device buffers are keyed by their address in dev_alloc's
+  // capacity table, so a re-upload of a same-sized problem allocates nothing
+  if (!h->imu) h->imu = new vc::ImuDev();
+  vc::ImuDev* d = imu_dev(h);
   const int nf = dp.n_frames, ni = nf - 1, G = dp.G, FD = 9;
   const int n = static_cast<int>(h->h_imu_t.size());
   // IMU samples SoA + the reference's running statistics (interpolation-buffer.h:70-85)
