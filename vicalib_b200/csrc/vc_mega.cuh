@@ -49,6 +49,10 @@ constexpr int kMaxRanks = 8;
 constexpr size_t kXchgBytes = 32u << 20;  // the inertial kernels' regions follow the vision kernel's (vc_xchg.cuh)
 constexpr int kXchgCOff = 409600;
 constexpr int kXchgCtlOff = 442368;
+// sharded runs: the totals summed over the ranks, as plain doubles, for this rank's CTAs (one reader per entry polls
+// the tagged words and writes here; a grid barrier later everybody reads the plain copy)
+constexpr int kXchgPlainS = kXchgCtlOff + 64;
+constexpr int kXchgPlainC = kXchgPlainS + 32768;
 constexpr int kMegaCommFailed = 1000;  // Ctl::done value when a peer never showed up
 static_assert(kSlabLd % 16 == 4, "fragment loads need ld == 4 (mod 16)");
 enum { kPCost = 0, kPGf2, kPDotG, kPDotD, kPStep2, kPXnorm2, kPGfMax, kPNotPD };
@@ -434,18 +438,22 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
       double* S = Swork;  // [G*G] lower triangle, then rhs [G]
       ++epS;
       const int parS = static_cast<int>(epS & 1);
-      double* totS = reinterpret_cast<double*>(a.xbuf[a.rank]);  // single GPU: plain totals in the same buffer
+      // plain totals: in the exchange buffer itself on one GPU, next to the tagged words in a sharded run
+      double* totS = reinterpret_cast<double*>(a.xbuf[a.rank] + (sharded ? kXchgPlainS : 0));
       if (sharded) {
+        // every rank's CTA sums go to every rank (tagged words over NVLink); ONE thread of this grid per entry waits for
+        // them and adds them up in rank order (every rank computes the same bits)
         mega_publish(a.partS, PS, nb, PS, a, 0, parS, epS, NS + kPNotPD, -1);
+        for (int e = bid * nthreads + tid; e < PS; e += nb * nthreads) totS[e] = mega_total(a, 0, PS, parS, epS, e, e == NS + kPNotPD);
       } else {
         mega_reduce_stage1(a.partS, PS, nb, PS, totS, NS + kPNotPD, -1);
-        mark(kProfG);
-        grid.sync();
-        mark(kProfSync);
       }
+      mark(kProfG);
+      grid.sync();
+      mark(kProfSync);
       for (int e = tid; e < NS; e += nthreads) {
         if (e < G * G && e % G > e / G) continue;  // lower triangle only
-        const double p = sharded ? mega_total(a, 0, PS, parS, epS, e, false) : __ldcg(totS + e);
+        const double p = __ldcg(totS + e);
         if (e < G * G) {
           const int r = e / G, c = e - r * G;
           if (c > r) continue;
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
         }
       }
       if (tid == 0) {
-        sc[kScNotPD] = sharded ? mega_total(a, 0, PS, parS, epS, NS + kPNotPD, true) : __ldcg(totS + NS + kPNotPD);
+        sc[kScNotPD] = __ldcg(totS + NS + kPNotPD);
         bad = 0;
       }
       __syncthreads();
@@ -747,17 +755,18 @@ __global__ void __launch_bounds__(kMegaMaxThreads, 1) lm_mega_kernel(MegaArgs a)
       double* Ctrial = Cacc + (1 - cur) * NS;
       ++epC;
       const int parC = static_cast<int>(epC & 1);
-      double* totC = reinterpret_cast<double*>(a.xbuf[a.rank] + kXchgCOff);
+      double* totC = reinterpret_cast<double*>(a.xbuf[a.rank] + (sharded ? kXchgPlainC : kXchgCOff));
       if (sharded) {
         mega_publish(a.partC, PC, nb, PC, a, kXchgCOff, parC, epC, NP + kPGfMax, NP + kPNotPD);
+        for (int e = bid * nthreads + tid; e < PC; e += nb * nthreads)
+          totC[e] = mega_total(a, kXchgCOff, PC, parC, epC, e, e == NP + kPGfMax || e == NP + kPNotPD);
       } else {
         mega_reduce_stage1(a.partC, PC, nb, PC, totC, NP + kPGfMax, NP + kPNotPD);
-        mark(kProfD);
-        grid.sync();
-        mark(kProfSync);
       }
-      for (int e = tid; e < PC; e += nthreads)
-        totc[e] = sharded ? mega_total(a, kXchgCOff, PC, parC, epC, e, e == NP + kPGfMax || e == NP + kPNotPD) : __ldcg(totC + e);
+      mark(kProfD);
+      grid.sync();
+      mark(kProfSync);
+      for (int e = tid; e < PC; e += nthreads) totc[e] = __ldcg(totC + e);
       __syncthreads();
       for (int e = tid; e < NS; e += nthreads) {  // packed per-camera blocks -> dense C | gc
         const int r = e < G * G ? e / G : e - G * G;

@@ -452,7 +452,7 @@ static int mega_prepare(vcgpu_handle* h) {
   }
   const size_t PS = static_cast<size_t>(dp.G) * dp.G + dp.G + vc::kMegaPartExtra;
   const size_t PC = static_cast<size_t>(dp.n_cams) * vc::kCgStride + vc::kMegaPartExtra;
-  if (4 * h->nranks * PS > static_cast<size_t>(vc::kXchgCOff) ||
+  if (PS > 32768 || 4 * h->nranks * PS > static_cast<size_t>(vc::kXchgCOff) ||
       4 * h->nranks * PC > static_cast<size_t>(vc::kXchgCtlOff - vc::kXchgCOff))
     return VCGPU_OK;  // the totals do not fit the totals buffer: multi-launch engine
   if (!h->xchg_local) {  // single GPU: the totals buffer is local only
