@@ -199,9 +199,10 @@ def roofline(g, stages, peaks, peak_src, p, K0, device, workload, engine, step_s
             want = "eval_mega_kernel" if t_ev >= t_cs else "chain_solve_kernel"
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "ncu_top_kernel.json")) as f:
-            cap = json.load(f)
-        if cap.get("workload") == workload and cap.get("kernel") == want:
-            traffic = cap.get("dram_bytes_per_launch")
+            caps = json.load(f)
+        for cap in caps.get("captures", [caps]):  # one entry per captured workload
+            if cap.get("workload") == workload and want in cap.get("kernels", {}):
+                traffic = cap["kernels"][want].get("dram_bytes_per_launch")
     except Exception:
         pass
     phase = {"stage": top, "kernel": kname, "ms": top_s * 1e3, "flops": flops, "achieved_tflops": flops / top_s / 1e12,

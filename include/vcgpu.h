@@ -222,11 +222,15 @@ int vcgpu_set_profiling(vcgpu_handle* h, int profile, int flush_l2);
 int vcgpu_get_stage_times(vcgpu_handle* h, double ms_total[VCGPU_STAGE_COUNT], int64_t launches[VCGPU_STAGE_COUNT]);
 /* raw device phase clocks (ns, summed over the iterations since vcgpu_set_profiling) of the persistent inertial kernels:
  * chain_solve_kernel: elimination level l at [l], Schur reduce [10], dense solve [11], back-substitution level at [12 + k],
- * step statistics [22]; eval_mega_kernel: tasks [32], IMU accumulate [33], reduce [34], decide [35], weights [36] */
+ * state update + step statistics [22], tail of the deferred UpdateImuWeights [23]; eval_mega_kernel: tasks [32], IMU
+ * accumulate [33], reduce [34], decide [35], weights [36] (only when the update is not deferred into the solve launch) */
 int vcgpu_get_phase_clocks(vcgpu_handle* h, uint64_t ns[64]);
 
-/* ---- multi-GPU: one process per GPU, frames sharded contiguously, one NCCL all-reduce of the
- * reduced normal equations per iteration ---------------------------------------------------- */
+/* ---- multi-GPU: one process per GPU of one node, frames sharded contiguously.  Two reductions per LM iteration (the
+ * reduced system before the dense solve; global blocks + cost / step scalars before the decision), both INSIDE the
+ * persistent kernels over NVLink peer memory: vcgpu_comm_init maps a 32 MiB totals buffer of every rank into every rank
+ * (CUDA IPC; NCCL is used to pass the handles).  If the mapping is not possible the same reductions run as NCCL
+ * all-reduces between kernel launches.  Every rank must issue the same sequence of calls. ---------------------------- */
 #define VCGPU_UNIQUE_ID_BYTES 128
 int vcgpu_comm_unique_id(uint8_t id[VCGPU_UNIQUE_ID_BYTES]);
 int vcgpu_comm_init(vcgpu_handle* h, const uint8_t id[VCGPU_UNIQUE_ID_BYTES], int rank, int nranks);
