@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <stdexcept>
 #include <vector>
 
 #include "../../vicalib_b200/host/vicalib_task_checks.h"
@@ -123,6 +124,43 @@ int main(int argc, char** argv) {
       for (int k = 0; k < 3; ++k) dp = std::max(dp, std::fabs(ip.back().t_wp_.d[4 + k] - cal.GetFrame(1)->t_wp_.d[4 + k]));
     }
     std::fprintf(o, "integration_poses %zu %.6g %.17g\n", ip.size(), dp, ip.empty() ? 0.0 : ip.back().time_);
+  }
+  // GetSolutionCovariance (vicalibrator.h:802-857): G, asymmetry, smallest / largest diagonal entry of the active blocks
+  try {
+    int G = 0;
+    const std::vector<double> cov = cal.GetSolutionCovariance(&G);
+    double asym = 0, dmin = 1e300, dmax = 0;
+    for (int r = 0; r < G; ++r) {
+      for (int c = 0; c < G; ++c) asym = std::max(asym, std::fabs(cov[r * G + c] - cov[c * G + r]));
+      if (cov[r * G + r] != 0.0) { dmin = std::min(dmin, cov[r * G + r]); dmax = std::max(dmax, cov[r * G + r]); }
+    }
+    std::fprintf(o, "covariance %d %.6g %.6g %.6g", G, asym, dmin, dmax);
+    for (int r = 0; r < G; ++r) std::fprintf(o, " %.17g", cov[r * G + r]);
+    std::fprintf(o, "\n");
+  } catch (const std::exception& e) {  // a short inertial trajectory leaves J^T J singular to working precision
+    std::fprintf(o, "covariance -1\n");
+  }
+  // pose seeds the way VicalibTask::AddSuperFrame gets them (vicalib-task.cc:322-349): PnP on camera 0's corners of the
+  // first frames, against the solved frame poses
+  {
+    const int nv = std::min(nf, 6);
+    std::vector<ViCalibrator::PnpView> views(nv);
+    for (int v = 0; v < nv; ++v) views[v].camera_id = 0;
+    for (int64_t i = 0; i < nobs; ++i)
+      if (oc[i] == 0 && of[i] < nv) {
+        views[of[i]].pixels.push_back(Vector2d{{pc[2 * i], pc[2 * i + 1]}});
+        views[of[i]].target_points.push_back(Vector3d{{pw[3 * i], pw[3 * i + 1], pw[3 * i + 2]}});
+      }
+    std::vector<bool> ok;
+    const std::vector<SE3d> seeds = cal.InitialPosesFromTarget(views, &ok);
+    double worst = 0;
+    int n_ok = 0;
+    for (int v = 0; v < nv; ++v) {
+      if (!ok[v]) continue;
+      ++n_ok;
+      for (int k = 0; k < 3; ++k) worst = std::max(worst, std::fabs(seeds[v].d[4 + k] - cal.GetFrame(v)->t_wp_.d[4 + k]));
+    }
+    std::fprintf(o, "pnp_seeds %d %d %.6g\n", nv, n_ok, worst);
   }
   fclose(o);
   return 0;

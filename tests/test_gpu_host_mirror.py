@@ -68,6 +68,14 @@ def test_vision_only_matches_python_binding(tmp_path):
         assert np.allclose(out[f"T_ck{c}"], np.concatenate([st["q_ck"][c], st["p_ck"][c]]), atol=1e-10)
         assert out[f"rmse{c}"] < 0.16
     assert out["solves"] == 1
+    # GetSolutionCovariance through the mirror == vcgpu_get_covariance at the same solution: symmetric, positive diagonal
+    cov = g.covariance()
+    G, asym, dmin, dmax = out["covariance"][:4]
+    assert int(G) == cov.shape[0] == 13 + 11 and asym <= 1e-12 * dmax and dmin > 0
+    assert np.allclose(out["covariance"][4:], np.diag(cov), rtol=1e-6)
+    # pose seeds (PosePnPRansac + T_cw^-1 T_ck, vicalib-task.cc:322-349) land on the solved frame poses (0.1 px noise)
+    nv, n_ok, worst = out["pnp_seeds"]
+    assert nv == n_ok == 6 and worst < 2e-3
     # cameras.xml: vision RDF (identity) and T_wc = T_ck^-1 (vicalibrator.h:221-224)
     assert xml.count("<camera>") == 2 and 'type="calibu_fu_fv_u0_v0_k1_k2_k3"' in xml and 'type="calibu_fu_fv_u0_v0_w"' in xml
     params = re.findall(r"<params> \[ (.*?) \] </params>", xml)

@@ -99,6 +99,23 @@ static int eval_reproj(vcgpu_handle* h, int which, bool jac, bool apply_loss, co
   return VCGPU_OK;
 }
 
+// Opt-in to more than 48 KB of dynamic shared memory for every kernel of the multi-launch engine that is launched with a
+// G-dependent amount (8 cameras + IMU: NS = G^2 + G = 20 592 doubles = 161 KB).  The attribute is per device and function:
+// set once per handle (a process may hold handles on several devices).
+static int kernel_smem_optin(vcgpu_handle* h) {
+  if (h->smem_optin_done) return VCGPU_OK;
+  const int big = 200 * 1024;
+  CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemDoubles * sizeof(double))));
+  CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemDoubles * sizeof(double))));
+  CUDA_TRY(h, cudaFuncSetAttribute(frame_solve_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_TRY(h, cudaFuncSetAttribute(reduce_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_TRY(h, cudaFuncSetAttribute(global_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_TRY(h, cudaFuncSetAttribute(chain_eliminate_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_TRY(h, cudaFuncSetAttribute(dense_solve_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  h->smem_optin_done = true;
+  return VCGPU_OK;
+}
+
 // ------------------------------------------------------------------ persistent inertial kernels
 // chain_solve_kernel + eval_mega_kernel (vc_imu_mega.cuh, vc_imu_eval_mega.cuh): two cooperative launches per iteration.
 // Frame-sharded runs use them too when the ranks' totals buffers are mapped (vcgpu_comm_init): the two reductions of
@@ -260,12 +277,7 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     fa.pw = h->d_pw; fa.pc = h->d_pc; fa.n_obs = h->n_obs; fa.mask = h->d_mask;
     fa.out[0] = h->blk[0]; fa.out[1] = h->blk[1]; fa.Cg = h->d_Cg; fa.cost_part = h->d_cost_part;
     const size_t fsm = kFusedSmemDoubles * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-      CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
-      CUDA_TRY(h, cudaFuncSetAttribute(fused_build_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));
-      attr_done = true;
-    }
+    VC_TRY(kernel_smem_optin(h));
     if (dp.fd == 6) fused_build_kernel<6><<<dp.n_frames, kFusedThreads, fsm, h->stream>>>(fa);
     else fused_build_kernel<9><<<dp.n_frames, kFusedThreads, fsm, h->stream>>>(fa);
     ++h->launches;
@@ -307,6 +319,7 @@ static int evaluate_into(vcgpu_handle* h, int which, bool with_step, int decide_
     ra.n_step_part = h->n_step_part - (h->rank == 0 ? 0 : 1);
     ra.n_frames_fd = dp.n_frames * dp.fd;
     ra.out[0] = h->blk[0]; ra.out[1] = h->blk[1]; ra.scalars = h->d_scalars; ra.counter = h->d_counter;
+    VC_TRY(kernel_smem_optin(h));
     reduce_finalize_kernel<<<kReduceBlocks, 256, NS * sizeof(double), h->stream>>>(ra);
     ++h->launches;
     if (split) {
@@ -363,11 +376,7 @@ static int solve_and_update(vcgpu_handle* h, const double* D2x, bool with_update
       sa.dp = dp; sa.b[0] = h->blk[0]; sa.b[1] = h->blk[1]; sa.ctl = h->d_ctl; sa.scale = h->d_scale; sa.D2x = D2x;
       sa.X = h->d_X; sa.Spart = h->d_Spart; sa.scalars = h->d_scalars;
       const size_t ssm = (NS + static_cast<size_t>(kSolveWarps) * 2 * 6 * (dp.G + 1)) * sizeof(double);
-      static bool attr_done = false;
-      if (!attr_done) {
-        CUDA_TRY(h, cudaFuncSetAttribute(frame_solve_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_done = true;
-      }
+      VC_TRY(kernel_smem_optin(h));
       frame_solve_kernel<6><<<h->n_solve_blocks, kSolveThreads, ssm, h->stream>>>(sa);
       ++h->launches;
     }
@@ -384,6 +393,7 @@ static int solve_and_update(vcgpu_handle* h, const double* D2x, bool with_update
       ga.dp = dp; ga.b[0] = h->blk[0]; ga.b[1] = h->blk[1]; ga.ctl = h->d_ctl; ga.scale = h->d_scale; ga.D2x = D2x;
       ga.Ssum = h->d_Ssum; ga.Spart = h->d_Spart; ga.n_part = sum_in_solve ? h->n_solve_blocks : 0;
       ga.delta = h->d_delta; ga.scalars = h->d_scalars;
+      VC_TRY(kernel_smem_optin(h));
       global_solve_kernel<<<1, 256, NS * sizeof(double), h->stream>>>(ga);
       ++h->launches;
     }

@@ -124,6 +124,7 @@ static int imu_prepare(vcgpu_handle* h) {
 }
 
 static int wts_join(vcgpu_handle* h);
+static int kernel_smem_optin(vcgpu_handle* h);
 static int imu_evaluate(vcgpu_handle* h, int which, bool apply_loss, int* n_cost, const double* mask_dev = nullptr) {
   VC_TRY(wts_join(h));  // the residuals are weighted
   vc::ImuDev* d = imu_dev(h);
@@ -167,12 +168,7 @@ static int imu_chain_eliminate(vcgpu_handle* h, const double* D2x) {
   ++h->launches;
   const size_t w_cols = 2 * FD + G + 1;
   const size_t esm = (NS + 3 * FD * FD + FD * G + FD + static_cast<size_t>(kChainC - 1) * FD * (FD + w_cols)) * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(h, cudaFuncSetAttribute(chain_eliminate_kernel<FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_TRY(h, cudaFuncSetAttribute(dense_solve_kernel<FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  VC_TRY(kernel_smem_optin(h));
   int part = 0;
   for (size_t l = 0; l + 1 < d->levels.size(); ++l) {
     ElimArgs ea;

@@ -208,6 +208,7 @@ struct vcgpu_handle {
   double* d_sep = nullptr;        // [2][nranks*9]: summed diag(B) and g of the separator frames (sharded inertial runs)
   unsigned long long* d_csync = nullptr;  // persistent inertial solve: two {barrier counter, weights queue} pairs
   unsigned cs_launches = 0;
+  bool smem_optin_done = false;   // dynamic shared-memory opt-ins of the multi-launch engine's kernels (per device)
   double* d_dsys = nullptr;       // persistent sharded inertial solve: the summed dense system in block form
   unsigned xchg_tag_dense = 0, xchg_tag_eval = 0;  // exchange numbers of the persistent inertial kernels (vc_xchg.cuh)
   double* d_dense = nullptr;      // [N*N+N] all-reduced dense system, N = G + 9*nranks

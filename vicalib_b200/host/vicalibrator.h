@@ -463,6 +463,60 @@ class ViCalibrator {
     return poses;
   }
 
+  // GetSolutionCovariance (vicalibrator.h:802-857, behind COMPUTE_VICALIB_COVARIANCE upstream): covariance of the
+  // calibration parameters at the current solution, tangent space, G x G row-major — per camera (w_ck 3 | p_ck 3 |
+  // intrinsics K), then (g 2 | b 6 | sf 6 | ts 1) when the inertial terms are on; constant blocks have zero rows /
+  // columns (ceres::Covariance convention).  Call after the solve has finished (not while IsRunning()).
+  std::vector<double> GetSolutionCovariance(int* n_globals = nullptr) {
+    int G = 0;
+    Check(vcgpu_num_globals(h_, &G), "num_globals");
+    std::vector<double> cov(static_cast<size_t>(G) * G, 0.0);
+    Check(vcgpu_get_covariance(h_, cov.data()), "get_covariance");
+    if (n_globals) *n_globals = G;
+    return cov;
+  }
+
+  // Pose seeds for AddFrame: what VicalibTask::AddSuperFrame computes per frame and camera with
+  // calibu::PosePnPRansac(camera, ellipses, target.Circles3D(), ellipse_target_map, 0, 0, &t_cw) and
+  // t_wp = t_cw.inverse() * t_ck (src/vicalib-task.cc:322-325, 341-349) — here for ALL views in one device call.
+  // views[v] = (camera id, detected centres in pixels, their target points); the cameras must have been added.
+  // Returns one T_wp per view (identity with ok[v] = false when fewer than 4 usable correspondences).
+  struct PnpView {
+    int camera_id;
+    std::vector<Vector2d> pixels;
+    std::vector<Vector3d> target_points;
+  };
+  std::vector<SE3d> InitialPosesFromTarget(const std::vector<PnpView>& views, std::vector<bool>* ok = nullptr, int robust_its = 0,
+                                           double robust_tol = 0.0) {
+    UploadCameras();
+    std::vector<int32_t> cam(views.size()), count(views.size());
+    std::vector<int64_t> start(views.size());
+    std::vector<double> pix, pw;
+    for (size_t v = 0; v < views.size(); ++v) {
+      VICALIB_CHECK(views[v].pixels.size() == views[v].target_points.size(), "one target point per detected centre");
+      cam[v] = views[v].camera_id;
+      start[v] = static_cast<int64_t>(pix.size() / 2);
+      count[v] = static_cast<int32_t>(views[v].pixels.size());
+      for (size_t k = 0; k < views[v].pixels.size(); ++k) {
+        pix.push_back(views[v].pixels[k][0]); pix.push_back(views[v].pixels[k][1]);
+        for (int q = 0; q < 3; ++q) pw.push_back(views[v].target_points[k][q]);
+      }
+    }
+    std::vector<double> T_cw(views.size() * 7, 0.0);
+    std::vector<int32_t> used(views.size(), 0);
+    Check(vcgpu_pose_pnp_ransac(h_, static_cast<int>(views.size()), cam.data(), start.data(), count.data(), pix.data(), pw.data(),
+                                robust_its, robust_tol, T_cw.data(), nullptr, used.data()), "pose_pnp_ransac");
+    std::vector<SE3d> out(views.size());
+    if (ok) ok->assign(views.size(), false);
+    for (size_t v = 0; v < views.size(); ++v) {
+      if (used[v] < 4) continue;
+      const SE3d t_cw(&T_cw[7 * v], &T_cw[7 * v + 4]);
+      out[v] = t_cw.inverse() * cameras_[views[v].camera_id]->T_ck;
+      if (ok) (*ok)[v] = true;
+    }
+    return out;
+  }
+
   void PrintResults() {  // :536-544
     std::printf("------------------------------------------\n");
     for (size_t c = 0; c < cameras_.size(); ++c) {
@@ -486,6 +540,22 @@ class ViCalibrator {
   }
   void Check(int rc, const char* what) {
     if (rc != VCGPU_OK) throw std::runtime_error(std::string(what) + ": " + vcgpu_last_error(h_));
+  }
+
+  // the cameras alone (models, intrinsics, T_ck): what the pose initialisation needs before any frame exists
+  void UploadCameras() {
+    const int nc = static_cast<int>(cameras_.size());
+    VICALIB_CHECK(nc > 0, "no camera added");
+    std::vector<int32_t> model(nc);
+    std::vector<double> intr(10 * static_cast<size_t>(nc), 0.0), q(4 * static_cast<size_t>(nc)), p(3 * static_cast<size_t>(nc));
+    for (int c = 0; c < nc; ++c) {
+      model[c] = cameras_[c]->camera->ModelId();
+      const std::vector<double>& pr = cameras_[c]->camera->GetParams();
+      std::copy(pr.begin(), pr.end(), intr.begin() + 10 * c);
+      std::memcpy(&q[4 * c], cameras_[c]->T_ck.d, 4 * sizeof(double));
+      std::memcpy(&p[3 * c], cameras_[c]->T_ck.d + 4, 3 * sizeof(double));
+    }
+    Check(vcgpu_set_cameras(h_, nc, model.data(), intr.data(), q.data(), p.data()), "set_cameras");
   }
 
   // SetupProblem (vicalibrator.h:548-679): hand the parameter blocks, residual data and masks to the device
