@@ -503,7 +503,13 @@ def oracle_rate(p, threads, iters, warm=2):
 
     t_w, _, _ = run(warm)
     t_a, o, s = run(warm + iters)
-    dt = max(t_a - t_w, 1e-9)
+    # on a noisy host and with few iterations the difference of the two runs can be anything, even negative: never report
+    # less than half of the time the iterations take if every iteration (and the initial evaluation, counted as one)
+    # costs the same share of the longer run
+    even = t_a * iters / (warm + iters + 1)
+    dt = t_a - t_w
+    if dt < 0.5 * even:
+        dt = even
     return iters / dt, t_a, o, s
 
 
