@@ -192,8 +192,13 @@ static int imu_mega_solve(vcgpu_handle* h, const double* D2x, bool do_update, bo
   imu_mega_xchg(h, &ca.x, kXchgImuDenseOff, imu_mega_dense_stride(dp), h->nranks > 1 ? ++h->xchg_tag_dense : 0u);
   ca.sepdiag = h->nranks > 1 ? h->d_sep : nullptr;
   ca.dsys = h->d_dsys;
-  static const int n_solver_env = std::getenv("VCGPU_N_SOLVER") ? std::atoi(std::getenv("VCGPU_N_SOLVER")) : 16;
-  ca.wts_on = deferred_weights ? 1 : 0; ca.n_solver = n_solver_env;
+  // CTAs that stay with the solve while the others work the weights queue: as many as leave one 16-interval task per
+  // leaving CTA (the update then takes one round), between 16 and 32 (measured on the target workload: 10..20 within
+  // 2 %, 24 — one task too many for one round — 14 % slower)
+  static const int n_solver_env = std::getenv("VCGPU_N_SOLVER") ? std::atoi(std::getenv("VCGPU_N_SOLVER")) : 0;
+  const int wtasks = (dp.n_frames - 1 + 15) / 16;
+  ca.wts_on = deferred_weights ? 1 : 0;
+  ca.n_solver = n_solver_env > 0 ? n_solver_env : std::min(32, std::max(16, h->imu_mega_grid - wtasks - 4));
   ca.buf = d->buf; ca.ftime = d->ftime; ca.wsqrt = h->d_wsqrt; ca.sigma_g = h->sigma_g; ca.sigma_a = h->sigma_a;
   const int par = static_cast<int>(h->cs_launches++ & 1u);
   ca.sync = h->d_csync + 4 * par; ca.sync_next = h->d_csync + 4 * (1 - par);
