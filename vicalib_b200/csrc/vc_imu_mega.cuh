@@ -46,7 +46,7 @@ struct ChainSolveArgs {
   const double* D2x;            // explicit damping (inspection hook / dogleg) or null: LM rule
   const ChainLevel* lev;        // [n_levels] level descriptors (device memory)
   int n_levels;
-  double* Spart;                // [grid * kCsGroups][G*G+G]
+  double* Spart;                // [grid][G*G+G] one Schur partial per CTA
   double* Ssum;                 // [G*G+G]
   double* delta;                // scaled step [nf*9 + G]
   double* scalars;
@@ -847,10 +847,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
       n_next = (nsep2 > nb || !a.narrow_ok) ? nb : max(ns, nsep2);
     }
     n_next = min(n_next, n_act);
-    if (l + 2 == a.n_levels || bid >= n_next) {  // last level of this CTA: publish the groups' Schur partials
-      group_sync(grp);
-      double* out = a.Spart + static_cast<int64_t>(gid) * NS;
-      for (int e = gtid; e < NS; e += kCsGroup) out[e] = gsm[e];
+    if (l + 2 == a.n_levels || bid >= n_next) {  // last level of this CTA: publish its Schur partial (the two groups'
+      __syncthreads();                             // accumulators added: half as many partials for the reduction)
+      double* out = a.Spart + static_cast<int64_t>(bid) * NS;
+      const double* g1 = smem + chain_group_doubles(G);
+      for (int e = tid; e < NS; e += kCsThreads) out[e] = smem[e] + g1[e];
       if (gtid == 0 && bad_s[grp]) a.scalars[kScNotPD] = 1.0;
     }
     mark(kCsProfElim + l);
@@ -876,15 +877,15 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
         if (tid == 0) L.orig[f] = f;
       }
     }
-    double* out = a.Spart + static_cast<int64_t>(gid) * NS;
-    for (int e = gtid; e < NS; e += kCsGroup) out[e] = 0.0;
+    double* out = a.Spart + static_cast<int64_t>(bid) * NS;
+    for (int e = tid; e < NS; e += kCsThreads) out[e] = 0.0;
     if (!barrier(ns)) {
       left = true;
       break;
     }
   }
   // ------------------------------------------------------------ Schur partials -> total (fixed order), distributed
-  mega_reduce_stage1(a.Spart, NS, n_groups, NS, a.Ssum, -1, -1, bid, ns);
+  mega_reduce_stage1(a.Spart, NS, nb, NS, a.Ssum, -1, -1, bid, ns);
   mark(kCsProfReduce);
   barrier(ns);
   // ------------------------------------------------------------ sharded: the ranks' partial systems meet here
@@ -1050,12 +1051,37 @@ __global__ void __launch_bounds__(kCsThreads, 1) chain_solve_kernel(ChainSolveAr
     __syncthreads();
     if (prof) { const long long t = clock64(); a.prof[53] += static_cast<unsigned long long>(t - dt0); dt0 = t; }
     if (warp == 0) {  // x_i = (u_Ni - sum_{k>i} u_ki x_k) / d_i
-      for (int i = N - 1; i >= 0; --i) {
-        const double xi = rhs[i] * wd[i];
-        __syncwarp();
-        if (lane == 0) rhs[i] = xi;
-        for (int k = lane; k < i; k += 32) rhs[k] -= S[i * LD + k] * xi;
-        __syncwarp();
+      constexpr int kQ = 5;
+      if (N <= 32 * kQ) {
+        // the right-hand side lives in registers (entry k in lane k mod 32, slot k / 32): per step one shuffle, one
+        // multiply and the lanes' updates — no shared-memory round trip on the dependency chain
+        double r[kQ];
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) r[q] = 32 * q + lane < N ? rhs[32 * q + lane] : 0.0;
+#pragma unroll
+        for (int q = kQ - 1; q >= 0; --q) {
+          for (int l = 31; l >= 0; --l) {
+            const int i = 32 * q + l;
+            if (i >= N) continue;
+            const double xi = __shfl_sync(0xffffffffu, r[q], l) * wd[i];
+            if (lane == l) r[q] = xi;
+            const double* row = S + i * LD + lane;
+#pragma unroll
+            for (int qq = 0; qq <= q; ++qq)
+              if (32 * qq + lane < i) r[qq] -= row[32 * qq] * xi;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kQ; ++q)
+          if (32 * q + lane < N) rhs[32 * q + lane] = r[q];
+      } else {
+        for (int i = N - 1; i >= 0; --i) {
+          const double xi = rhs[i] * wd[i];
+          __syncwarp();
+          if (lane == 0) rhs[i] = xi;
+          for (int k = lane; k < i; k += 32) rhs[k] -= S[i * LD + k] * xi;
+          __syncwarp();
+        }
       }
     }
     __syncthreads();
